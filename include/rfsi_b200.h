@@ -1,0 +1,194 @@
+/*
+ * rfsi_b200.h -- C ABI of the B200-native RFSI prediction engine.
+ *
+ * The reference (AleksandarSekulic/RFSI) has no FFI of its own: its boundary for
+ * this path is the R call shapes near.obs(...) and predict(<ranger>, ...) (and the
+ * rfsi()/pred.rfsi() wrappers of README.md:93-143), which land in the CRAN
+ * packages meteo/nabor and ranger.  Each entry point below names the reference
+ * call it replaces; INTEGRATION.md shows the R-side .Call stub that binds it.
+ *
+ * Conventions
+ *  - plain C, caller-owned buffers, no ownership transfer except the forest handle;
+ *  - matrices are COLUMN-MAJOR (R's layout): column j of an npix x n matrix starts
+ *    at base + j*ld;
+ *  - missing values are R's: NA_real_ (NaN, payload 1954) and NA_integer_ (INT_MIN);
+ *  - every function returns 0 (RFSI_OK), a positive warning code, or a negative
+ *    RFSI_E_* error; rfsi_last_error() gives the thread-local message;
+ *  - there is NO CPU fallback: without an sm_100 device calls fail with
+ *    RFSI_E_NO_DEVICE;
+ *  - rfsi_*      : HOST pointers in, HOST pointers out (copies are inside the call);
+ *    rfsi_dev_*  : DEVICE pointers on `device`, enqueued on `stream` (a cudaStream_t
+ *                  passed as void*; NULL = the legacy default stream), asynchronous.
+ */
+#ifndef RFSI_B200_H
+#define RFSI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFSI_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+    RFSI_OK = 0,
+    RFSI_W_TOO_FEW_OBS = 1, /* some outputs were NA-filled: fewer stations than n.obs(+1) */
+    RFSI_E_CUDA = -1,
+    RFSI_E_NO_DEVICE = -2,
+    RFSI_E_ARG = -3,
+    RFSI_E_NA_INPUT = -4, /* NA/NaN coordinate, or NA in a feature column the forest uses */
+    RFSI_E_OOM = -5,
+    RFSI_E_FOREST = -6 /* malformed forest (child out of range, cycle, bad varID) */
+};
+
+/* feature-map codes for rfsi_predict_fused: which model column is what */
+#define RFSI_FEAT_COV(c) ((int32_t)(c))             /* external covariate column c      */
+#define RFSI_FEAT_DIST(j) ((int32_t)(0x10000 + (j))) /* dist{j+1}, j = 0..n_obs-1        */
+#define RFSI_FEAT_OBS(j) ((int32_t)(0x20000 + (j)))  /* obs{j+1},  j = 0..n_obs-1        */
+
+typedef struct rfsi_forest rfsi_forest_t;
+
+int rfsi_version(void);
+const char* rfsi_last_error(void);
+/* number of usable sm_100 devices (0 = none; negative = RFSI_E_*) */
+int rfsi_device_count(void);
+
+/* Pinned host memory for callers that want full-rate PCIe copies (optional). */
+int rfsi_host_alloc(void** out, size_t bytes);
+void rfsi_host_free(void* p);
+
+/* ---- stage 1 ------------------------------------------------------------------
+ * near.obs(locations, observations, zcol, n.obs): simulation/simulation.R:191-196,
+ * simulation/sim_500.R:134-139, temp_croatia/2_predictions.R:160-165,
+ * prcp_catalonia/5_prcp_prediction.R:278-283, temp_croatia/1_models.R:1040-1045.
+ * k = n_obs+1 exact nearest observation points under the total order (d2, index),
+ * zero-distance self match dropped when rm_dupl; out_dist/out_obs are npix x n_obs
+ * column-major (ld = npix) = the dist1..distN / obs1..obsN columns; out_idx
+ * (nullable) 1-based observation indices.  obs_z may hold NA (propagates to obs). */
+int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix,
+                      const double* obs_x, const double* obs_y, const double* obs_z,
+                      int32_t nobs, int32_t n_obs, int32_t rm_dupl,
+                      double* out_dist, double* out_obs, int32_t* out_idx, int device);
+
+int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix,
+                          const double* obs_x, const double* obs_y, const double* obs_z,
+                          int32_t nobs, int32_t n_obs, int32_t rm_dupl,
+                          double* out_dist, double* out_obs, int32_t* out_idx,
+                          int32_t* warn_flag /* device int, nullable */,
+                          int device, void* stream);
+
+/* ---- forest import --------------------------------------------------------------
+ * The ranger model object saved at temp_croatia/1_models.R:1056-1063 and loaded at
+ * temp_croatia/2_predictions.R:59 / prcp_catalonia/5_prcp_prediction.R:233, flattened
+ * (rfsi_import_ranger): trees concatenated, tree t owning nodes
+ * [node_offsets[t], node_offsets[t+1]); left/right = child.nodeIDs[[t]][[1]]/[[2]]
+ * (tree-local, 0-based, both 0 at a terminal node); split_var = split.varIDs[[t]]
+ * (0-based column of X, already re-based for old ranger objects); split_val =
+ * split.values[[t]] (threshold, or the prediction at a terminal node);
+ * random_node_values (nullable; needed for quantiles) with tree t's column starting
+ * at rnv_offsets[t] and indexed by tree-local node id. */
+int rfsi_forest_create(int32_t ntrees, const int64_t* node_offsets,
+                       const int32_t* left, const int32_t* right,
+                       const int32_t* split_var, const double* split_val,
+                       const int64_t* rnv_offsets, const double* random_node_values,
+                       int32_t nfeat, rfsi_forest_t** out);
+void rfsi_forest_destroy(rfsi_forest_t* f);
+/* push the device image of the forest to `device` now (otherwise done on first use) */
+int rfsi_forest_upload(const rfsi_forest_t* f, int device);
+/* info: 0 ntrees, 1 nfeat, 2 total nodes (device layout), 3 max depth, 4 has quantile
+ * samples, 5 device bytes, 6 total internal nodes */
+int64_t rfsi_forest_info(const rfsi_forest_t* f, int what);
+
+/* ---- stage 2 ------------------------------------------------------------------
+ * predict(<ranger>, df)$predictions: simulation/simulation.R:214,
+ * temp_croatia/2_predictions.R:167, prcp_catalonia/5_prcp_prediction.R:287.
+ * X is npix x nfeat column-major with leading dimension ldx, columns in the model's
+ * independent.variable.names order.  NA/NaN in X -> RFSI_E_NA_INPUT (ranger errors). */
+int rfsi_forest_predict(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
+                        double* out, int device);
+
+/* predict(<ranger quantreg=TRUE>, df, type="quantiles", quantiles=probs):
+ * temp_croatia/2_predictions.R:174-176, prcp_catalonia/5_prcp_prediction.R:289-291.
+ * out is npix x nprobs column-major. */
+int rfsi_forest_quantiles(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
+                          const double* probs, int32_t nprobs, double* out, int device);
+
+/* predict(type="terminalNodes"): npix x ntrees column-major tree-local node ids */
+int rfsi_forest_terminal_nodes(const rfsi_forest_t* f, const double* X, int64_t npix,
+                               int64_t ldx, int32_t* out, int device);
+
+/* device-pointer forms; any of out_mean / out_q / out_terminal may be NULL.
+ * scratch: device buffer of rfsi_dev_forest_scratch_bytes(f, npix, nprobs) bytes
+ * (only needed when out_q != NULL). visits (nullable, device uint64) accumulates the
+ * number of internal nodes visited (the roofline's algorithmic figure). */
+size_t rfsi_dev_forest_scratch_bytes(const rfsi_forest_t* f, int64_t npix, int32_t nprobs);
+int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
+                            double* out_mean, const double* probs_host, int32_t nprobs,
+                            double* out_q, int32_t* out_terminal, void* scratch,
+                            unsigned long long* visits, int32_t* na_flag,
+                            int device, void* stream);
+
+/* ---- fused stage 1 -> stage 2 over pixels x days ----------------------------------
+ * One call = what the mapping loops do per day (temp_croatia/2_predictions.R:73-183,
+ * prcp_catalonia/5_prcp_prediction.R:244-309): filter that day's stations
+ * (!is.na(value)), near.obs, cbind the covariates, predict mean and/or quantiles --
+ * for every day of the batch, without materialising the feature table. */
+typedef struct rfsi_fused_args {
+    size_t struct_size; /* = sizeof(rfsi_fused_args_t) */
+    /* prediction locations: explicit (loc_x/loc_y, npix) or, when loc_x == NULL, the
+     * raster cells [pix_begin, pix_begin+npix) of a row-major grid: cell p -> row
+     * p / grid_ncol, col p % grid_ncol, x = grid_x0 + col*grid_dx, y = grid_y0 + row*grid_dy */
+    const double* loc_x;
+    const double* loc_y;
+    int64_t npix;
+    double grid_x0, grid_y0, grid_dx, grid_dy;
+    int64_t grid_ncol;
+    int64_t pix_begin;
+    /* stations: coordinates (day-invariant) and the ndays x nobs table of observed
+     * values, row d = day d, NA/NaN = no observation that day */
+    const double* obs_x;
+    const double* obs_y;
+    int32_t nobs;
+    const double* obs_z;
+    int32_t ndays;
+    int32_t n_obs;
+    int32_t rm_dupl;
+    /* covariates: ncov columns; column c is cov[c][d*cov_day_stride[c] + p]
+     * (cov_day_stride 0 = static over days, npix = one layer per day) */
+    int32_t ncov;
+    const double* const* cov;
+    const int64_t* cov_day_stride;
+    /* model column f is feat_map[f] (RFSI_FEAT_COV / _DIST / _OBS) */
+    const int32_t* feat_map;
+    /* outputs (each nullable): mean[d*npix + p]; q[(j*ndays + d)*npix + p] */
+    const double* probs;
+    int32_t nprobs;
+    double* out_mean;
+    double* out_q;
+    /* product epilogue (nullable): round-half-even(mean*100) as Int16, NA -> -32767
+     * (5_prcp_prediction.R:288,303); iqr = round((q[last]-q[first])/2*100) */
+    int16_t* out_mean_i16;
+    int16_t* out_iqr_i16;
+    /* optional pixel validity mask (nullable): 0 = skip pixel, outputs NA / -32767 */
+    const uint8_t* pix_mask;
+} rfsi_fused_args_t;
+
+int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device);
+/* same with every pointer in `a` (except probs, feat_map, cov, cov_day_stride, which
+ * stay host arrays; cov[c] are device pointers) already on `device`.  workspace:
+ * rfsi_dev_fused_workspace_bytes() bytes of device memory.  counters (nullable):
+ * device uint64[4] = {internal nodes visited, pixel-days done, fallback pixel-days,
+ * too-few-obs pixel-days}. */
+size_t rfsi_dev_fused_workspace_bytes(const rfsi_forest_t* f, const rfsi_fused_args_t* a);
+int rfsi_dev_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, void* workspace,
+                           unsigned long long* counters, int device, void* stream);
+
+/* number of kernels this library has launched in this process (bench accounting) */
+uint64_t rfsi_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFSI_B200_H */

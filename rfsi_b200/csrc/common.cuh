@@ -1,0 +1,60 @@
+// common.cuh -- shared device/host definitions for the RFSI sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rfsi {
+
+// One forest node, 16 bytes, loaded with a single 128-bit access.
+//   internal: val = threshold, child = absolute index of the LEFT child (the right
+//             child is child+1: siblings share one 32-byte sector), feat >= 0
+//   leaf    : val = prediction, child = ranger's tree-local node id, feat = -1
+// (ranger layout, SURVEY.md 8a row a7: split.values holds the threshold or, at a
+// terminal node, the prediction.)
+struct __align__(16) Node {
+    double val;
+    int32_t child;
+    int32_t feat;
+};
+static_assert(sizeof(Node) == 16, "node record must be 16 bytes");
+
+constexpr int32_t kIdxNone = 0x7fffffff;        // empty slot of a neighbour list
+constexpr unsigned long long kNaRealBits = 0x7FF00000000007A2ULL;  // R NA_real_
+constexpr int32_t kNaInteger = INT32_MIN;                          // R NA_integer_
+
+__host__ __device__ __forceinline__ double na_real() {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)kNaRealBits);
+#else
+    union { unsigned long long u; double d; } v;
+    v.u = kNaRealBits;
+    return v.d;
+#endif
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ Node load_node(const Node* __restrict__ p) {
+    const int4 r = __ldg(reinterpret_cast<const int4*>(p));
+    Node n;
+    n.val = __hiloint2double(r.y, r.x);
+    n.child = r.z;
+    n.feat = r.w;
+    return n;
+}
+
+// squared distance exactly as the CPU does it without FMA contraction:
+// fl(fl(dx*dx) + fl(dy*dy)), x term first.
+__device__ __forceinline__ double dist2_rn(double px, double py, double sx, double sy) {
+    const double dx = __dsub_rn(px, sx);
+    const double dy = __dsub_rn(py, sy);
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
+}  // namespace rfsi

@@ -1,0 +1,958 @@
+// engine.cu -- host side of librfsi_b200.so: forest import, kernel launches, C ABI.
+// Entry points are declared (with the reference call each one replaces) in
+// include/rfsi_b200.h.  No CPU compute path exists in this library: without an
+// sm_100 device every compute call returns RFSI_E_NO_DEVICE.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rfsi_b200.h"
+#include "common.cuh"
+#include "forest.cuh"
+#include "fused.cuh"
+#include "knn.cuh"
+#include "qrf.cuh"
+
+using namespace rfsi;
+
+// ------------------------------------------------------------------------------------
+// errors, devices, options
+// ------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(e__ == cudaErrorMemoryAllocation ? RFSI_E_OOM : RFSI_E_CUDA,         \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,   \
+                        __LINE__);                                                           \
+    } while (0)
+
+#define RF_TRY(expr)              \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ < 0) return rc__; \
+    } while (0)
+
+int use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(RFSI_E_NO_DEVICE, "no CUDA device visible (%s); this library has no CPU path",
+                    e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(RFSI_E_NO_DEVICE, "device %d out of range [0,%d)", device, n);
+    int major = 0;
+    CU_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10)
+        return fail(RFSI_E_NO_DEVICE, "device %d is sm_%d0, this build is sm_100a only", device, major);
+    CU_TRY(cudaSetDevice(device));
+    return RFSI_OK;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        if (p) { cudaFree(p); p = nullptr; }
+        CU_TRY(cudaMalloc(&p, bytes ? bytes : 1));
+        return RFSI_OK;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Stream {
+    cudaStream_t s = nullptr;
+    ~Stream() { if (s) cudaStreamDestroy(s); }
+    int create() { CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return RFSI_OK; }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// forest: import ranger layout -> device layout
+// ------------------------------------------------------------------------------------
+struct rfsi_forest {
+    int32_t ntrees = 0, nfeat = 0;
+    std::vector<Node> nodes;          // device layout, host copy
+    std::vector<double> leaf_sample;  // per device node (empty when no quantile samples)
+    int max_depth = 0;
+    int64_t n_internal = 0;
+    struct Image { Node* nodes = nullptr; double* leaf_sample = nullptr; };
+    mutable std::mutex mu;
+    mutable std::map<int, Image> images;
+};
+
+namespace {
+
+int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
+    std::lock_guard<std::mutex> lk(f->mu);
+    auto it = f->images.find(device);
+    if (it != f->images.end()) { *out = it->second; return RFSI_OK; }
+    rfsi_forest::Image im;
+    CU_TRY(cudaMalloc(&im.nodes, f->nodes.size() * sizeof(Node)));
+    CU_TRY(cudaMemcpy(im.nodes, f->nodes.data(), f->nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
+    if (!f->leaf_sample.empty()) {
+        CU_TRY(cudaMalloc(&im.leaf_sample, f->leaf_sample.size() * sizeof(double)));
+        CU_TRY(cudaMemcpy(im.leaf_sample, f->leaf_sample.data(), f->leaf_sample.size() * sizeof(double),
+                          cudaMemcpyHostToDevice));
+    }
+    f->images[device] = im;
+    *out = im;
+    return RFSI_OK;
+}
+
+}  // namespace
+
+extern "C" int rfsi_forest_create(int32_t ntrees, const int64_t* node_offsets, const int32_t* left,
+                                  const int32_t* right, const int32_t* split_var, const double* split_val,
+                                  const int64_t* rnv_offsets, const double* rnv, int32_t nfeat,
+                                  rfsi_forest_t** out)
+{
+    if (!out) return fail(RFSI_E_ARG, "out is NULL");
+    *out = nullptr;
+    if (ntrees < 1 || nfeat < 1 || !node_offsets || !left || !right || !split_var || !split_val)
+        return fail(RFSI_E_ARG, "forest_create: ntrees/nfeat must be >= 1 and arrays non-NULL");
+    if ((rnv == nullptr) != (rnv_offsets == nullptr))
+        return fail(RFSI_E_ARG, "forest_create: random_node_values and rnv_offsets go together");
+    if (nfeat > 32767) return fail(RFSI_E_ARG, "forest_create: nfeat %d > 32767 unsupported", nfeat);
+
+    auto* f = new rfsi_forest();
+    f->ntrees = ntrees;
+    f->nfeat = nfeat;
+    const int64_t roots = (ntrees + 1) & ~int64_t(1);  // roots first, padded so pairs start even
+    int64_t total = roots;
+    for (int32_t t = 0; t < ntrees; ++t) {
+        const int64_t n = node_offsets[t + 1] - node_offsets[t];
+        if (n < 1) { delete f; return fail(RFSI_E_FOREST, "tree %d has no nodes", t); }
+        total += n;  // upper bound: unreachable nodes are dropped
+    }
+    if (total >= (int64_t)0x7fffffff) { delete f; return fail(RFSI_E_FOREST, "forest has >= 2^31 nodes"); }
+    f->nodes.assign((size_t)total, Node{0.0, 0, -1});
+    if (rnv) f->leaf_sample.assign((size_t)total, na_real());
+
+    struct Item { int32_t rid; int32_t slot; int32_t depth; };
+    std::vector<Item> queue;
+    int64_t next = roots;
+    for (int32_t t = 0; t < ntrees; ++t) {
+        const int64_t o = node_offsets[t];
+        const int64_t n = node_offsets[t + 1] - o;
+        queue.clear();
+        queue.push_back({0, t, 0});
+        size_t head = 0;
+        while (head < queue.size()) {
+            const Item it = queue[head++];
+            if ((int64_t)queue.size() > n) {
+                delete f;
+                return fail(RFSI_E_FOREST, "tree %d: a node is reachable twice (cycle or shared child)", t);
+            }
+            const int32_t l = left[o + it.rid], r = right[o + it.rid];
+            f->max_depth = std::max(f->max_depth, it.depth);
+            if (l == 0 && r == 0) {
+                f->nodes[it.slot] = Node{split_val[o + it.rid], it.rid, -1};
+                if (rnv) f->leaf_sample[it.slot] = rnv[rnv_offsets[t] + it.rid];
+            } else {
+                if (l <= 0 || l >= n || r <= 0 || r >= n) {
+                    delete f;
+                    return fail(RFSI_E_FOREST, "tree %d node %d: child id out of range", t, it.rid);
+                }
+                const int32_t v = split_var[o + it.rid];
+                if (v < 0 || v >= nfeat) {
+                    delete f;
+                    return fail(RFSI_E_FOREST, "tree %d node %d: split variable %d outside [0,%d)", t, it.rid, v, nfeat);
+                }
+                f->nodes[it.slot] = Node{split_val[o + it.rid], (int32_t)next, v};
+                queue.push_back({l, (int32_t)next, it.depth + 1});
+                queue.push_back({r, (int32_t)next + 1, it.depth + 1});
+                next += 2;
+                ++f->n_internal;
+            }
+        }
+    }
+    f->nodes.resize((size_t)next);
+    if (rnv) f->leaf_sample.resize((size_t)next);
+    *out = f;
+    return RFSI_OK;
+}
+
+extern "C" void rfsi_forest_destroy(rfsi_forest_t* f) {
+    if (!f) return;
+    for (auto& kv : f->images) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cudaSetDevice(kv.first) == cudaSuccess) {
+            if (kv.second.nodes) cudaFree(kv.second.nodes);
+            if (kv.second.leaf_sample) cudaFree(kv.second.leaf_sample);
+        }
+        cudaSetDevice(cur);
+    }
+    delete f;
+}
+
+extern "C" int rfsi_forest_upload(const rfsi_forest_t* f, int device) {
+    if (!f) return fail(RFSI_E_ARG, "forest is NULL");
+    RF_TRY(use_device(device));
+    rfsi_forest::Image im;
+    return forest_image(f, device, &im);
+}
+
+extern "C" int64_t rfsi_forest_info(const rfsi_forest_t* f, int what) {
+    if (!f) return -1;
+    switch (what) {
+        case 0: return f->ntrees;
+        case 1: return f->nfeat;
+        case 2: return (int64_t)f->nodes.size();
+        case 3: return f->max_depth;
+        case 4: return f->leaf_sample.empty() ? 0 : 1;
+        case 5: return (int64_t)(f->nodes.size() * sizeof(Node) + f->leaf_sample.size() * sizeof(double));
+        case 6: return f->n_internal;
+        default: return -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// misc entry points
+// ------------------------------------------------------------------------------------
+extern "C" int rfsi_version(void) { return RFSI_B200_VERSION; }
+extern "C" const char* rfsi_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t rfsi_launch_count(void) { return g_launches.load(); }
+
+extern "C" int rfsi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+extern "C" int rfsi_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail(RFSI_E_ARG, "out is NULL");
+    CU_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+    return RFSI_OK;
+}
+extern "C" void rfsi_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------
+namespace {
+
+__global__ void interleave_xy_kernel(const double* __restrict__ x, const double* __restrict__ y, int n,
+                                     double2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(x[i], y[i]);
+}
+
+constexpr int kKnnP = 128;
+
+template <int MODE>
+int launch_knn(const LocSpec& L, int64_t npix, const double2* st_xy, int S, int k, const double* st_z,
+               int rm_dupl, double* out_a, double* out_b, int32_t* out_i, int64_t ld, int* warn, int* na_flag,
+               cudaStream_t stream)
+{
+    if (npix == 0) return RFSI_OK;
+    const size_t smem = knn_smem_bytes<kKnnP>(k);
+    if (smem > 227 * 1024) return fail(RFSI_E_ARG, "n.obs = %d needs %zu B of shared memory (> 227 KB)", k - 1, smem);
+    auto kern = knn_brute_kernel<kKnnP, MODE>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((npix + kKnnP - 1) / kKnnP);
+    kern<<<grid, kKnnP, smem, stream>>>(L, npix, st_xy, S, k, st_z, rm_dupl, out_a, out_b, out_i, ld, warn, na_flag);
+    count_launch();
+    CU_TRY(cudaGetLastError());
+    return RFSI_OK;
+}
+
+int forest_J() {
+    static int j = env_int("RFSI_B200_J", 4);
+    return j;
+}
+
+template <int P, int J>
+int launch_forest_x_pj(const Node* nodes, int T, int F, const double* X, int64_t npix, int64_t ldx,
+                       const ForestOut& o, unsigned long long* visits, int* na_flag, cudaStream_t stream)
+{
+    const size_t smem = forest_smem_bytes<P>(F);
+    const unsigned grid = (unsigned)((npix + P - 1) / P);
+    if (visits) {
+        auto kern = forest_x_kernel<P, J, true>;
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, P, smem, stream>>>(nodes, T, F, X, npix, ldx, o, visits, na_flag);
+    } else {
+        auto kern = forest_x_kernel<P, J, false>;
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, P, smem, stream>>>(nodes, T, F, X, npix, ldx, o, visits, na_flag);
+    }
+    count_launch();
+    CU_TRY(cudaGetLastError());
+    return RFSI_OK;
+}
+
+int launch_forest_x(const Node* nodes, int T, int F, const double* X, int64_t npix, int64_t ldx,
+                    const ForestOut& o, unsigned long long* visits, int* na_flag, cudaStream_t stream)
+{
+    if (npix == 0) return RFSI_OK;
+    const bool big = forest_smem_bytes<256>(F) <= 100 * 1024;
+    if (!big && forest_smem_bytes<128>(F) > 227 * 1024)
+        return fail(RFSI_E_ARG, "forest with %d features exceeds the shared-memory feature tile (max %d)", F,
+                    227 * 1024 / (128 * 8));
+    const int J = forest_J();
+    if (big) {
+        if (J >= 8) return launch_forest_x_pj<256, 8>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
+        if (J <= 2) return launch_forest_x_pj<256, 2>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
+        return launch_forest_x_pj<256, 4>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
+    }
+    if (J >= 8) return launch_forest_x_pj<128, 8>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
+    if (J <= 2) return launch_forest_x_pj<128, 2>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
+    return launch_forest_x_pj<128, 4>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
+}
+
+constexpr int kMaxProbs = 128;
+
+int launch_qrf(const double* samples, const unsigned char* skip, int64_t nrows, int T, const double* probs_dev,
+               int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr, cudaStream_t stream)
+{
+    if (nrows == 0) return RFSI_OK;
+    const unsigned grid = (unsigned)((nrows + 7) / 8);
+    const int R = (T + 31) / 32;
+#define RFSI_QRF_CASE(RR)                                                                            \
+    qrf_quantile_kernel<RR><<<grid, 256, 0, stream>>>(samples, skip, nrows, T, probs_dev, nprobs, out_q, \
+                                                      ld_q, out_iqr)
+    if (R <= 1) RFSI_QRF_CASE(1);
+    else if (R <= 2) RFSI_QRF_CASE(2);
+    else if (R <= 4) RFSI_QRF_CASE(4);
+    else if (R <= 8) RFSI_QRF_CASE(8);
+    else if (R <= 16) RFSI_QRF_CASE(16);
+    else if (R <= 32) RFSI_QRF_CASE(32);
+    else return fail(RFSI_E_ARG, "quantile forests with more than 1024 trees are not supported (T=%d)", T);
+#undef RFSI_QRF_CASE
+    count_launch();
+    CU_TRY(cudaGetLastError());
+    return RFSI_OK;
+}
+
+int check_probs(const double* probs, int nprobs) {
+    if (nprobs < 1 || nprobs > kMaxProbs || !probs) return fail(RFSI_E_ARG, "need 1..%d quantiles", kMaxProbs);
+    for (int i = 0; i < nprobs; ++i)
+        if (!(probs[i] >= 0.0 && probs[i] <= 1.0)) return fail(RFSI_E_ARG, "quantile %g outside [0,1]", probs[i]);
+    return RFSI_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// stage 1 API
+// ------------------------------------------------------------------------------------
+extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix,
+                                     const double* obs_x, const double* obs_y, const double* obs_z,
+                                     int32_t nobs, int32_t n_obs, int32_t rm_dupl, double* out_dist,
+                                     double* out_obs, int32_t* out_idx, int32_t* warn_flag, int device,
+                                     void* stream)
+{
+    if (npix < 0 || nobs < 0 || n_obs < 1) return fail(RFSI_E_ARG, "near_obs: bad sizes");
+    RF_TRY(use_device(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // interleave the station coordinates so one 128-bit broadcast feeds a distance
+    double2* xy = nullptr;
+    CU_TRY(cudaMallocAsync(&xy, sizeof(double2) * (size_t)std::max(nobs, 1), st));
+    if (nobs > 0) {
+        interleave_xy_kernel<<<(nobs + 255) / 256, 256, 0, st>>>(obs_x, obs_y, nobs, xy);
+        count_launch();
+    }
+    LocSpec L{loc_x, loc_y, 0, 0, 0, 0, 1, 0};
+    int rc = launch_knn<KNN_FINAL>(L, npix, xy, nobs, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx, npix,
+                                   warn_flag, nullptr, st);
+    cudaFreeAsync(xy, st);
+    return rc;
+}
+
+extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix, const double* obs_x,
+                                 const double* obs_y, const double* obs_z, int32_t nobs, int32_t n_obs,
+                                 int32_t rm_dupl, double* out_dist, double* out_obs, int32_t* out_idx, int device)
+{
+    if (npix < 0 || nobs < 0 || n_obs < 1) return fail(RFSI_E_ARG, "near_obs: npix/nobs must be >= 0, n.obs >= 1");
+    if (npix > 0 && (!loc_x || !loc_y || !out_dist || !out_obs)) return fail(RFSI_E_ARG, "near_obs: NULL buffer");
+    if (nobs > 0 && (!obs_x || !obs_y || !obs_z)) return fail(RFSI_E_ARG, "near_obs: NULL observations");
+    for (int32_t s = 0; s < nobs; ++s)
+        if (obs_x[s] != obs_x[s] || obs_y[s] != obs_y[s])
+            return fail(RFSI_E_NA_INPUT, "near_obs: observation %d has an NA coordinate", s + 1);
+    RF_TRY(use_device(device));
+    if (npix == 0) return RFSI_OK;
+
+    std::vector<double2> xy((size_t)std::max(nobs, 1));
+    for (int32_t s = 0; s < nobs; ++s) xy[s] = make_double2(obs_x[s], obs_y[s]);
+    DevBuf d_xy, d_z, d_flags;
+    RF_TRY(d_xy.alloc(sizeof(double2) * xy.size()));
+    RF_TRY(d_z.alloc(sizeof(double) * (size_t)std::max(nobs, 1)));
+    RF_TRY(d_flags.alloc(2 * sizeof(int)));
+    CU_TRY(cudaMemcpy(d_xy.p, xy.data(), sizeof(double2) * xy.size(), cudaMemcpyHostToDevice));
+    if (nobs > 0) CU_TRY(cudaMemcpy(d_z.p, obs_z, sizeof(double) * nobs, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemset(d_flags.p, 0, 2 * sizeof(int)));
+
+    const int64_t chunk = std::min<int64_t>(npix, 1 << 20);
+    Stream st[2];
+    DevBuf d_lx[2], d_ly[2], d_dist[2], d_obs[2], d_idx[2];
+    for (int s = 0; s < 2; ++s) {
+        RF_TRY(st[s].create());
+        RF_TRY(d_lx[s].alloc(sizeof(double) * chunk));
+        RF_TRY(d_ly[s].alloc(sizeof(double) * chunk));
+        RF_TRY(d_dist[s].alloc(sizeof(double) * chunk * n_obs));
+        RF_TRY(d_obs[s].alloc(sizeof(double) * chunk * n_obs));
+        if (out_idx) RF_TRY(d_idx[s].alloc(sizeof(int32_t) * chunk * n_obs));
+        if (npix <= chunk) break;
+    }
+    int slot = 0;
+    for (int64_t p0 = 0; p0 < npix; p0 += chunk, slot ^= 1) {
+        const int64_t cur = std::min(chunk, npix - p0);
+        cudaStream_t s = st[slot].s;
+        CU_TRY(cudaMemcpyAsync(d_lx[slot].p, loc_x + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(d_ly[slot].p, loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+        LocSpec L{d_lx[slot].as<double>(), d_ly[slot].as<double>(), 0, 0, 0, 0, 1, 0};
+        RF_TRY(launch_knn<KNN_FINAL>(L, cur, d_xy.as<double2>(), nobs, n_obs + 1, d_z.as<double>(), rm_dupl,
+                                     d_dist[slot].as<double>(), d_obs[slot].as<double>(),
+                                     out_idx ? d_idx[slot].as<int32_t>() : nullptr, cur, d_flags.as<int>(),
+                                     d_flags.as<int>() + 1, s));
+        CU_TRY(cudaMemcpy2DAsync(out_dist + p0, sizeof(double) * npix, d_dist[slot].p, sizeof(double) * cur,
+                                 sizeof(double) * cur, n_obs, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpy2DAsync(out_obs + p0, sizeof(double) * npix, d_obs[slot].p, sizeof(double) * cur,
+                                 sizeof(double) * cur, n_obs, cudaMemcpyDeviceToHost, s));
+        if (out_idx)
+            CU_TRY(cudaMemcpy2DAsync(out_idx + p0, sizeof(int32_t) * npix, d_idx[slot].p, sizeof(int32_t) * cur,
+                                     sizeof(int32_t) * cur, n_obs, cudaMemcpyDeviceToHost, s));
+    }
+    for (int s = 0; s < 2; ++s)
+        if (st[s].s) CU_TRY(cudaStreamSynchronize(st[s].s));
+    int flags[2] = {0, 0};
+    CU_TRY(cudaMemcpy(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost));
+    if (flags[1]) return fail(RFSI_E_NA_INPUT, "near_obs: a location has an NA coordinate");
+    if (flags[0]) {
+        g_err = "near_obs: fewer observations than n.obs(+1); missing neighbours are NA";
+        return RFSI_W_TOO_FEW_OBS;
+    }
+    return RFSI_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// stage 2 API
+// ------------------------------------------------------------------------------------
+extern "C" size_t rfsi_dev_forest_scratch_bytes(const rfsi_forest_t* f, int64_t npix, int32_t nprobs) {
+    if (!f || npix <= 0 || nprobs <= 0) return 256;
+    return align_up(sizeof(double) * (size_t)npix * f->ntrees, 256) + align_up(sizeof(double) * kMaxProbs, 256);
+}
+
+extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
+                                       double* out_mean, const double* probs_host, int32_t nprobs, double* out_q,
+                                       int32_t* out_terminal, void* scratch, unsigned long long* visits,
+                                       int32_t* na_flag, int device, void* stream)
+{
+    if (!f) return fail(RFSI_E_ARG, "forest is NULL");
+    if (npix < 0 || ldx < npix) return fail(RFSI_E_ARG, "predict: need 0 <= npix <= ldx");
+    RF_TRY(use_device(device));
+    rfsi_forest::Image im;
+    RF_TRY(forest_image(f, device, &im));
+    cudaStream_t st = (cudaStream_t)stream;
+    ForestOut o{out_mean, nullptr, im.leaf_sample, out_terminal, npix};
+    double* probs_dev = nullptr;
+    if (out_q) {
+        if (!im.leaf_sample) return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
+        RF_TRY(check_probs(probs_host, nprobs));
+        if (!scratch) return fail(RFSI_E_ARG, "quantiles need a scratch buffer");
+        o.samples = reinterpret_cast<double*>(scratch);
+        probs_dev = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) +
+                                              align_up(sizeof(double) * (size_t)npix * f->ntrees, 256));
+        CU_TRY(cudaMemcpyAsync(probs_dev, probs_host, sizeof(double) * nprobs, cudaMemcpyHostToDevice, st));
+    }
+    RF_TRY(launch_forest_x(im.nodes, f->ntrees, f->nfeat, X, npix, ldx, o, visits, na_flag, st));
+    if (out_q) RF_TRY(launch_qrf(o.samples, nullptr, npix, f->ntrees, probs_dev, nprobs, out_q, npix, nullptr, st));
+    return RFSI_OK;
+}
+
+namespace {
+
+// host-buffer driver shared by predict / quantiles / terminalNodes
+int host_forest(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx, double* out_mean,
+                const double* probs, int nprobs, double* out_q, int32_t* out_term, int device)
+{
+    if (!f) return fail(RFSI_E_ARG, "forest is NULL");
+    if (npix < 0 || ldx < npix) return fail(RFSI_E_ARG, "predict: need 0 <= npix <= ldx");
+    if (npix > 0 && !X) return fail(RFSI_E_ARG, "predict: X is NULL");
+    if (out_q) RF_TRY(check_probs(probs, nprobs));
+    RF_TRY(use_device(device));
+    if (npix == 0) return RFSI_OK;
+    rfsi_forest::Image im;
+    RF_TRY(forest_image(f, device, &im));
+    const int F = f->nfeat, T = f->ntrees;
+    // rows per chunk: bound the X tile (and the quantile scratch) to ~256 MB
+    int64_t chunk = std::max<int64_t>(4096, (int64_t(256) << 20) / (8 * (int64_t)F));
+    if (out_q) chunk = std::min(chunk, std::max<int64_t>(4096, (int64_t(512) << 20) / (8 * (int64_t)T)));
+    chunk = std::min<int64_t>(npix, chunk / 256 * 256);
+    DevBuf d_flag;
+    RF_TRY(d_flag.alloc(sizeof(int)));
+    CU_TRY(cudaMemset(d_flag.p, 0, sizeof(int)));
+    Stream st[2];
+    DevBuf d_X[2], d_mean[2], d_q[2], d_term[2], d_scr[2];
+    for (int s = 0; s < 2; ++s) {
+        RF_TRY(st[s].create());
+        RF_TRY(d_X[s].alloc(sizeof(double) * chunk * F));
+        if (out_mean) RF_TRY(d_mean[s].alloc(sizeof(double) * chunk));
+        if (out_q) {
+            RF_TRY(d_q[s].alloc(sizeof(double) * chunk * nprobs));
+            RF_TRY(d_scr[s].alloc(rfsi_dev_forest_scratch_bytes(f, chunk, nprobs)));
+        }
+        if (out_term) RF_TRY(d_term[s].alloc(sizeof(int32_t) * chunk * T));
+        if (npix <= chunk) break;
+    }
+    int slot = 0;
+    for (int64_t p0 = 0; p0 < npix; p0 += chunk, slot ^= 1) {
+        const int64_t cur = std::min(chunk, npix - p0);
+        cudaStream_t s = st[slot].s;
+        CU_TRY(cudaMemcpy2DAsync(d_X[slot].p, sizeof(double) * cur, X + p0, sizeof(double) * ldx,
+                                 sizeof(double) * cur, F, cudaMemcpyHostToDevice, s));
+        RF_TRY(rfsi_dev_forest_predict(f, d_X[slot].as<double>(), cur, cur, out_mean ? d_mean[slot].as<double>() : nullptr,
+                                       probs, nprobs, out_q ? d_q[slot].as<double>() : nullptr,
+                                       out_term ? d_term[slot].as<int32_t>() : nullptr, d_scr[slot].p, nullptr,
+                                       d_flag.as<int>(), device, s));
+        if (out_mean)
+            CU_TRY(cudaMemcpyAsync(out_mean + p0, d_mean[slot].p, sizeof(double) * cur, cudaMemcpyDeviceToHost, s));
+        if (out_q)
+            CU_TRY(cudaMemcpy2DAsync(out_q + p0, sizeof(double) * npix, d_q[slot].p, sizeof(double) * cur,
+                                     sizeof(double) * cur, nprobs, cudaMemcpyDeviceToHost, s));
+        if (out_term)
+            CU_TRY(cudaMemcpy2DAsync(out_term + p0, sizeof(int32_t) * npix, d_term[slot].p, sizeof(int32_t) * cur,
+                                     sizeof(int32_t) * cur, T, cudaMemcpyDeviceToHost, s));
+    }
+    for (int s = 0; s < 2; ++s)
+        if (st[s].s) CU_TRY(cudaStreamSynchronize(st[s].s));
+    int flag = 0;
+    CU_TRY(cudaMemcpy(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) return fail(RFSI_E_NA_INPUT, "predict: missing data in a column the forest uses");
+    return RFSI_OK;
+}
+
+}  // namespace
+
+extern "C" int rfsi_forest_predict(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
+                                   double* out, int device) {
+    if (npix > 0 && !out) return fail(RFSI_E_ARG, "predict: out is NULL");
+    return host_forest(f, X, npix, ldx, out, nullptr, 0, nullptr, nullptr, device);
+}
+
+extern "C" int rfsi_forest_quantiles(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
+                                     const double* probs, int32_t nprobs, double* out, int device) {
+    if (npix > 0 && !out) return fail(RFSI_E_ARG, "quantiles: out is NULL");
+    if (f && f->leaf_sample.empty())
+        return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
+    return host_forest(f, X, npix, ldx, nullptr, probs, nprobs, out, nullptr, device);
+}
+
+extern "C" int rfsi_forest_terminal_nodes(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
+                                          int32_t* out, int device) {
+    if (npix > 0 && !out) return fail(RFSI_E_ARG, "terminal_nodes: out is NULL");
+    return host_forest(f, X, npix, ldx, nullptr, nullptr, 0, nullptr, out, device);
+}
+
+// ------------------------------------------------------------------------------------
+// fused API
+// ------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kFusedP = 256;
+constexpr int kFallbackP = 128;
+
+struct FusedPlan {
+    int KC = 0;
+    int db = 1;               // days per launch
+    int64_t rows = 0;         // npix * db
+    bool want_q = false;
+    // workspace offsets
+    size_t off_cand_d2 = 0, off_cand_id = 0, off_xy = 0, off_fb = 0, off_misc = 0, off_samples = 0, off_skip = 0,
+           off_probs = 0, total = 0;
+};
+
+int validate_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
+    if (!f || !a) return fail(RFSI_E_ARG, "fused: NULL forest or args");
+    if (a->struct_size != sizeof(rfsi_fused_args_t))
+        return fail(RFSI_E_ARG, "fused: struct_size %zu != %zu (header/library mismatch)", a->struct_size,
+                    sizeof(rfsi_fused_args_t));
+    if (a->npix < 0 || a->nobs < 0 || a->ndays < 1) return fail(RFSI_E_ARG, "fused: bad npix/nobs/ndays");
+    if (a->n_obs < 1 || a->n_obs > kMaxNObs) return fail(RFSI_E_ARG, "fused: n.obs must be in 1..%d", kMaxNObs);
+    if (a->ncov < 0 || a->ncov > kMaxCov) return fail(RFSI_E_ARG, "fused: at most %d covariates", kMaxCov);
+    if (!a->feat_map) return fail(RFSI_E_ARG, "fused: feat_map is NULL");
+    if (!a->loc_x && (a->grid_ncol < 1)) return fail(RFSI_E_ARG, "fused: raster form needs grid_ncol >= 1");
+    if ((a->loc_x == nullptr) != (a->loc_y == nullptr)) return fail(RFSI_E_ARG, "fused: loc_x/loc_y go together");
+    if (a->nobs > 0 && (!a->obs_x || !a->obs_y || !a->obs_z)) return fail(RFSI_E_ARG, "fused: NULL stations");
+    if (a->npix > (int64_t)0x7ffffff0) return fail(RFSI_E_ARG, "fused: at most 2^31 pixels per call; band the raster");
+    for (int fidx = 0; fidx < f->nfeat; ++fidx) {
+        const int32_t c = a->feat_map[fidx];
+        const bool ok = (c >= 0 && c < a->ncov) || (c >= 0x10000 && c < 0x10000 + a->n_obs) ||
+                        (c >= 0x20000 && c < 0x20000 + a->n_obs);
+        if (!ok) return fail(RFSI_E_ARG, "fused: feat_map[%d] = 0x%x is not a covariate/dist/obs code", fidx, c);
+    }
+    if ((a->out_q || a->out_iqr_i16)) {
+        RF_TRY(check_probs(a->probs, a->nprobs));
+        if (f->leaf_sample.empty())
+            return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
+    }
+    if (forest_smem_bytes<kFusedP>(f->nfeat) > 100 * 1024 &&
+        fused_smem_bytes<kFallbackP>(f->nfeat, a->n_obs + 1, true) > 227 * 1024)
+        return fail(RFSI_E_ARG, "fused: %d features exceed the shared-memory feature tile", f->nfeat);
+    return RFSI_OK;
+}
+
+FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_extra) {
+    FusedPlan pl;
+    const int k = a->n_obs + 1;
+    pl.KC = std::max(1, std::min<int>(std::max(a->nobs, 1), k + std::max(0, kc_extra)));
+    pl.want_q = a->out_q || a->out_iqr_i16;
+    const int64_t npix = std::max<int64_t>(a->npix, 1);
+    int db = std::min(a->ndays, 16);
+    if (pl.want_q) {
+        const int64_t per_day = npix * f->ntrees * 8;
+        db = (int)std::max<int64_t>(1, std::min<int64_t>(db, (int64_t(1) << 30) / per_day));
+    }
+    // keep the 1-D grid below 2^31 CTAs
+    while (db > 1 && ((npix + kFusedP - 1) / kFusedP + 64) * db > (int64_t)0x7fffffff) --db;
+    pl.db = db;
+    pl.rows = npix * db;
+    size_t o = 0;
+    pl.off_cand_d2 = o; o += align_up(sizeof(double) * (size_t)pl.KC * npix, 256);
+    pl.off_cand_id = o; o += align_up(sizeof(int32_t) * (size_t)pl.KC * npix, 256);
+    pl.off_xy = o; o += align_up(sizeof(double2) * (size_t)std::max(a->nobs, 1), 256);
+    pl.off_fb = o; o += align_up(sizeof(int2) * (size_t)pl.rows, 256);
+    pl.off_misc = o; o += 256;  // fb_count, na_flag
+    pl.off_probs = o; o += align_up(sizeof(double) * kMaxProbs, 256);
+    if (pl.want_q) {
+        pl.off_samples = o; o += align_up(sizeof(double) * (size_t)pl.rows * f->ntrees, 256);
+        pl.off_skip = o; o += align_up((size_t)pl.rows, 256);
+    }
+    pl.total = o;
+    return pl;
+}
+
+int kc_extra_default() {
+    static int v = env_int("RFSI_B200_KC_EXTRA", 11);
+    return v;
+}
+
+template <int P, int J, bool FALLBACK>
+int launch_fused_pj(const FusedParams& fp, unsigned grid, size_t smem, bool count, cudaStream_t st) {
+    if (count) {
+        auto kern = fused_kernel<P, J, true, FALLBACK>;
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, P, smem, st>>>(fp);
+    } else {
+        auto kern = fused_kernel<P, J, false, FALLBACK>;
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, P, smem, st>>>(fp);
+    }
+    count_launch();
+    CU_TRY(cudaGetLastError());
+    return RFSI_OK;
+}
+
+template <int P, bool FALLBACK>
+int launch_fused_p(const FusedParams& fp, unsigned grid, size_t smem, bool count, cudaStream_t st) {
+    const int J = forest_J();
+    if (J >= 8) return launch_fused_pj<P, 8, FALLBACK>(fp, grid, smem, count, st);
+    if (J <= 2) return launch_fused_pj<P, 2, FALLBACK>(fp, grid, smem, count, st);
+    return launch_fused_pj<P, 4, FALLBACK>(fp, grid, smem, count, st);
+}
+
+// One pixel chunk, all days, everything already on the device.
+int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPlan& pl, void* workspace,
+              unsigned long long* counters, int device, cudaStream_t st, bool reuse_candidates)
+{
+    rfsi_forest::Image im;
+    RF_TRY(forest_image(f, device, &im));
+    if (a->npix == 0) return RFSI_OK;
+    char* ws = reinterpret_cast<char*>(workspace);
+    double* cand_d2 = reinterpret_cast<double*>(ws + pl.off_cand_d2);
+    int32_t* cand_id = reinterpret_cast<int32_t*>(ws + pl.off_cand_id);
+    double2* xy = reinterpret_cast<double2*>(ws + pl.off_xy);
+    int2* fb = reinterpret_cast<int2*>(ws + pl.off_fb);
+    unsigned int* fb_count = reinterpret_cast<unsigned int*>(ws + pl.off_misc);
+    int* na_flag = reinterpret_cast<int*>(ws + pl.off_misc + 16);
+    double* probs_dev = reinterpret_cast<double*>(ws + pl.off_probs);
+    double* samples = pl.want_q ? reinterpret_cast<double*>(ws + pl.off_samples) : nullptr;
+    unsigned char* skip = pl.want_q ? reinterpret_cast<unsigned char*>(ws + pl.off_skip) : nullptr;
+
+    LocSpec L{a->loc_x, a->loc_y, a->grid_x0, a->grid_y0, a->grid_dx, a->grid_dy,
+              a->loc_x ? 1 : a->grid_ncol, a->loc_x ? 0 : a->pix_begin};
+    if (!reuse_candidates) {
+        if (a->nobs > 0) {
+            interleave_xy_kernel<<<(a->nobs + 255) / 256, 256, 0, st>>>(a->obs_x, a->obs_y, a->nobs, xy);
+            count_launch();
+        }
+        // geometry pass: the KC nearest of ALL stations, once per pixel
+        RF_TRY(launch_knn<KNN_RAW>(L, a->npix, xy, a->nobs, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id, a->npix,
+                                   nullptr, nullptr, st));
+    }
+    if (pl.want_q)
+        CU_TRY(cudaMemcpyAsync(probs_dev, a->probs, sizeof(double) * a->nprobs, cudaMemcpyHostToDevice, st));
+
+    FusedParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.loc = L;
+    fp.npix = a->npix;
+    fp.cand_d2 = cand_d2; fp.cand_id = cand_id; fp.ld_cand = a->npix; fp.KC = pl.KC;
+    fp.exhaustive = pl.KC >= a->nobs;
+    fp.st_xy = xy; fp.obs_z = a->obs_z; fp.S = a->nobs;
+    fp.n_obs = a->n_obs; fp.rm_dupl = a->rm_dupl;
+    fp.ncov = a->ncov;
+    for (int c = 0; c < kMaxCov; ++c) fp.cov_row[c] = -1;
+    for (int j = 0; j < kMaxNObs; ++j) { fp.dist_row[j] = -1; fp.obs_row[j] = -1; }
+    for (int c = 0; c < a->ncov; ++c) { fp.cov[c] = a->cov[c]; fp.cov_stride[c] = a->cov_day_stride[c]; }
+    for (int fi = 0; fi < f->nfeat; ++fi) {
+        const int32_t code = a->feat_map[fi];
+        if (code >= 0x20000) fp.obs_row[code - 0x20000] = (short)fi;
+        else if (code >= 0x10000) fp.dist_row[code - 0x10000] = (short)fi;
+        else fp.cov_row[code] = (short)fi;  // a covariate feeds one model column
+    }
+    fp.pix_mask = a->pix_mask;
+    fp.nodes = im.nodes; fp.leaf_sample = im.leaf_sample; fp.T = f->ntrees; fp.F = f->nfeat;
+    fp.fb_list = fb; fp.fb_count = fb_count; fp.fb_capacity = (unsigned int)std::min<int64_t>(pl.rows, 0xffffffffLL);
+    fp.counters = counters; fp.na_flag = na_flag;
+    fp.tile2d = (!a->loc_x && env_int("RFSI_B200_TILE2D", 1) && a->pix_begin % a->grid_ncol == 0 &&
+                 a->grid_ncol >= 16) ? 1 : 0;
+
+    const bool main256 = forest_smem_bytes<kFusedP>(f->nfeat) <= 100 * 1024;
+    const int Pm = main256 ? kFusedP : kFallbackP;
+    long long ntiles;
+    if (fp.tile2d) {
+        fp.tiles_per_row = (a->grid_ncol + 15) / 16;
+        const long long nrows = (a->npix + a->grid_ncol - 1) / a->grid_ncol;
+        ntiles = fp.tiles_per_row * ((nrows + (Pm / 16) - 1) / (Pm / 16));
+    } else {
+        ntiles = (a->npix + Pm - 1) / Pm;
+    }
+    const bool count = counters != nullptr;
+
+    for (int d0 = 0; d0 < a->ndays; d0 += pl.db) {
+        const int nd = std::min(pl.db, a->ndays - d0);
+        const int64_t rows = a->npix * nd;
+        fp.day0 = d0; fp.ndays = nd;
+        const int64_t obase = (int64_t)d0 * a->npix;
+        fp.out_mean = a->out_mean ? a->out_mean + obase : nullptr;
+        fp.out_mean_i16 = a->out_mean_i16 ? a->out_mean_i16 + obase : nullptr;
+        fp.samples = samples; fp.row_skip = skip;
+        CU_TRY(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int), st));
+        const unsigned grid = (unsigned)(ntiles * nd);
+        if (main256) RF_TRY((launch_fused_p<kFusedP, false>(fp, grid, fused_smem_bytes<kFusedP>(f->nfeat, 0, false), count, st)));
+        else RF_TRY((launch_fused_p<kFallbackP, false>(fp, grid, fused_smem_bytes<kFallbackP>(f->nfeat, 0, false), count, st)));
+        if (!fp.exhaustive) {
+            const unsigned fgrid = (unsigned)((rows + kFallbackP - 1) / kFallbackP);
+            RF_TRY((launch_fused_p<kFallbackP, true>(fp, fgrid, fused_smem_bytes<kFallbackP>(f->nfeat, a->n_obs + 1, true), count, st)));
+        }
+        if (pl.want_q) {
+            double* oq = a->out_q ? a->out_q + obase : nullptr;
+            // q[(j*ndays + d)*npix + p]: column stride between quantiles is ndays*npix
+            RF_TRY(launch_qrf(samples, skip, rows, f->ntrees, probs_dev, a->nprobs, oq, (int64_t)a->ndays * a->npix,
+                              a->out_iqr_i16 ? a->out_iqr_i16 + obase : nullptr, st));
+        }
+    }
+    return RFSI_OK;
+}
+
+}  // namespace
+
+extern "C" size_t rfsi_dev_fused_workspace_bytes(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
+    if (!f || !a || a->struct_size != sizeof(rfsi_fused_args_t)) return 0;
+    return plan_fused(f, a, kc_extra_default()).total;
+}
+
+extern "C" int rfsi_dev_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, void* workspace,
+                                      unsigned long long* counters, int device, void* stream)
+{
+    RF_TRY(validate_fused(f, a));
+    if (!workspace) return fail(RFSI_E_ARG, "fused: workspace is NULL");
+    RF_TRY(use_device(device));
+    const FusedPlan pl = plan_fused(f, a, kc_extra_default());
+    int* na_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + pl.off_misc + 16);
+    CU_TRY(cudaMemsetAsync(na_flag, 0, sizeof(int), (cudaStream_t)stream));
+    return dev_fused(f, a, pl, workspace, counters, device, (cudaStream_t)stream, false);
+}
+
+extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device)
+{
+    RF_TRY(validate_fused(f, a));
+    for (int32_t s = 0; s < a->nobs; ++s)
+        if (a->obs_x[s] != a->obs_x[s] || a->obs_y[s] != a->obs_y[s])
+            return fail(RFSI_E_NA_INPUT, "fused: station %d has an NA coordinate", s + 1);
+    RF_TRY(use_device(device));
+    if (a->npix == 0) return RFSI_OK;
+    const int S = a->nobs, D = a->ndays;
+    // candidates beyond n.obs+1: as many as the worst day has missing stations (capped)
+    int worst_missing = 0;
+    for (int d = 0; d < D; ++d) {
+        int miss = 0;
+        for (int s = 0; s < S; ++s) miss += std::isnan(a->obs_z[(size_t)d * S + s]) ? 1 : 0;
+        worst_missing = std::max(worst_missing, miss);
+    }
+    const int kc_extra = std::min(worst_missing, std::max(kc_extra_default(), 0) + 5);
+
+    // pixel chunking: bound per-chunk device memory
+    const bool want_q = a->out_q || a->out_iqr_i16;
+    int64_t chunk = 1 << 20;
+    if (want_q) chunk = std::max<int64_t>(4096, std::min<int64_t>(chunk, (int64_t(1) << 30) / (8 * (int64_t)f->ntrees)));
+    chunk = std::min(chunk, a->npix);
+    if (!a->loc_x && a->pix_begin % a->grid_ncol == 0 && chunk < a->npix && chunk >= a->grid_ncol)
+        chunk = chunk / a->grid_ncol * a->grid_ncol;  // whole raster rows per chunk keeps 2-D tiles
+
+    DevBuf d_ox, d_oy, d_oz, d_cnt;
+    RF_TRY(d_ox.alloc(sizeof(double) * std::max(S, 1)));
+    RF_TRY(d_oy.alloc(sizeof(double) * std::max(S, 1)));
+    RF_TRY(d_oz.alloc(sizeof(double) * (size_t)std::max(S, 1) * D));
+    if (S > 0) {
+        CU_TRY(cudaMemcpy(d_ox.p, a->obs_x, sizeof(double) * S, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(d_oy.p, a->obs_y, sizeof(double) * S, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(d_oz.p, a->obs_z, sizeof(double) * (size_t)S * D, cudaMemcpyHostToDevice));
+    }
+    RF_TRY(d_cnt.alloc(4 * sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(d_cnt.p, 0, 4 * sizeof(unsigned long long)));
+
+    // per-slot device buffers: a work item is (pixel chunk, day batch)
+    rfsi_fused_args_t proto = *a;
+    proto.npix = chunk;
+    FusedPlan pl = plan_fused(f, &proto, kc_extra);
+    const int db = pl.db;
+    struct Slot {
+        Stream st;
+        DevBuf ws, lx, ly, mask, mean, q, mean16, iqr16;
+        DevBuf cov[kMaxCov];
+        int64_t cand_chunk = -1;
+    } slot[2];
+    const int nslots = (a->npix <= chunk && D <= db) ? 1 : 2;
+    for (int s = 0; s < nslots; ++s) {
+        RF_TRY(slot[s].st.create());
+        RF_TRY(slot[s].ws.alloc(pl.total));
+        if (a->loc_x) { RF_TRY(slot[s].lx.alloc(sizeof(double) * chunk)); RF_TRY(slot[s].ly.alloc(sizeof(double) * chunk)); }
+        if (a->pix_mask) RF_TRY(slot[s].mask.alloc((size_t)chunk));
+        if (a->out_mean) RF_TRY(slot[s].mean.alloc(sizeof(double) * chunk * db));
+        if (a->out_q) RF_TRY(slot[s].q.alloc(sizeof(double) * chunk * db * a->nprobs));
+        if (a->out_mean_i16) RF_TRY(slot[s].mean16.alloc(sizeof(int16_t) * chunk * db));
+        if (a->out_iqr_i16) RF_TRY(slot[s].iqr16.alloc(sizeof(int16_t) * chunk * db));
+        for (int c = 0; c < a->ncov; ++c)
+            RF_TRY(slot[s].cov[c].alloc(sizeof(double) * chunk * (a->cov_day_stride[c] ? db : 1)));
+        CU_TRY(cudaMemset(reinterpret_cast<char*>(slot[s].ws.p) + pl.off_misc, 0, 256));
+    }
+
+    int si = 0;
+    for (int64_t p0 = 0; p0 < a->npix; p0 += chunk) {
+        const int64_t cur = std::min(chunk, a->npix - p0);
+        for (int d0 = 0; d0 < D; d0 += db, si = (si + 1) % nslots) {
+            const int nd = std::min(db, D - d0);
+            Slot& sl = slot[si];
+            cudaStream_t s = sl.st.s;
+            const bool reuse = sl.cand_chunk == p0;
+            rfsi_fused_args_t b = *a;
+            b.npix = cur;
+            b.ndays = nd;
+            b.obs_x = d_ox.as<double>(); b.obs_y = d_oy.as<double>();
+            b.obs_z = d_oz.as<double>() + (size_t)d0 * S;
+            if (a->loc_x) {
+                if (!reuse) {
+                    CU_TRY(cudaMemcpyAsync(sl.lx.p, a->loc_x + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+                    CU_TRY(cudaMemcpyAsync(sl.ly.p, a->loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+                }
+                b.loc_x = sl.lx.as<double>(); b.loc_y = sl.ly.as<double>();
+            } else {
+                b.pix_begin = a->pix_begin + p0;
+            }
+            if (a->pix_mask) {
+                if (!reuse) CU_TRY(cudaMemcpyAsync(sl.mask.p, a->pix_mask + p0, (size_t)cur, cudaMemcpyHostToDevice, s));
+                b.pix_mask = sl.mask.as<unsigned char>();
+            }
+            const double* covp[kMaxCov];
+            int64_t covs[kMaxCov];
+            for (int c = 0; c < a->ncov; ++c) {
+                const int64_t hs = a->cov_day_stride[c];
+                if (hs == 0) {
+                    if (!reuse)
+                        CU_TRY(cudaMemcpyAsync(sl.cov[c].p, a->cov[c] + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+                    covs[c] = 0;
+                } else {
+                    CU_TRY(cudaMemcpy2DAsync(sl.cov[c].p, sizeof(double) * cur, a->cov[c] + (size_t)d0 * hs + p0,
+                                             sizeof(double) * hs, sizeof(double) * cur, nd, cudaMemcpyHostToDevice, s));
+                    covs[c] = cur;
+                }
+                covp[c] = sl.cov[c].as<double>();
+            }
+            b.cov = covp; b.cov_day_stride = covs;
+            b.out_mean = a->out_mean ? sl.mean.as<double>() : nullptr;
+            b.out_q = a->out_q ? sl.q.as<double>() : nullptr;
+            b.out_mean_i16 = a->out_mean_i16 ? sl.mean16.as<int16_t>() : nullptr;
+            b.out_iqr_i16 = a->out_iqr_i16 ? sl.iqr16.as<int16_t>() : nullptr;
+            FusedPlan bpl = pl;  // same offsets (sized for a full chunk); only row counts differ
+            RF_TRY(dev_fused(f, &b, bpl, sl.ws.p, d_cnt.as<unsigned long long>(), device, s, reuse));
+            sl.cand_chunk = p0;
+            // results back: device [dloc*cur + p] -> host [(d0+dloc)*npix + p0 + p]
+            if (a->out_mean)
+                CU_TRY(cudaMemcpy2DAsync(a->out_mean + (size_t)d0 * a->npix + p0, sizeof(double) * a->npix, sl.mean.p,
+                                         sizeof(double) * cur, sizeof(double) * cur, nd, cudaMemcpyDeviceToHost, s));
+            if (a->out_mean_i16)
+                CU_TRY(cudaMemcpy2DAsync(a->out_mean_i16 + (size_t)d0 * a->npix + p0, sizeof(int16_t) * a->npix,
+                                         sl.mean16.p, sizeof(int16_t) * cur, sizeof(int16_t) * cur, nd,
+                                         cudaMemcpyDeviceToHost, s));
+            if (a->out_iqr_i16)
+                CU_TRY(cudaMemcpy2DAsync(a->out_iqr_i16 + (size_t)d0 * a->npix + p0, sizeof(int16_t) * a->npix,
+                                         sl.iqr16.p, sizeof(int16_t) * cur, sizeof(int16_t) * cur, nd,
+                                         cudaMemcpyDeviceToHost, s));
+            if (a->out_q)
+                for (int j = 0; j < a->nprobs; ++j)
+                    CU_TRY(cudaMemcpy2DAsync(a->out_q + ((size_t)j * D + d0) * a->npix + p0, sizeof(double) * a->npix,
+                                             sl.q.as<double>() + (size_t)j * nd * cur, sizeof(double) * cur,
+                                             sizeof(double) * cur, nd, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    for (int s = 0; s < nslots; ++s) CU_TRY(cudaStreamSynchronize(slot[s].st.s));
+    unsigned long long cnt[4];
+    CU_TRY(cudaMemcpy(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost));
+    int na = 0;
+    for (int s = 0; s < nslots; ++s) {
+        int v = 0;
+        CU_TRY(cudaMemcpy(&v, reinterpret_cast<char*>(slot[s].ws.p) + pl.off_misc + 16, sizeof v, cudaMemcpyDeviceToHost));
+        na |= v;
+    }
+    if (na) return fail(RFSI_E_NA_INPUT, "fused: missing data in a covariate column the forest uses (outputs NA there)");
+    if (cnt[3]) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "fused: %llu pixel-days had fewer valid stations than n.obs(+1); outputs NA there", cnt[3]);
+        g_err = buf;
+        return RFSI_W_TOO_FEW_OBS;
+    }
+    return RFSI_OK;
+}

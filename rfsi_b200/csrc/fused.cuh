@@ -1,0 +1,244 @@
+// fused.cuh -- stage 1 -> stage 2 without materialising the feature table.
+//
+// One CTA = a tile of P pixels on one day: what one iteration of the mapping loops does
+// (temp_croatia/2_predictions.R:122-125,160-168,174-178;
+//  prcp_catalonia/5_prcp_prediction.R:246-251,278-296): keep that day's stations
+// (!is.na(value)), near.obs, cbind the covariates, predict the mean and/or the quantiles.
+//
+// Station geometry does not change with the day, only validity does.  A geometry pass
+// (knn_brute_kernel, MODE RAW) therefore stores, once per pixel, the KC = n_obs+1+m
+// nearest stations of ALL stations in (d2, index) order; per day the nearest VALID
+// stations are the first valid entries of that list -- exactly the list a per-day search
+// returns, because the list is a prefix of the full order.  A pixel-day whose list runs
+// dry before n_obs valid stations are found (possible only when more than m of its
+// candidates are missing that day) is appended to a fallback list and redone by the
+// FALLBACK instantiation below with a full scan of that day's valid stations.
+#pragma once
+#include "common.cuh"
+#include "forest.cuh"
+#include "knn.cuh"
+
+namespace rfsi {
+
+constexpr int kMaxNObs = 64;
+constexpr int kMaxCov = 32;
+
+struct FusedParams {
+    LocSpec loc;                 // only the FALLBACK scan needs coordinates
+    long long npix;              // pixels in this chunk
+    int day0, ndays;             // days [day0, day0+ndays) of the obs table are in this launch
+    // candidates (RAW lists of the geometry pass)
+    const double* cand_d2;
+    const int32_t* cand_id;
+    long long ld_cand;
+    int KC;
+    int exhaustive;              // 1 when the candidate list holds every station
+    // stations
+    const double2* st_xy;
+    const double* obs_z;         // [total days][S]
+    int S;
+    int n_obs, rm_dupl;
+    // covariates
+    int ncov;
+    const double* cov[kMaxCov];
+    long long cov_stride[kMaxCov];
+    short cov_row[kMaxCov];      // model column of covariate c (-1 unused)
+    short dist_row[kMaxNObs];    // model column of dist{j+1} (-1 unused)
+    short obs_row[kMaxNObs];
+    const unsigned char* pix_mask;
+    // forest
+    const Node* nodes;
+    const double* leaf_sample;
+    int T, F;
+    // outputs; row index = (d - day0)*npix + p relative to the *_base pointers
+    double* out_mean;
+    int16_t* out_mean_i16;
+    double* samples;             // [ndays*npix][T]
+    unsigned char* row_skip;     // [ndays*npix]
+    // fallback list
+    int2* fb_list;
+    unsigned int* fb_count;
+    unsigned int fb_capacity;
+    unsigned long long* counters;  // {visits, pixel-days, fallback pixel-days, too-few pixel-days}
+    int* na_flag;
+    int tile2d;                  // raster form: 16x16 pixel tiles of 8x4 warp patches
+    long long tiles_per_row;     // tile2d only
+};
+
+template <int P>
+__device__ __forceinline__ long long fused_pixel_of_thread(const FusedParams& a, long long tile) {
+    if (!a.tile2d) return tile * P + threadIdx.x;
+    // 16 x (P/16) pixel tile; a warp covers an 8 x 4 patch
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const long long tr = tile / a.tiles_per_row, tc = tile - tr * a.tiles_per_row;
+    const long long first_row = a.loc.pix_begin / a.loc.ncol;
+    const long long col = tc * 16 + (w & 1) * 8 + (l & 7);
+    const long long row = first_row + tr * (P / 16) + (w >> 1) * 4 + (l >> 3);
+    if (col >= a.loc.ncol) return -1;
+    return row * a.loc.ncol + col - a.loc.pix_begin;  // may be < 0 or >= npix: caller checks
+}
+
+__device__ __forceinline__ int16_t centi_i16(double v) {
+    const double c = __dmul_rn(v, 100.0);
+    if (c != c) return (int16_t)-32767;
+    return (int16_t)fmin(fmax(rint(c), -32767.0), 32767.0);
+}
+
+template <int P, int J, bool COUNT, bool FALLBACK>
+__global__ void __launch_bounds__(P)
+fused_kernel(const __grid_constant__ FusedParams a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* fs = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
+
+    long long p;
+    int d;
+    bool active;
+    if (!FALLBACK) {
+        const long long tile = blockIdx.x / a.ndays;
+        d = a.day0 + (int)(blockIdx.x - tile * a.ndays);
+        p = fused_pixel_of_thread<P>(a, tile);
+        active = p >= 0 && p < a.npix;
+        if (active && a.pix_mask && !a.pix_mask[p]) {
+            const long long row = (long long)(d - a.day0) * a.npix + p;
+            if (a.out_mean) a.out_mean[row] = na_real();
+            if (a.out_mean_i16) a.out_mean_i16[row] = (int16_t)-32767;
+            if (a.row_skip) a.row_skip[row] = 1;
+            active = false;
+        }
+    } else {
+        const unsigned int n = min(*a.fb_count, a.fb_capacity);
+        const unsigned int e = blockIdx.x * P + threadIdx.x;
+        active = e < n;
+        p = 0; d = 0;
+        if (active) { const int2 pd = a.fb_list[e]; p = pd.x; d = pd.y; }
+        if (blockIdx.x * P >= n) return;  // whole CTA idle
+    }
+    const long long row = (long long)(d - a.day0) * a.npix + p;
+    const double* zday = a.obs_z + (long long)d * a.S;
+
+    int taken = 0;
+    bool ok = active;
+    if (!FALLBACK) {
+        if (active) {
+            bool first_valid = true;
+            for (int c = 0; c < a.KC; ++c) {
+                const int32_t id = a.cand_id[(long long)c * a.ld_cand + p];
+                if (id == kIdxNone) break;
+                const double z = __ldg(zday + id);
+                if (z != z) continue;  // no observation at this station today
+                const double d2 = a.cand_d2[(long long)c * a.ld_cand + p];
+                if (first_valid) {
+                    first_valid = false;
+                    if (a.rm_dupl && d2 == 0.0) continue;  // the pixel IS this station
+                }
+                const int rd = a.dist_row[taken], ro = a.obs_row[taken];
+                if (rd >= 0) fs[rd * P] = __dsqrt_rn(d2);
+                if (ro >= 0) fs[ro * P] = z;
+                if (++taken == a.n_obs) break;
+            }
+            if (taken < a.n_obs) {
+                ok = false;
+                if (a.exhaustive) {  // genuinely fewer valid stations than n.obs(+1)
+                    if (a.counters) atomicAdd(&a.counters[3], 1ULL);
+                    if (a.out_mean) a.out_mean[row] = na_real();
+                    if (a.out_mean_i16) a.out_mean_i16[row] = (int16_t)-32767;
+                    if (a.row_skip) a.row_skip[row] = 1;
+                } else {
+                    const unsigned int slot = atomicAdd(a.fb_count, 1u);
+                    if (slot < a.fb_capacity) a.fb_list[slot] = make_int2((int)p, d);
+                    if (a.row_skip) a.row_skip[row] = 0;
+                }
+            }
+        }
+    } else {
+        // full scan of today's valid stations; lists live after the feature rows
+        const int k = a.n_obs + 1;
+        double* ld2 = reinterpret_cast<double*>(smem_raw) + (size_t)a.F * P + threadIdx.x;
+        int32_t* lid = reinterpret_cast<int32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)(a.F + k) * P) +
+                       threadIdx.x;
+        if (active) {
+            double px, py;
+            get_loc(a.loc, p, px, py);
+            const double inf = __longlong_as_double(0x7FF0000000000000LL);
+            for (int j = 0; j < k; ++j) { ld2[j * P] = inf; lid[j * P] = kIdxNone; }
+            double thr = inf;
+            for (int s = 0; s < a.S; ++s) {
+                const double z = __ldg(zday + s);
+                if (z != z) continue;
+                const double2 xy = __ldg(a.st_xy + s);
+                const double d2 = dist2_rn(px, py, xy.x, xy.y);
+                if (d2 < thr) {
+                    list_insert<P>(ld2, lid, k, d2, s);
+                    thr = ld2[(k - 1) * P];
+                }
+            }
+            const int first = (a.rm_dupl && lid[0] != kIdxNone && ld2[0] == 0.0) ? 1 : 0;
+            for (int j = 0; j < a.n_obs; ++j) {
+                const int32_t id = lid[(j + first) * P];
+                if (id == kIdxNone) break;
+                const int rd = a.dist_row[j], ro = a.obs_row[j];
+                if (rd >= 0) fs[rd * P] = __dsqrt_rn(ld2[(j + first) * P]);
+                if (ro >= 0) fs[ro * P] = __ldg(zday + id);
+                ++taken;
+            }
+            if (a.counters) atomicAdd(&a.counters[2], 1ULL);
+            if (taken < a.n_obs) {
+                ok = false;
+                if (a.counters) atomicAdd(&a.counters[3], 1ULL);
+                if (a.out_mean) a.out_mean[row] = na_real();
+                if (a.out_mean_i16) a.out_mean_i16[row] = (int16_t)-32767;
+                if (a.row_skip) a.row_skip[row] = 1;
+            }
+        }
+    }
+
+    if (ok) {
+        bool has_na = false;
+        for (int c = 0; c < a.ncov; ++c) {
+            const int r = a.cov_row[c];
+            if (r < 0) continue;
+            const double v = a.cov[c][(long long)d * a.cov_stride[c] + p];
+            fs[r * P] = v;
+            has_na |= (v != v);
+        }
+        if (has_na) {  // ranger refuses NA in a used column: report it, emit NA
+            ok = false;
+            if (a.na_flag) *a.na_flag = 1;
+            if (a.out_mean) a.out_mean[row] = na_real();
+            if (a.out_mean_i16) a.out_mean_i16[row] = (int16_t)-32767;
+            if (a.row_skip) a.row_skip[row] = 1;
+        }
+    }
+
+    unsigned nvisit = 0;
+    if (ok) {
+        ForestOut o;
+        o.mean = nullptr;
+        o.samples = a.samples;
+        o.leaf_sample = a.leaf_sample;
+        o.terminal = nullptr;
+        o.ld_term = 0;
+        const double sum = traverse_all<P, J, COUNT>(a.nodes, a.T, fs, o, row, nvisit);
+        const double mean = sum / (double)a.T;
+        if (a.out_mean) a.out_mean[row] = mean;
+        if (a.out_mean_i16) a.out_mean_i16[row] = centi_i16(mean);
+        if (a.row_skip) a.row_skip[row] = 0;
+    }
+    if (COUNT && a.counters) {
+        const unsigned long long w = warp_sum_u64(nvisit);
+        const unsigned long long done = warp_sum_u64(ok ? 1ULL : 0ULL);
+        if ((threadIdx.x & 31) == 0) {
+            if (w) atomicAdd(&a.counters[0], w);
+            if (done) atomicAdd(&a.counters[1], done);
+        }
+    }
+}
+
+template <int P>
+__host__ __device__ constexpr size_t fused_smem_bytes(int F, int k, bool fallback) {
+    return (size_t)F * P * sizeof(double) +
+           (fallback ? (size_t)k * P * (sizeof(double) + sizeof(int32_t)) : 0);
+}
+
+}  // namespace rfsi

@@ -1,0 +1,76 @@
+"""Mint the golden vectors under tests/golden/ from the CPU oracle.
+
+The reference holds no golden vectors for this path, so these are the
+repo's own: inputs from seeded generators, expected outputs from oracle/rfsi_oracle.c,
+cross-checked at mint time against the independent NumPy and kd-tree restatements.
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+import oracle  # noqa: E402
+from oracle import rfsi_oracle_np as onp  # noqa: E402
+from rfsi_b200 import synth  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def knn_lattice():
+    """C1-named: 100x100 lattice, 200 stations from the centres (ties + self matches), n=6."""
+    case = synth.make_case("c1")
+    loc = case.locations()
+    z = case.obs_z[0]
+    d, o, i, _ = oracle.near_obs(loc, case.obs_xy, z, 6)
+    d2, o2, i2, _ = oracle.near_obs(loc, case.obs_xy, z, 6, kdtree=True, nthreads=2)
+    assert np.array_equal(d, d2) and np.array_equal(i, i2) and np.array_equal(o, o2)
+    sub = np.arange(0, loc.shape[0], 7)
+    d3, o3, i3 = onp.near_obs(loc[sub], case.obs_xy, z, 6)
+    assert np.array_equal(d[sub], d3) and np.array_equal(i[sub], i3)
+    np.savez_compressed(OUT / "knn_c1_lattice.npz", grid=np.array(case.grid), nrow=case.nrow, obs_xy=case.obs_xy,
+                        obs_z=z, n_obs=6, dist=d, obs=o, idx=i)
+
+
+def knn_realgeom():
+    """C3 geometry (UTM-sized coordinates, 1 km cells), first 8 raster rows, n=10."""
+    case = synth.make_case("c3", ndays=1)
+    loc = case.locations(0, 8 * case.ncol)
+    valid = ~np.isnan(case.obs_z[0])
+    d, o, i, _ = oracle.near_obs(loc, case.obs_xy[valid], case.obs_z[0][valid], 10)
+    d2, _, i2, _ = oracle.near_obs(loc, case.obs_xy[valid], case.obs_z[0][valid], 10, kdtree=True, nthreads=2)
+    assert np.array_equal(d, d2) and np.array_equal(i, i2)
+    np.savez_compressed(OUT / "knn_c3_utm.npz", grid=np.array(case.grid), npix=loc.shape[0],
+                        obs_xy=case.obs_xy[valid], obs_z=case.obs_z[0][valid], n_obs=10, dist=d, obs=o, idx=i)
+
+
+def forest_small():
+    """sklearn-grown 40-tree quantile forest on C1 features; mean, terminal nodes, quantiles."""
+    case = synth.make_case("c1", ndays=3)
+    X, y = synth.training_table(case, lambda l, o, z, n: oracle.near_obs(l, o, z, n)[:2])
+    flat = synth.grow_forest_sklearn(X, y, case.feature_names, num_trees=40, quantreg=True, n_jobs=1)
+    loc = case.locations()[::13]
+    d, o, _, _ = oracle.near_obs(loc, case.obs_xy, case.obs_z[0], 6)
+    Xp = np.concatenate([d, o], axis=1)
+    fo = flat.as_dict()
+    mean = oracle.forest_predict(fo, Xp)
+    term = oracle.forest_terminal_nodes(fo, Xp)
+    probs = np.array([0.25, 0.5, 0.75])
+    q = oracle.forest_quantiles(fo, Xp, probs)
+    assert np.array_equal(mean[:50], onp.forest_predict(fo, Xp[:50]))
+    assert np.array_equal(q[:50], onp.forest_quantiles(fo, Xp[:50], probs))
+    assert np.array_equal(mean, oracle.forest_predict(fo, Xp, threads=2))
+    np.savez_compressed(OUT / "forest_c1_40trees.npz", X=Xp, probs=probs, mean=mean, term=term, q=q,
+                        feature_names=np.array(flat.feature_names),
+                        **{k: v for k, v in fo.items() if v is not None})
+
+
+if __name__ == "__main__":
+    knn_lattice()
+    knn_realgeom()
+    forest_small()
+    for p in sorted(OUT.glob("*.npz")):
+        print(p.name, p.stat().st_size)

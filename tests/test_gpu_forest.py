@@ -1,0 +1,141 @@
+"""Stage-2 parity on a real B200: forest / quantile-forest forward pass vs the CPU oracle.
+Tolerance from north_star: 1e-12 relative in fp64 (the mean is summed in tree order, so we
+also require bit equality; quantiles use R's exact interpolation expression)."""
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import oracle
+import rfsi_b200 as rb
+from rfsi_b200 import synth
+from rfsi_b200.forest import FlatForest
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+RTOL = 1e-12
+
+
+def _golden_forest():
+    f = np.load(GOLD / "forest_c1_40trees.npz")
+    flat = FlatForest(int(f["ntrees"]), f["node_offsets"], f["left"], f["right"], f["split_var"], f["split_val"],
+                      [str(s) for s in f["feature_names"]], f["rnv_offsets"], f["random_node_values"])
+    return f, flat
+
+
+def test_golden_mean_terminal_nodes_quantiles():
+    f, flat = _golden_forest()
+    model = rb.RangerForest(flat)
+    X = f["X"]
+    mean = rb.predict(model, X).predictions
+    np.testing.assert_allclose(mean, f["mean"], rtol=RTOL, atol=0)
+    np.testing.assert_array_equal(mean, f["mean"])                       # tree-order sum: bit-exact
+    np.testing.assert_array_equal(rb.predict(model, X, type="terminalNodes").predictions, f["term"])
+    q = rb.predict(model, X, type="quantiles", quantiles=f["probs"]).predictions
+    np.testing.assert_allclose(q, f["q"], rtol=RTOL, atol=0)
+    np.testing.assert_array_equal(q, f["q"])
+
+
+def test_predict_matches_columns_by_name_like_ranger():
+    f, flat = _golden_forest()
+    model = rb.RangerForest(flat)
+    X = f["X"]
+    df = pd.DataFrame({n: X[:, j] for j, n in enumerate(flat.feature_names)})
+    df = df[df.columns[::-1]].assign(sim1=0.0, fold=True)               # shuffled + extra columns
+    np.testing.assert_array_equal(rb.predict(model, df).predictions, f["mean"])
+    assert rb.predict(model, df, type="quantiles").predictions.shape == (X.shape[0], 3)   # default 0.1/0.5/0.9
+
+
+def test_missing_data_is_an_error_like_ranger():
+    f, flat = _golden_forest()
+    model = rb.RangerForest(flat)
+    X = f["X"].copy()
+    X[5, 3] = np.nan
+    with pytest.raises(rb.RfsiError) as e:
+        rb.predict(model, X)
+    assert e.value.code == -4
+    plain = FlatForest(flat.ntrees, flat.node_offsets, flat.left, flat.right, flat.split_var, flat.split_val,
+                       flat.feature_names)
+    with pytest.raises(ValueError):
+        rb.predict(rb.RangerForest(plain), f["X"], type="quantiles")
+
+
+def _random_forest_case(seed, n_train, F, T, min_leaf, quantreg=True):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n_train, F))
+    y = X[:, 0] * 2 + np.sin(X[:, 1 % F] * 3) + rng.normal(scale=0.3, size=n_train)
+    flat = synth.grow_forest_sklearn(X, y, [f"f{i}" for i in range(F)], num_trees=T, min_node_size=min_leaf,
+                                     quantreg=quantreg, n_jobs=8, seed=seed)
+    return flat, rng
+
+
+@pytest.mark.parametrize("F,T,npix", [(2, 1, 100), (12, 7, 1000), (50, 33, 5000), (80, 250, 3000), (130, 9, 700)])
+def test_parity_many_shapes(F, T, npix):
+    """T not a multiple of the trees-in-flight count, single tree, F up to the 128-pixel tile path."""
+    flat, rng = _random_forest_case(F * 1000 + T, 600, F, T, 3)
+    model = rb.RangerForest(flat)
+    X = rng.normal(size=(npix, F))
+    fo = flat.as_dict()
+    np.testing.assert_array_equal(rb.predict(model, X).predictions, oracle.forest_predict(fo, X, threads=8))
+    np.testing.assert_array_equal(rb.predict(model, X, type="terminalNodes").predictions,
+                                  oracle.forest_terminal_nodes(fo, X))
+    probs = [0.0, 0.1, 0.25, 0.5, 0.75, 0.9, 1.0]
+    np.testing.assert_array_equal(rb.predict(model, X, type="quantiles", quantiles=probs).predictions,
+                                  oracle.forest_quantiles(fo, X, probs, threads=8))
+
+
+def test_quantiles_with_na_samples_and_duplicates():
+    """na.rm=TRUE path: terminal nodes whose random.node.values cell was never set."""
+    flat, rng = _random_forest_case(77, 300, 6, 64, 5)
+    rnv = flat.random_node_values.copy()
+    leaves = np.flatnonzero((flat.left == 0) & (flat.right == 0))
+    # knock out a third of the leaf samples, duplicate values elsewhere
+    for t in range(flat.ntrees):
+        a, b = flat.node_offsets[t], flat.node_offsets[t + 1]
+        lt = leaves[(leaves >= a) & (leaves < b)] - a
+        rnv[flat.rnv_offsets[t] + lt[::3]] = np.nan
+        rnv[flat.rnv_offsets[t] + lt[1::3]] = 1.25
+    flat.random_node_values = rnv
+    model = rb.RangerForest(flat)
+    X = rng.normal(size=(2000, 6))
+    probs = [0.25, 0.5, 0.75]
+    got = rb.predict(model, X, type="quantiles", quantiles=probs).predictions
+    np.testing.assert_array_equal(got, oracle.forest_quantiles(flat.as_dict(), X, probs, threads=8))
+
+
+def test_deep_skinny_tree_and_chunked_rows():
+    """A degenerate chain tree (depth 300) and > 1 row chunk through the host API."""
+    depth = 300
+    left = np.zeros(2 * depth + 1, dtype=np.int32); right = left.copy()
+    var = left.copy(); val = np.zeros(2 * depth + 1)
+    for k in range(depth):                       # node 2k: internal, children 2k+1 (leaf) and 2k+2
+        left[2 * k], right[2 * k], val[2 * k] = 2 * k + 1, 2 * k + 2, float(k)
+        val[2 * k + 1] = 1000.0 + k
+    val[2 * depth] = -1.0
+    flat = FlatForest(1, np.array([0, 2 * depth + 1], dtype=np.int64), left, right, var, val, ["x"])
+    model = rb.RangerForest(flat)
+    assert model.info()["max_depth"] == depth
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-5, depth + 5, size=(900_000, 1))
+    got = rb.predict(model, X).predictions
+    exp = np.where(X[:, 0] > depth - 1, -1.0, 1000.0 + np.maximum(np.ceil(X[:, 0]), 0))
+    np.testing.assert_array_equal(got, exp)
+
+
+def test_forest_properties_at_simulation_size():
+    """simulation.R scripted size: 250 000 rows x 250 trees x F=50; checked against the
+    threaded oracle on a sample and through invariants everywhere."""
+    flat, rng = _random_forest_case(5, 2000, 50, 250, 5)
+    model = rb.RangerForest(flat)
+    X = rng.normal(size=(250_000, 50))
+    mean = rb.predict(model, X).predictions
+    q = rb.predict(model, X, type="quantiles", quantiles=[0.25, 0.5, 0.75]).predictions
+    leaf_vals = flat.split_val[(flat.left == 0) & (flat.right == 0)]
+    assert mean.min() >= leaf_vals.min() and mean.max() <= leaf_vals.max()
+    assert np.all(np.diff(q, axis=1) >= 0)                       # quantiles monotone in p
+    sel = rng.choice(250_000, 5000, replace=False)
+    np.testing.assert_array_equal(mean[sel], oracle.forest_predict(flat.as_dict(), X[sel], threads=8))
+    np.testing.assert_array_equal(q[sel], oracle.forest_quantiles(flat.as_dict(), X[sel], [0.25, 0.5, 0.75], threads=8))
+    # idempotence / determinism
+    np.testing.assert_array_equal(mean, rb.predict(model, X).predictions)

@@ -1,0 +1,137 @@
+"""Stage-1 parity on a real B200: CUDA near.obs (through the C ABI) vs the CPU oracle.
+Neighbour indices and distances must be bit-exact (north_star: indices bit-exact,
+distances within 1e-12 relative -- we require equality)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+import rfsi_b200 as rb
+from rfsi_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def _gpu(loc, obs, z, n, **kw):
+    df, idx = rb.near_obs(loc, np.column_stack([obs, z]), zcol=2, n_obs=n, return_idx=True, **kw)
+    d = np.stack([df[f"dist{j + 1}"].to_numpy() for j in range(n)], 1)
+    o = np.stack([df[f"obs{j + 1}"].to_numpy() for j in range(n)], 1)
+    assert list(df.columns) == [f"dist{j + 1}" for j in range(n)] + [f"obs{j + 1}" for j in range(n)]
+    return d, o, idx
+
+
+def _same(a, b):
+    np.testing.assert_array_equal(np.asarray(a).view(np.uint64) if a.dtype == np.float64 else a,
+                                  np.asarray(b).view(np.uint64) if b.dtype == np.float64 else b)
+
+
+def test_hand_case():
+    obs = np.array([[0.0, 0.0], [10.0, 0.0], [3.0, 4.0], [2.0, 0.0], [0.0, 7.0]])
+    z = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    loc = np.array([[3.0, 4.0], [1.0, 0.0], [10.0, 1.0], [-1.0, -1.0]])
+    d, o, i = _gpu(loc, obs, z, 2)
+    assert i.tolist() == [[4, 5], [1, 4], [2, 3], [1, 4]]
+    ed, eo, ei, _ = oracle.near_obs(loc, obs, z, 2)
+    _same(d, ed); _same(o, eo); _same(i, ei)
+    d, o, i = _gpu(loc, obs, z, 2, rm_dupl=False)
+    assert i[0].tolist() == [3, 4] and d[0, 0] == 0.0
+
+
+def test_golden_lattice_ties_and_self_matches():
+    g = np.load(GOLD / "knn_c1_lattice.npz")
+    x0, y0, dx, dy, ncol = g["grid"]
+    loc = synth.lattice(int(ncol), int(g["nrow"]), x0, y0, dx, dy)
+    d, o, i = _gpu(loc, g["obs_xy"], g["obs_z"], int(g["n_obs"]))
+    _same(d, g["dist"]); _same(i, g["idx"]); _same(o, g["obs"])
+
+
+def test_golden_utm_geometry():
+    g = np.load(GOLD / "knn_c3_utm.npz")
+    case = synth.make_case("c3", ndays=1)
+    loc = case.locations(0, int(g["npix"]))
+    d, o, i = _gpu(loc, g["obs_xy"], g["obs_z"], int(g["n_obs"]))
+    _same(d, g["dist"]); _same(i, g["idx"]); _same(o, g["obs"])
+
+
+@pytest.mark.parametrize("S,n,seed", [(500, 40, 1), (3000, 25, 2), (1024, 10, 3), (1025, 1, 4), (7, 6, 5)])
+def test_lattice_parity_many_shapes(S, n, seed):
+    """sim_500.R shape (n = 40), multi-tile station sets (S > 1024), tile edges, n.obs+1 == S."""
+    rng = np.random.default_rng(seed)
+    side = 120
+    loc = synth.lattice(side, side)
+    obs = loc[rng.choice(side * side, S, replace=False)]
+    z = rng.normal(size=S)
+    d, o, i = _gpu(loc, obs, z, n)
+    ed, eo, ei, _ = oracle.near_obs(loc, obs, z, n, kdtree=True, nthreads=8)
+    _same(d, ed); _same(i, ei); _same(o, eo)
+
+
+def test_too_few_observations_are_na_filled_with_warning():
+    obs = np.array([[0.0, 0.0], [1.0, 0.0]])
+    z = np.array([1.0, 2.0])
+    loc = np.array([[0.5, 0.0], [0.0, 0.0]])
+    with pytest.warns(UserWarning):
+        d, o, i = _gpu(loc, obs, z, 3)
+    ed, eo, ei, rc = oracle.near_obs(loc, obs, z, 3)
+    assert rc == 1
+    _same(d, ed); _same(i, ei); _same(o, eo)
+    assert d.view(np.uint64)[0, 2] == 0x7FF00000000007A2 and i[0, 2] == np.iinfo(np.int32).min
+
+
+def test_na_observation_values_propagate_and_na_coordinates_are_refused():
+    obs = np.array([[0.0, 0.0], [1.0, 0.0], [5.0, 5.0]])
+    z = np.array([1.0, np.nan, 3.0])
+    loc = np.array([[0.9, 0.0]])
+    d, o, i = _gpu(loc, obs, z, 2)
+    assert i[0].tolist() == [2, 1] and np.isnan(o[0, 0]) and o[0, 1] == 1.0
+    with pytest.raises(rb.RfsiError) as e:
+        _gpu(np.array([[np.nan, 0.0]]), obs, z, 1)
+    assert e.value.code == -4
+    with pytest.raises(rb.RfsiError):
+        _gpu(loc, np.array([[0.0, np.nan], [1.0, 1.0]]), np.array([1.0, 2.0]), 1)
+
+
+def test_empty_and_ragged_inputs():
+    obs = np.array([[0.0, 0.0], [1.0, 0.0], [5.0, 5.0]])
+    z = np.array([1.0, 2.0, 3.0])
+    d, o, i = _gpu(np.zeros((0, 2)), obs, z, 2)
+    assert d.shape == (0, 2)
+    # not a multiple of the CTA width, continuous coordinates
+    rng = np.random.default_rng(0)
+    loc = rng.uniform(-10, 10, size=(1000 + 37, 2))
+    obs = rng.uniform(-10, 10, size=(333, 2))
+    z = rng.normal(size=333)
+    d, o, i = _gpu(loc, obs, z, 12)
+    ed, eo, ei, _ = oracle.near_obs(loc, obs, z, 12)
+    _same(d, ed); _same(i, ei); _same(o, eo)
+
+
+def test_training_shape_locations_equal_observations():
+    """temp_croatia/1_models.R:1040-1045: every station's own observation is excluded."""
+    rng = np.random.default_rng(11)
+    xy = rng.uniform(0, 1e5, size=(150, 2))
+    z = rng.normal(size=150)
+    d, o, i = _gpu(xy, xy, z, 10)
+    assert (d[:, 0] > 0).all() and (i != np.arange(1, 151)[:, None]).all()
+    ed, eo, ei, _ = oracle.near_obs(xy, xy, z, 10)
+    _same(d, ed); _same(i, ei)
+
+
+def test_chunked_large_call_matches_properties():
+    """> 2^20 locations (two chunks, double-buffered streams): checked through
+    size-independent properties + a kd-tree oracle sample."""
+    rng = np.random.default_rng(21)
+    side = 1100                                   # 1.21 M cells
+    loc = synth.lattice(side, side)
+    obs = loc[rng.choice(side * side, 2000, replace=False)]
+    z = rng.normal(size=2000)
+    d, o, i = _gpu(loc, obs, z, 8)
+    assert np.all(np.diff(d, axis=1) >= 0) and (d[:, 0] > 0).all()
+    rec = np.sqrt((loc[:, 0] - obs[i[:, 3] - 1, 0]) ** 2 + (loc[:, 1] - obs[i[:, 3] - 1, 1]) ** 2)
+    np.testing.assert_array_equal(rec, d[:, 3])
+    np.testing.assert_array_equal(z[i - 1], o)
+    sel = rng.choice(side * side, 20000, replace=False)
+    ed, eo, ei, _ = oracle.near_obs(loc[sel], obs, z, 8, kdtree=True, nthreads=8)
+    _same(d[sel], ed); _same(i[sel], ei)

@@ -1,0 +1,96 @@
+"""Host-side logic above the C ABI (no GPU): ranger import, column matching, feature maps."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import rfsi_b200 as rb
+from rfsi_b200 import api, synth
+from rfsi_b200.forest import flatten_ranger, ranger_dict_from_flat
+
+
+def _ranger_like():
+    return {
+        "num.trees": 2, "treetype": "Regression",
+        "forest": {
+            "num.trees": 2,
+            "child.nodeIDs": [([1, 0, 0], [2, 0, 0]), ([1, 3, 0, 0, 0], [2, 4, 0, 0, 0])],
+            "split.varIDs": [[1, 0, 0], [0, 2, 0, 0, 0]],
+            "split.values": [[0.5, 1.0, 2.0], [3.0, 7.0, 9.0, 4.0, 5.0]],
+            "independent.variable.names": ["a", "b", "c"],
+            "is.ordered": [True, True, True],
+        },
+        "random.node.values": np.array([[np.nan, np.nan], [1.5, np.nan], [2.5, 9.5], [np.nan, 4.5], [np.nan, 5.5]]),
+    }
+
+
+def test_flatten_ranger_roundtrip():
+    ff = flatten_ranger(_ranger_like())
+    assert ff.ntrees == 2 and ff.node_offsets.tolist() == [0, 3, 8]
+    assert ff.left.tolist() == [1, 0, 0, 1, 3, 0, 0, 0] and ff.split_var.tolist() == [1, 0, 0, 0, 2, 0, 0, 0]
+    assert ff.rnv_offsets.tolist() == [0, 5]
+    assert ff.random_node_values[5 + 2] == 9.5 and np.isnan(ff.random_node_values[0])
+    back = ranger_dict_from_flat(ff)
+    ff2 = flatten_ranger(back)
+    for k in ("node_offsets", "left", "right", "split_var", "split_val"):
+        np.testing.assert_array_equal(getattr(ff, k), getattr(ff2, k))
+
+
+def test_old_ranger_dependent_varid_is_rebased():
+    m = _ranger_like()
+    # old objects index columns of the training frame including the response at dependent.varID
+    m["forest"]["dependent.varID"] = 1
+    m["forest"]["split.varIDs"] = [[2, 0, 0], [0, 3, 0, 0, 0]]
+    ff = flatten_ranger(m)
+    assert ff.split_var.tolist() == [1, 0, 0, 0, 2, 0, 0, 0]
+
+
+def test_unsupported_models_are_refused():
+    m = _ranger_like(); m["treetype"] = "Classification"
+    with pytest.raises(ValueError):
+        flatten_ranger(m)
+    m = _ranger_like(); m["forest"]["is.ordered"] = [True, False, True]
+    with pytest.raises(ValueError):
+        flatten_ranger(m)
+
+
+def test_model_matrix_matches_by_name_and_ignores_extras():
+    model = rb.RangerForest(flatten_ranger(_ranger_like()))
+    df = pd.DataFrame({"c": [1.0, 2.0], "zzz": [9.0, 9.0], "a": [3.0, 4.0], "b": [5.0, 6.0]})
+    Xt = api._model_matrix(model, df)
+    assert Xt.shape == (3, 2) and Xt.tolist() == [[3.0, 4.0], [5.0, 6.0], [1.0, 2.0]]
+    with pytest.raises(ValueError):
+        api._model_matrix(model, df.drop(columns=["b"]))
+    with pytest.raises(ValueError):
+        api._model_matrix(model, np.zeros((4, 2)))
+
+
+def test_feature_map_codes():
+    names = ["cov1", "dist1", "dist2", "obs1", "obs2", "elev"]
+    fm = api.feature_map(names, ["elev", "cov1"], 2)
+    assert fm.tolist() == [1, 0x10000, 0x10001, 0x20000, 0x20001, 0]
+    with pytest.raises(ValueError):
+        api.feature_map(["dist3"], [], 2)
+
+
+def test_near_obs_argument_errors_mirror_reference_usage():
+    with pytest.raises(NotImplementedError):
+        rb.near_obs(np.zeros((2, 2)), np.zeros((2, 3)), idw=True)
+    with pytest.raises(ValueError):
+        rb.near_obs(np.zeros((2, 2)), np.zeros((2, 3)), n_obs=0)
+
+
+def test_synth_cases_have_the_named_shapes():
+    c1 = synth.make_case("c1")
+    assert c1.npix == 10000 and c1.obs_xy.shape == (200, 2) and c1.n_obs == 6 and len(c1.feature_names) == 12
+    # stations are pixel centres: self matches exist
+    loc = c1.locations()
+    assert set(map(tuple, c1.obs_xy)).issubset(set(map(tuple, loc)))
+    c4 = synth.make_case("c4")
+    assert c4.npix == 380 * 280 and c4.obs_xy.shape[0] == 87 and len(c4.feature_names) == 17
+    miss = np.isnan(c4.obs_z).sum(axis=1)
+    assert miss.min() >= 1 and miss.max() <= 5
+    # raster form and explicit form of the coordinates agree bit for bit
+    c3 = synth.make_case("c3", ndays=1)
+    x0, y0, dx, dy, ncol = c3.grid
+    p = np.arange(1000, 1500)
+    np.testing.assert_array_equal(c3.locations(1000, 500)[:, 0], x0 + (p % ncol) * dx)
