@@ -188,6 +188,13 @@ int rfsi_dev_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, v
 /* number of kernels this library has launched in this process (bench accounting) */
 uint64_t rfsi_launch_count(void);
 
+/* Per-kernel device timing for roofline accounting: while enabled, every launch is
+ * bracketed by CUDA events on its own stream.  rfsi_profile_read sums (and clears) the
+ * elapsed time of one kernel class: 0 kNN geometry pass, 1 forest (matrix input),
+ * 2 fused near.obs->forest, 3 fused full-scan fallback, 4 quantile epilogue, 5 near.obs. */
+int rfsi_profile_enable(int on);
+int rfsi_profile_read(int kernel_class, double* total_ms, uint64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

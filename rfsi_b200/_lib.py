@@ -90,6 +90,8 @@ _SIGNATURES = [
     ("rfsi_dev_fused_workspace_bytes", C.c_size_t, [_P, C.POINTER(FusedArgs)]),
     ("rfsi_dev_predict_fused", C.c_int, [_P, C.POINTER(FusedArgs), _P, _P, C.c_int, _P]),
     ("rfsi_launch_count", C.c_uint64, []),
+    ("rfsi_profile_enable", C.c_int, [C.c_int]),
+    ("rfsi_profile_read", C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 

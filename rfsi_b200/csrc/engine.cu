@@ -80,6 +80,32 @@ int env_int(const char* name, int dflt) {
 
 inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Optional per-kernel device timing (bench.py's roofline): CUDA events recorded on the
+// launching stream around each launch, summed when read.
+enum ProfClass { PROF_KNN_RAW = 0, PROF_FOREST_X = 1, PROF_FUSED = 2, PROF_FALLBACK = 3, PROF_QRF = 4,
+                 PROF_KNN_FINAL = 5, PROF_NCLASS = 6 };
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+struct ProfRec { int cls; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+
+struct ProfScope {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st;
+    int cls;
+    ProfScope(int c, cudaStream_t s) : st(s), cls(c) {
+        if (!g_prof_on.load(std::memory_order_relaxed)) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back({cls, a, b});
+    }
+};
+
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -249,6 +275,29 @@ extern "C" int rfsi_version(void) { return RFSI_B200_VERSION; }
 extern "C" const char* rfsi_last_error(void) { return g_err.c_str(); }
 extern "C" uint64_t rfsi_launch_count(void) { return g_launches.load(); }
 
+extern "C" int rfsi_profile_enable(int on) {
+    g_prof_on.store(on ? 1 : 0);
+    return RFSI_OK;
+}
+
+extern "C" int rfsi_profile_read(int kernel_class, double* total_ms, uint64_t* launches) {
+    if (kernel_class < 0 || kernel_class >= PROF_NCLASS) return fail(RFSI_E_ARG, "profile_read: class %d", kernel_class);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double ms = 0.0;
+    uint64_t n = 0;
+    std::vector<ProfRec> keep;
+    for (auto& r : g_prof) {
+        if (r.cls != kernel_class) { keep.push_back(r); continue; }
+        float e = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&e, r.a, r.b) == cudaSuccess) { ms += e; ++n; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.swap(keep);
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    return RFSI_OK;
+}
+
 extern "C" int rfsi_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -291,7 +340,10 @@ int launch_knn(const LocSpec& L, int64_t npix, const double2* st_xy, int S, int 
     auto kern = knn_brute_kernel<kKnnP, MODE>;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((npix + kKnnP - 1) / kKnnP);
-    kern<<<grid, kKnnP, smem, stream>>>(L, npix, st_xy, S, k, st_z, rm_dupl, out_a, out_b, out_i, ld, warn, na_flag);
+    {
+        ProfScope ps(MODE == KNN_RAW ? PROF_KNN_RAW : PROF_KNN_FINAL, stream);
+        kern<<<grid, kKnnP, smem, stream>>>(L, npix, st_xy, S, k, st_z, rm_dupl, out_a, out_b, out_i, ld, warn, na_flag);
+    }
     count_launch();
     CU_TRY(cudaGetLastError());
     return RFSI_OK;
@@ -308,6 +360,7 @@ int launch_forest_x_pj(const Node* nodes, int T, int F, const double* X, int64_t
 {
     const size_t smem = forest_smem_bytes<P>(F);
     const unsigned grid = (unsigned)((npix + P - 1) / P);
+    ProfScope ps(PROF_FOREST_X, stream);
     if (visits) {
         auto kern = forest_x_kernel<P, J, true>;
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -349,6 +402,7 @@ int launch_qrf(const double* samples, const unsigned char* skip, int64_t nrows, 
     if (nrows == 0) return RFSI_OK;
     const unsigned grid = (unsigned)((nrows + 7) / 8);
     const int R = (T + 31) / 32;
+    ProfScope ps(PROF_QRF, stream);
 #define RFSI_QRF_CASE(RR)                                                                            \
     qrf_quantile_kernel<RR><<<grid, 256, 0, stream>>>(samples, skip, nrows, T, probs_dev, nprobs, out_q, \
                                                       ld_q, out_iqr)
@@ -670,6 +724,7 @@ int kc_extra_default() {
 
 template <int P, int J, bool FALLBACK>
 int launch_fused_pj(const FusedParams& fp, unsigned grid, size_t smem, bool count, cudaStream_t st) {
+    ProfScope ps(FALLBACK ? PROF_FALLBACK : PROF_FUSED, st);
     if (count) {
         auto kern = fused_kernel<P, J, true, FALLBACK>;
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
