@@ -8,7 +8,9 @@ namespace rfsi {
 // One forest node, 16 bytes, loaded with a single 128-bit access.
 //   internal: val = threshold, child = absolute index of the LEFT child (the right
 //             child is child+1: siblings share one 32-byte sector), feat >= 0
-//   leaf    : val = prediction, child = ranger's tree-local node id, feat = -1
+//   leaf    : val = prediction, child = the leaf's OWN index, feat = nfeat (the sentinel
+//             feature row, -inf for every pixel): x > val is never true there, so a leaf
+//             maps to itself and the traversal loop needs no leaf test (forest.cuh)
 // (ranger layout, SURVEY.md 8a row a7: split.values holds the threshold or, at a
 // terminal node, the prediction.)
 struct __align__(16) Node {

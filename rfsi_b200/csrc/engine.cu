@@ -134,9 +134,11 @@ struct rfsi_forest {
     int32_t ntrees = 0, nfeat = 0;
     std::vector<Node> nodes;          // device layout, host copy
     std::vector<double> leaf_sample;  // per device node (empty when no quantile samples)
+    std::vector<int32_t> leaf_rid;    // per device node: ranger's tree-local node id (terminalNodes)
     int max_depth = 0;
     int64_t n_internal = 0;
-    struct Image { Node* nodes = nullptr; double* leaf_sample = nullptr; };
+    std::vector<int64_t> tree_nodes;  // reachable nodes per tree (device layout, excl. the root slot)
+    struct Image { Node* nodes = nullptr; double* leaf_sample = nullptr; int32_t* leaf_rid = nullptr; };
     mutable std::mutex mu;
     mutable std::map<int, Image> images;
 };
@@ -157,6 +159,18 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
     }
     f->images[device] = im;
     *out = im;
+    return RFSI_OK;
+}
+
+// the ranger-id table is only needed by predict(type="terminalNodes"): uploaded on first use
+int forest_leaf_rid(const rfsi_forest* f, int device, const int32_t** out) {
+    std::lock_guard<std::mutex> lk(f->mu);
+    rfsi_forest::Image& im = f->images[device];
+    if (!im.leaf_rid) {
+        CU_TRY(cudaMalloc(&im.leaf_rid, f->leaf_rid.size() * sizeof(int32_t)));
+        CU_TRY(cudaMemcpy(im.leaf_rid, f->leaf_rid.data(), f->leaf_rid.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    *out = im.leaf_rid;
     return RFSI_OK;
 }
 
@@ -186,15 +200,19 @@ extern "C" int rfsi_forest_create(int32_t ntrees, const int64_t* node_offsets, c
         total += n;  // upper bound: unreachable nodes are dropped
     }
     if (total >= (int64_t)0x7fffffff) { delete f; return fail(RFSI_E_FOREST, "forest has >= 2^31 nodes"); }
-    f->nodes.assign((size_t)total, Node{0.0, 0, -1});
+    // unused slots (the root padding) are harmless self-looping leaves
+    f->nodes.assign((size_t)total, Node{0.0, 0, nfeat});
+    f->leaf_rid.assign((size_t)total, 0);
     if (rnv) f->leaf_sample.assign((size_t)total, na_real());
 
     struct Item { int32_t rid; int32_t slot; int32_t depth; };
     std::vector<Item> queue;
     int64_t next = roots;
+    f->tree_nodes.assign((size_t)ntrees, 0);
     for (int32_t t = 0; t < ntrees; ++t) {
         const int64_t o = node_offsets[t];
         const int64_t n = node_offsets[t + 1] - o;
+        const int64_t next_at_start = next;
         queue.clear();
         queue.push_back({0, t, 0});
         size_t head = 0;
@@ -207,7 +225,13 @@ extern "C" int rfsi_forest_create(int32_t ntrees, const int64_t* node_offsets, c
             const int32_t l = left[o + it.rid], r = right[o + it.rid];
             f->max_depth = std::max(f->max_depth, it.depth);
             if (l == 0 && r == 0) {
-                f->nodes[it.slot] = Node{split_val[o + it.rid], it.rid, -1};
+                const double pred = split_val[o + it.rid];
+                if (pred != pred) {
+                    delete f;
+                    return fail(RFSI_E_FOREST, "tree %d node %d: terminal node prediction is NaN", t, it.rid);
+                }
+                f->nodes[it.slot] = Node{pred, it.slot, nfeat};  // absorbing leaf (see common.cuh)
+                f->leaf_rid[it.slot] = it.rid;
                 if (rnv) f->leaf_sample[it.slot] = rnv[rnv_offsets[t] + it.rid];
             } else {
                 if (l <= 0 || l >= n || r <= 0 || r >= n) {
@@ -226,8 +250,10 @@ extern "C" int rfsi_forest_create(int32_t ntrees, const int64_t* node_offsets, c
                 ++f->n_internal;
             }
         }
+        f->tree_nodes[t] = next - next_at_start;
     }
     f->nodes.resize((size_t)next);
+    f->leaf_rid.resize((size_t)next);
     if (rnv) f->leaf_sample.resize((size_t)next);
     *out = f;
     return RFSI_OK;
@@ -241,6 +267,7 @@ extern "C" void rfsi_forest_destroy(rfsi_forest_t* f) {
         if (cudaSetDevice(kv.first) == cudaSuccess) {
             if (kv.second.nodes) cudaFree(kv.second.nodes);
             if (kv.second.leaf_sample) cudaFree(kv.second.leaf_sample);
+            if (kv.second.leaf_rid) cudaFree(kv.second.leaf_rid);
         }
         cudaSetDevice(cur);
     }
@@ -350,48 +377,73 @@ int launch_knn(const LocSpec& L, int64_t npix, const double2* st_xy, int S, int 
 }
 
 int forest_J() {
-    static int j = env_int("RFSI_B200_J", 4);
+    static int j = env_int("RFSI_B200_J", 8);
     return j;
 }
 
+// Tree ranges whose nodes total about RFSI_B200_CHUNK_MB each: one launch per range keeps
+// the part of the forest being walked resident in L2 (126 MB) while all CTAs sweep it.
+std::vector<int> tree_chunks(const rfsi_forest* f) {
+    static int mb = env_int("RFSI_B200_CHUNK_MB", 0);  // 0 = one launch (chunking measured slower)
+    std::vector<int> b{0};
+    if (mb <= 0) { b.push_back(f->ntrees); return b; }
+    const int64_t cap = (int64_t)mb * (1 << 20) / (int64_t)sizeof(Node);
+    int64_t cur = 0;
+    for (int t = 0; t < f->ntrees; ++t) {
+        if (cur > 0 && cur + f->tree_nodes[t] > cap) { b.push_back(t); cur = 0; }
+        cur += f->tree_nodes[t];
+    }
+    b.push_back(f->ntrees);
+    return b;
+}
+
 template <int P, int J>
-int launch_forest_x_pj(const Node* nodes, int T, int F, const double* X, int64_t npix, int64_t ldx,
+int launch_forest_x_pj(const rfsi_forest* f, const Node* nodes, const double* X, int64_t npix, int64_t ldx,
                        const ForestOut& o, unsigned long long* visits, int* na_flag, cudaStream_t stream)
 {
+    const int T = f->ntrees, F = f->nfeat;
     const size_t smem = forest_smem_bytes<P>(F);
     const unsigned grid = (unsigned)((npix + P - 1) / P);
-    ProfScope ps(PROF_FOREST_X, stream);
-    if (visits) {
-        auto kern = forest_x_kernel<P, J, true>;
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, P, smem, stream>>>(nodes, T, F, X, npix, ldx, o, visits, na_flag);
-    } else {
-        auto kern = forest_x_kernel<P, J, false>;
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, P, smem, stream>>>(nodes, T, F, X, npix, ldx, o, visits, na_flag);
+    // the running sum lives in o.mean; without it (terminal nodes / samples only) chunks are independent
+    const std::vector<int> cb = tree_chunks(f);
+    for (size_t c = 0; c + 1 < cb.size(); ++c) {
+        ProfScope ps(PROF_FOREST_X, stream);
+        if (visits) {
+            auto kern = forest_x_kernel<P, J, true>;
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, P, smem, stream>>>(nodes, cb[c], cb[c + 1], T, F, X, npix, ldx, o, visits, na_flag);
+        } else {
+            auto kern = forest_x_kernel<P, J, false>;
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, P, smem, stream>>>(nodes, cb[c], cb[c + 1], T, F, X, npix, ldx, o, visits, na_flag);
+        }
+        count_launch();
+        CU_TRY(cudaGetLastError());
     }
-    count_launch();
-    CU_TRY(cudaGetLastError());
     return RFSI_OK;
 }
 
-int launch_forest_x(const Node* nodes, int T, int F, const double* X, int64_t npix, int64_t ldx,
+#define RFSI_DISPATCH_J(CALL_PREFIX, P, ...)                 \
+    do {                                                     \
+        const int J__ = forest_J();                          \
+        if (J__ >= 16) return CALL_PREFIX<P, 16>(__VA_ARGS__); \
+        if (J__ >= 12) return CALL_PREFIX<P, 12>(__VA_ARGS__); \
+        if (J__ >= 8) return CALL_PREFIX<P, 8>(__VA_ARGS__);   \
+        if (J__ >= 4) return CALL_PREFIX<P, 4>(__VA_ARGS__);   \
+        return CALL_PREFIX<P, 2>(__VA_ARGS__);                 \
+    } while (0)
+
+int launch_forest_x(const rfsi_forest* f, const Node* nodes, const double* X, int64_t npix, int64_t ldx,
                     const ForestOut& o, unsigned long long* visits, int* na_flag, cudaStream_t stream)
 {
     if (npix == 0) return RFSI_OK;
+    const int F = f->nfeat;
     const bool big = forest_smem_bytes<256>(F) <= 100 * 1024;
     if (!big && forest_smem_bytes<128>(F) > 227 * 1024)
         return fail(RFSI_E_ARG, "forest with %d features exceeds the shared-memory feature tile (max %d)", F,
                     227 * 1024 / (128 * 8));
-    const int J = forest_J();
-    if (big) {
-        if (J >= 8) return launch_forest_x_pj<256, 8>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
-        if (J <= 2) return launch_forest_x_pj<256, 2>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
-        return launch_forest_x_pj<256, 4>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
-    }
-    if (J >= 8) return launch_forest_x_pj<128, 8>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
-    if (J <= 2) return launch_forest_x_pj<128, 2>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
-    return launch_forest_x_pj<128, 4>(nodes, T, F, X, npix, ldx, o, visits, na_flag, stream);
+    if (big) RFSI_DISPATCH_J(launch_forest_x_pj, 256, f, nodes, X, npix, ldx, o, visits, na_flag, stream);
+    RFSI_DISPATCH_J(launch_forest_x_pj, 128, f, nodes, X, npix, ldx, o, visits, na_flag, stream);
 }
 
 constexpr int kMaxProbs = 128;
@@ -539,7 +591,8 @@ extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, 
     rfsi_forest::Image im;
     RF_TRY(forest_image(f, device, &im));
     cudaStream_t st = (cudaStream_t)stream;
-    ForestOut o{out_mean, nullptr, im.leaf_sample, out_terminal, npix};
+    ForestOut o{out_mean, nullptr, im.leaf_sample, out_terminal, nullptr, npix};
+    if (out_terminal) RF_TRY(forest_leaf_rid(f, device, &o.leaf_rid));
     double* probs_dev = nullptr;
     if (out_q) {
         if (!im.leaf_sample) return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
@@ -550,7 +603,7 @@ extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, 
                                               align_up(sizeof(double) * (size_t)npix * f->ntrees, 256));
         CU_TRY(cudaMemcpyAsync(probs_dev, probs_host, sizeof(double) * nprobs, cudaMemcpyHostToDevice, st));
     }
-    RF_TRY(launch_forest_x(im.nodes, f->ntrees, f->nfeat, X, npix, ldx, o, visits, na_flag, st));
+    RF_TRY(launch_forest_x(f, im.nodes, X, npix, ldx, o, visits, na_flag, st));
     if (out_q) RF_TRY(launch_qrf(o.samples, nullptr, npix, f->ntrees, probs_dev, nprobs, out_q, npix, nullptr, st));
     return RFSI_OK;
 }
@@ -653,7 +706,7 @@ struct FusedPlan {
     int64_t rows = 0;         // npix * db
     bool want_q = false;
     // workspace offsets
-    size_t off_cand_d2 = 0, off_cand_id = 0, off_xy = 0, off_fb = 0, off_misc = 0, off_samples = 0, off_skip = 0,
+    size_t off_cand_d2 = 0, off_cand_id = 0, off_xy = 0, off_fb = 0, off_acc = 0, off_misc = 0, off_samples = 0, off_skip = 0,
            off_probs = 0, total = 0;
 };
 
@@ -707,6 +760,7 @@ FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_
     pl.off_cand_id = o; o += align_up(sizeof(int32_t) * (size_t)pl.KC * npix, 256);
     pl.off_xy = o; o += align_up(sizeof(double2) * (size_t)std::max(a->nobs, 1), 256);
     pl.off_fb = o; o += align_up(sizeof(int2) * (size_t)pl.rows, 256);
+    pl.off_acc = o; o += align_up(sizeof(double) * (size_t)pl.rows, 256);
     pl.off_misc = o; o += 256;  // fb_count, na_flag
     pl.off_probs = o; o += align_up(sizeof(double) * kMaxProbs, 256);
     if (pl.want_q) {
@@ -742,9 +796,13 @@ int launch_fused_pj(const FusedParams& fp, unsigned grid, size_t smem, bool coun
 template <int P, bool FALLBACK>
 int launch_fused_p(const FusedParams& fp, unsigned grid, size_t smem, bool count, cudaStream_t st) {
     const int J = forest_J();
+    if (!FALLBACK) {
+        if (J >= 16) return launch_fused_pj<P, 16, FALLBACK>(fp, grid, smem, count, st);
+        if (J >= 12) return launch_fused_pj<P, 12, FALLBACK>(fp, grid, smem, count, st);
+    }
     if (J >= 8) return launch_fused_pj<P, 8, FALLBACK>(fp, grid, smem, count, st);
-    if (J <= 2) return launch_fused_pj<P, 2, FALLBACK>(fp, grid, smem, count, st);
-    return launch_fused_pj<P, 4, FALLBACK>(fp, grid, smem, count, st);
+    if (J >= 4) return launch_fused_pj<P, 4, FALLBACK>(fp, grid, smem, count, st);
+    return launch_fused_pj<P, 2, FALLBACK>(fp, grid, smem, count, st);
 }
 
 // One pixel chunk, all days, everything already on the device.
@@ -759,6 +817,7 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
     int32_t* cand_id = reinterpret_cast<int32_t*>(ws + pl.off_cand_id);
     double2* xy = reinterpret_cast<double2*>(ws + pl.off_xy);
     int2* fb = reinterpret_cast<int2*>(ws + pl.off_fb);
+    double* acc = reinterpret_cast<double*>(ws + pl.off_acc);
     unsigned int* fb_count = reinterpret_cast<unsigned int*>(ws + pl.off_misc);
     int* na_flag = reinterpret_cast<int*>(ws + pl.off_misc + 16);
     double* probs_dev = reinterpret_cast<double*>(ws + pl.off_probs);
@@ -798,7 +857,8 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         else fp.cov_row[code] = (short)fi;  // a covariate feeds one model column
     }
     fp.pix_mask = a->pix_mask;
-    fp.nodes = im.nodes; fp.leaf_sample = im.leaf_sample; fp.T = f->ntrees; fp.F = f->nfeat;
+    fp.nodes = im.nodes; fp.leaf_sample = im.leaf_sample; fp.leaf_rid = nullptr; fp.T = f->ntrees; fp.F = f->nfeat;
+    fp.acc = acc;
     fp.fb_list = fb; fp.fb_count = fb_count; fp.fb_capacity = (unsigned int)std::min<int64_t>(pl.rows, 0xffffffffLL);
     fp.counters = counters; fp.na_flag = na_flag;
     fp.tile2d = (!a->loc_x && env_int("RFSI_B200_TILE2D", 1) && a->pix_begin % a->grid_ncol == 0 &&
@@ -815,6 +875,7 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         ntiles = (a->npix + Pm - 1) / Pm;
     }
     const bool count = counters != nullptr;
+    const std::vector<int> cb = tree_chunks(f);
 
     for (int d0 = 0; d0 < a->ndays; d0 += pl.db) {
         const int nd = std::min(pl.db, a->ndays - d0);
@@ -826,11 +887,14 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         fp.samples = samples; fp.row_skip = skip;
         CU_TRY(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int), st));
         const unsigned grid = (unsigned)(ntiles * nd);
-        if (main256) RF_TRY((launch_fused_p<kFusedP, false>(fp, grid, fused_smem_bytes<kFusedP>(f->nfeat, 0, false), count, st)));
-        else RF_TRY((launch_fused_p<kFallbackP, false>(fp, grid, fused_smem_bytes<kFallbackP>(f->nfeat, 0, false), count, st)));
-        if (!fp.exhaustive) {
-            const unsigned fgrid = (unsigned)((rows + kFallbackP - 1) / kFallbackP);
-            RF_TRY((launch_fused_p<kFallbackP, true>(fp, fgrid, fused_smem_bytes<kFallbackP>(f->nfeat, a->n_obs + 1, true), count, st)));
+        for (size_t c = 0; c + 1 < cb.size(); ++c) {  // one sweep of all tiles per L2-sized forest chunk
+            fp.t_begin = cb[c]; fp.t_end = cb[c + 1];
+            if (main256) RF_TRY((launch_fused_p<kFusedP, false>(fp, grid, fused_smem_bytes<kFusedP>(f->nfeat, 0, false), count, st)));
+            else RF_TRY((launch_fused_p<kFallbackP, false>(fp, grid, fused_smem_bytes<kFallbackP>(f->nfeat, 0, false), count, st)));
+            if (!fp.exhaustive) {
+                const unsigned fgrid = (unsigned)((rows + kFallbackP - 1) / kFallbackP);
+                RF_TRY((launch_fused_p<kFallbackP, true>(fp, fgrid, fused_smem_bytes<kFallbackP>(f->nfeat, a->n_obs + 1, true), count, st)));
+            }
         }
         if (pl.want_q) {
             double* oq = a->out_q ? a->out_q + obase : nullptr;

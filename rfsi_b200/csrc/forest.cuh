@@ -25,50 +25,47 @@ struct ForestOut {
     double* samples;          // [npix][T] pixel-major leaf samples for the quantile pass (nullable)
     const double* leaf_sample;  // per device-node sample (random.node.values), needed if samples
     int32_t* terminal;        // [T][ld_term] tree-local terminal node ids (nullable)
+    const int32_t* leaf_rid;  // per device-node ranger node id, needed if terminal
     long long ld_term;
 };
 
-// Walk all T trees for one pixel whose features are fs[f*P].  Returns the tree-order
-// sum of leaf predictions.  row = this pixel's output row.
+// Walk trees [t_begin, t_end) for one pixel whose features are fs[f*P]; `sum` carries the
+// tree-order partial sum of the trees before and the updated sum is returned.
+//
+// Leaves are absorbing: a leaf's `feat` names the sentinel feature row F (which holds -inf
+// for every pixel) and its `child` is its own index, so "x > val ? child+1 : child" maps a
+// leaf to itself.  The inner loop therefore has no per-chain leaf test and no divergent
+// branch: J loads, J (LDS, compare, add), one min-reduction of the J feature ids to see
+// whether any chain is still at an internal node.
 template <int P, int J, bool COUNT>
-__device__ __forceinline__ double traverse_all(const Node* __restrict__ nodes, int T,
-                                               const double* __restrict__ fs, const ForestOut& o,
-                                               long long row, unsigned& nvisit)
+__device__ __forceinline__ double traverse_all(const Node* __restrict__ nodes, int t_begin, int t_end, int T,
+                                               int F, double sum, const double* __restrict__ fs,
+                                               const ForestOut& o, long long row, unsigned& nvisit)
 {
-    double sum = 0.0;
-    for (int t0 = 0; t0 < T; t0 += J) {
+    for (int t0 = t_begin; t0 < t_end; t0 += J) {
         int idx[J];
         Node nd[J];
-        unsigned live = 0;
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            idx[j] = t0 + j;  // the root of tree t is node t
-            nd[j].val = 0.0; nd[j].child = 0; nd[j].feat = -1;
-            if (t0 + j < T) live |= 1u << j;
-        }
-        while (live) {
+        for (int j = 0; j < J; ++j) idx[j] = min(t0 + j, t_end - 1);  // the root of tree t is node t
+        int mn;
+        do {
 #pragma unroll
-            for (int j = 0; j < J; ++j)
-                if (live & (1u << j)) nd[j] = load_node(nodes + idx[j]);
+            for (int j = 0; j < J; ++j) nd[j] = load_node(nodes + idx[j]);
+            mn = F;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (live & (1u << j)) {
-                    if (nd[j].feat >= 0) {
-                        const double x = fs[nd[j].feat * P];
-                        idx[j] = nd[j].child + ((x <= nd[j].val) ? 0 : 1);
-                        if (COUNT) ++nvisit;
-                    } else {
-                        live &= ~(1u << j);
-                    }
-                }
+                const double x = fs[nd[j].feat * P];
+                idx[j] = nd[j].child + ((x <= nd[j].val) ? 0 : 1);
+                mn = min(mn, nd[j].feat);
+                if (COUNT) nvisit += (nd[j].feat != F) ? 1u : 0u;
             }
-        }
+        } while (mn != F);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            if (t0 + j < T) {
+            if (t0 + j < t_end) {
                 sum += nd[j].val;
                 if (o.samples) o.samples[row * T + t0 + j] = o.leaf_sample[idx[j]];
-                if (o.terminal) o.terminal[(long long)(t0 + j) * o.ld_term + row] = nd[j].child;
+                if (o.terminal) o.terminal[(long long)(t0 + j) * o.ld_term + row] = o.leaf_rid[idx[j]];
             }
         }
     }
@@ -77,15 +74,18 @@ __device__ __forceinline__ double traverse_all(const Node* __restrict__ nodes, i
 
 template <int P>
 __host__ __device__ constexpr size_t forest_smem_bytes(int F) {
-    return (size_t)F * P * sizeof(double);
+    return (size_t)(F + 1) * P * sizeof(double);  // + the sentinel row of -inf
 }
 
 // Unfused form: features come from a column-major matrix X (predict(rf, df)).
+// One launch walks trees [t_begin, t_end): the host issues one launch per L2-sized chunk of
+// the forest so every CTA on the chip reads the same few tens of MB of nodes at a time; the
+// running sum lives in o.mean between launches (still accumulated in tree order).
 template <int P, int J, bool COUNT>
-__global__ void __launch_bounds__(P)
-forest_x_kernel(const Node* __restrict__ nodes, int T, int F, const double* __restrict__ X,
-                long long npix, long long ldx, ForestOut o, unsigned long long* __restrict__ visits,
-                int* __restrict__ na_flag)
+__global__ void __launch_bounds__(P, (P * (20 + 6 * J) <= 32768) ? 2 : 1)
+forest_x_kernel(const Node* __restrict__ nodes, int t_begin, int t_end, int T, int F,
+                const double* __restrict__ X, long long npix, long long ldx, ForestOut o,
+                unsigned long long* __restrict__ visits, int* __restrict__ na_flag)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* fs = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
@@ -98,6 +98,7 @@ forest_x_kernel(const Node* __restrict__ nodes, int T, int F, const double* __re
             fs[f * P] = v;
             has_na |= (v != v);
         }
+        fs[F * P] = __longlong_as_double(0xFFF0000000000000LL);  // sentinel row: -inf
     }
     // each thread reads only its own column: no barrier needed
     unsigned nvisit = 0;
@@ -106,8 +107,9 @@ forest_x_kernel(const Node* __restrict__ nodes, int T, int F, const double* __re
             if (na_flag) *na_flag = 1;  // ranger: "Missing data in columns" -> error upstream
             if (o.mean) o.mean[p] = na_real();
         } else {
-            const double sum = traverse_all<P, J, COUNT>(nodes, T, fs, o, p, nvisit);
-            if (o.mean) o.mean[p] = sum / (double)T;
+            double sum = (t_begin > 0 && o.mean) ? o.mean[p] : 0.0;
+            sum = traverse_all<P, J, COUNT>(nodes, t_begin, t_end, T, F, sum, fs, o, p, nvisit);
+            if (o.mean) o.mean[p] = (t_end == T) ? sum / (double)T : sum;
         }
     }
     if (COUNT && visits) {

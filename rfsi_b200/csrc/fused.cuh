@@ -49,7 +49,10 @@ struct FusedParams {
     // forest
     const Node* nodes;
     const double* leaf_sample;
+    const int32_t* leaf_rid;
     int T, F;
+    int t_begin, t_end;          // this launch walks trees [t_begin, t_end) (one L2-sized chunk)
+    double* acc;                 // [ndays*npix] running tree-order sums between chunk launches
     // outputs; row index = (d - day0)*npix + p relative to the *_base pointers
     double* out_mean;
     int16_t* out_mean_i16;
@@ -85,7 +88,7 @@ __device__ __forceinline__ int16_t centi_i16(double v) {
 }
 
 template <int P, int J, bool COUNT, bool FALLBACK>
-__global__ void __launch_bounds__(P)
+__global__ void __launch_bounds__(P, (P * (20 + 6 * J) <= 32768) ? 2 : 1)
 fused_kernel(const __grid_constant__ FusedParams a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -140,11 +143,11 @@ fused_kernel(const __grid_constant__ FusedParams a)
             if (taken < a.n_obs) {
                 ok = false;
                 if (a.exhaustive) {  // genuinely fewer valid stations than n.obs(+1)
-                    if (a.counters) atomicAdd(&a.counters[3], 1ULL);
+                    if (a.counters && a.t_begin == 0) atomicAdd(&a.counters[3], 1ULL);
                     if (a.out_mean) a.out_mean[row] = na_real();
                     if (a.out_mean_i16) a.out_mean_i16[row] = (int16_t)-32767;
                     if (a.row_skip) a.row_skip[row] = 1;
-                } else {
+                } else if (a.t_begin == 0) {  // queued once; the fallback kernel follows every chunk
                     const unsigned int slot = atomicAdd(a.fb_count, 1u);
                     if (slot < a.fb_capacity) a.fb_list[slot] = make_int2((int)p, d);
                     if (a.row_skip) a.row_skip[row] = 0;
@@ -154,8 +157,8 @@ fused_kernel(const __grid_constant__ FusedParams a)
     } else {
         // full scan of today's valid stations; lists live after the feature rows
         const int k = a.n_obs + 1;
-        double* ld2 = reinterpret_cast<double*>(smem_raw) + (size_t)a.F * P + threadIdx.x;
-        int32_t* lid = reinterpret_cast<int32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)(a.F + k) * P) +
+        double* ld2 = reinterpret_cast<double*>(smem_raw) + (size_t)(a.F + 1) * P + threadIdx.x;
+        int32_t* lid = reinterpret_cast<int32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)(a.F + 1 + k) * P) +
                        threadIdx.x;
         if (active) {
             double px, py;
@@ -182,10 +185,10 @@ fused_kernel(const __grid_constant__ FusedParams a)
                 if (ro >= 0) fs[ro * P] = __ldg(zday + id);
                 ++taken;
             }
-            if (a.counters) atomicAdd(&a.counters[2], 1ULL);
+            if (a.counters && a.t_begin == 0) atomicAdd(&a.counters[2], 1ULL);
             if (taken < a.n_obs) {
                 ok = false;
-                if (a.counters) atomicAdd(&a.counters[3], 1ULL);
+                if (a.counters && a.t_begin == 0) atomicAdd(&a.counters[3], 1ULL);
                 if (a.out_mean) a.out_mean[row] = na_real();
                 if (a.out_mean_i16) a.out_mean_i16[row] = (int16_t)-32767;
                 if (a.row_skip) a.row_skip[row] = 1;
@@ -204,7 +207,7 @@ fused_kernel(const __grid_constant__ FusedParams a)
         }
         if (has_na) {  // ranger refuses NA in a used column: report it, emit NA
             ok = false;
-            if (a.na_flag) *a.na_flag = 1;
+            if (a.na_flag && a.t_begin == 0) *a.na_flag = 1;
             if (a.out_mean) a.out_mean[row] = na_real();
             if (a.out_mean_i16) a.out_mean_i16[row] = (int16_t)-32767;
             if (a.row_skip) a.row_skip[row] = 1;
@@ -218,16 +221,23 @@ fused_kernel(const __grid_constant__ FusedParams a)
         o.samples = a.samples;
         o.leaf_sample = a.leaf_sample;
         o.terminal = nullptr;
+        o.leaf_rid = nullptr;
         o.ld_term = 0;
-        const double sum = traverse_all<P, J, COUNT>(a.nodes, a.T, fs, o, row, nvisit);
-        const double mean = sum / (double)a.T;
-        if (a.out_mean) a.out_mean[row] = mean;
-        if (a.out_mean_i16) a.out_mean_i16[row] = centi_i16(mean);
-        if (a.row_skip) a.row_skip[row] = 0;
+        fs[a.F * P] = __longlong_as_double(0xFFF0000000000000LL);  // sentinel row: -inf
+        double sum = a.t_begin > 0 ? a.acc[row] : 0.0;
+        sum = traverse_all<P, J, COUNT>(a.nodes, a.t_begin, a.t_end, a.T, a.F, sum, fs, o, row, nvisit);
+        if (a.t_end == a.T) {
+            const double mean = sum / (double)a.T;
+            if (a.out_mean) a.out_mean[row] = mean;
+            if (a.out_mean_i16) a.out_mean_i16[row] = centi_i16(mean);
+            if (a.row_skip) a.row_skip[row] = 0;
+        } else {
+            a.acc[row] = sum;
+        }
     }
     if (COUNT && a.counters) {
         const unsigned long long w = warp_sum_u64(nvisit);
-        const unsigned long long done = warp_sum_u64(ok ? 1ULL : 0ULL);
+        const unsigned long long done = warp_sum_u64((ok && a.t_end == a.T) ? 1ULL : 0ULL);
         if ((threadIdx.x & 31) == 0) {
             if (w) atomicAdd(&a.counters[0], w);
             if (done) atomicAdd(&a.counters[1], done);
@@ -237,7 +247,7 @@ fused_kernel(const __grid_constant__ FusedParams a)
 
 template <int P>
 __host__ __device__ constexpr size_t fused_smem_bytes(int F, int k, bool fallback) {
-    return (size_t)F * P * sizeof(double) +
+    return (size_t)(F + 1) * P * sizeof(double) +
            (fallback ? (size_t)k * P * (sizeof(double) + sizeof(int32_t)) : 0);
 }
 
