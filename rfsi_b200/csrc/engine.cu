@@ -377,7 +377,7 @@ int launch_knn(const LocSpec& L, int64_t npix, const double2* st_xy, int S, int 
 }
 
 int forest_J() {
-    static int j = env_int("RFSI_B200_J", 8);
+    static int j = env_int("RFSI_B200_J", 12);
     return j;
 }
 
