@@ -1,0 +1,22 @@
+# near.obs -- drop-in for meteo::near.obs as the reference scripts call it
+# (simulation/simulation.R:191-196; sim_500.R:134-139; temp_croatia/2_predictions.R:160-165;
+#  prcp_catalonia/5_prcp_prediction.R:278-283; temp_croatia/1_models.R:1040-1045).
+# Same argument names, same defaults, same return value: a data.frame with columns
+# dist1..distN then obs1..obsN.  The search runs on the GPU through .Call(C_rfsi_near_obs).
+near.obs <- function(locations, locations.x.y = c(1, 2), observations, observations.x.y = c(1, 2),
+                     zcol = 3, n.obs = 10, rm.dupl = TRUE, avg = FALSE, increment, range,
+                     direct = FALSE, idw = FALSE, idw.p = 2, device = 0L) {
+  if (avg || direct || idw) stop("near.obs (rfsi_b200): avg/direct/idw are not supported")
+  xy <- function(obj, cols) {
+    if (inherits(obj, "Spatial")) return(unname(as.matrix(sp::coordinates(obj))[, 1:2, drop = FALSE]))
+    unname(as.matrix(as.data.frame(obj)[, cols, drop = FALSE]))
+  }
+  loc <- xy(locations, locations.x.y)
+  obs <- xy(observations, observations.x.y)
+  z <- if (inherits(observations, "Spatial")) observations@data[[zcol]] else as.data.frame(observations)[[zcol]]
+  storage.mode(loc) <- "double"; storage.mode(obs) <- "double"
+  res <- .Call(C_rfsi_near_obs, loc, obs, as.double(z), as.integer(n.obs), as.logical(rm.dupl), as.integer(device))
+  dist <- as.data.frame(res$dist); names(dist) <- paste0("dist", seq_len(n.obs))
+  ob <- as.data.frame(res$obs); names(ob) <- paste0("obs", seq_len(n.obs))
+  cbind(dist, ob)
+}
