@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rfsi_b200.h"
@@ -138,7 +139,20 @@ struct rfsi_forest {
     int max_depth = 0;
     int64_t n_internal = 0;
     std::vector<int64_t> tree_nodes;  // reachable nodes per tree (device layout, excl. the root slot)
-    struct Image { Node* nodes = nullptr; double* leaf_sample = nullptr; int32_t* leaf_rid = nullptr; };
+    // compact format (common.cuh): same indices as `nodes`
+    bool compact_ok = false;
+    std::vector<uint64_t> qnodes;     // (w1 << 32) | w0
+    std::vector<QRoot> qroots;
+    std::vector<double> leaf_val;
+    std::vector<double> uvals;
+    std::vector<int32_t> uoff;
+    struct Image {
+        Node* nodes = nullptr;
+        double* leaf_sample = nullptr;
+        int32_t* leaf_rid = nullptr;
+        bool compact = false;
+        QForest q{nullptr, nullptr, nullptr, nullptr, nullptr};
+    };
     mutable std::mutex mu;
     mutable std::map<int, Image> images;
 };
@@ -150,8 +164,24 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
     auto it = f->images.find(device);
     if (it != f->images.end()) { *out = it->second; return RFSI_OK; }
     rfsi_forest::Image im;
-    CU_TRY(cudaMalloc(&im.nodes, f->nodes.size() * sizeof(Node)));
-    CU_TRY(cudaMemcpy(im.nodes, f->nodes.data(), f->nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
+    im.compact = f->compact_ok && env_int("RFSI_B200_COMPACT", 1) != 0;
+    if (im.compact) {
+        auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+            void* d = nullptr;
+            CU_TRY(cudaMalloc(&d, bytes ? bytes : 8));
+            CU_TRY(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+            *dst = d;
+            return RFSI_OK;
+        };
+        RF_TRY(up(f->qnodes.data(), f->qnodes.size() * sizeof(uint64_t), reinterpret_cast<const void**>(&im.q.nodes)));
+        RF_TRY(up(f->qroots.data(), f->qroots.size() * sizeof(QRoot), reinterpret_cast<const void**>(&im.q.roots)));
+        RF_TRY(up(f->leaf_val.data(), f->leaf_val.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.leaf_val)));
+        RF_TRY(up(f->uvals.data(), f->uvals.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.uvals)));
+        RF_TRY(up(f->uoff.data(), f->uoff.size() * sizeof(int32_t), reinterpret_cast<const void**>(&im.q.uoff)));
+    } else {
+        CU_TRY(cudaMalloc(&im.nodes, f->nodes.size() * sizeof(Node)));
+        CU_TRY(cudaMemcpy(im.nodes, f->nodes.data(), f->nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
+    }
     if (!f->leaf_sample.empty()) {
         CU_TRY(cudaMalloc(&im.leaf_sample, f->leaf_sample.size() * sizeof(double)));
         CU_TRY(cudaMemcpy(im.leaf_sample, f->leaf_sample.data(), f->leaf_sample.size() * sizeof(double),
@@ -172,6 +202,84 @@ int forest_leaf_rid(const rfsi_forest* f, int device, const int32_t** out) {
     }
     *out = im.leaf_rid;
     return RFSI_OK;
+}
+
+}  // namespace
+
+namespace {
+
+// Derive the compact image (common.cuh) from the wide one.  Exact: ranks preserve order.
+void build_compact(rfsi_forest* f) {
+    const int F = f->nfeat, T = f->ntrees;
+    const size_t n = f->nodes.size();
+    f->compact_ok = false;
+    if (F >= (1 << kQFeatBits)) return;
+    const int64_t roots = (T + 1) & ~int64_t(1);
+    // sorted unique thresholds per feature
+    std::vector<std::vector<double>> u((size_t)F);
+    {
+        std::vector<size_t> cnt((size_t)F, 0);
+        for (size_t i = 0; i < n; ++i) if (f->nodes[i].feat < F) ++cnt[f->nodes[i].feat];
+        for (int j = 0; j < F; ++j) u[j].reserve(cnt[j]);
+        for (size_t i = 0; i < n; ++i) if (f->nodes[i].feat < F) u[f->nodes[i].feat].push_back(f->nodes[i].val);
+    }
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    {
+        std::atomic<int> nextf{0};
+        auto work = [&] {
+            for (int j; (j = nextf.fetch_add(1)) < F;) {
+                std::sort(u[j].begin(), u[j].end());
+                u[j].erase(std::unique(u[j].begin(), u[j].end()), u[j].end());
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t + 1 < hw; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+    }
+    f->uoff.assign((size_t)F + 1, 0);
+    for (int j = 0; j < F; ++j) {
+        if (u[j].size() >= 0xFFFFFFF0ull || f->uoff[j] + (int64_t)u[j].size() > 0x7fffffff) return;
+        f->uoff[j + 1] = f->uoff[j] + (int32_t)u[j].size();
+    }
+    f->uvals.resize((size_t)f->uoff[F]);
+    for (int j = 0; j < F; ++j) std::copy(u[j].begin(), u[j].end(), f->uvals.begin() + f->uoff[j]);
+
+    f->qnodes.assign(n, (uint64_t)kQLeafRank);       // {rank = leaf, w1 = 0}
+    f->leaf_val.assign(n, 0.0);
+    f->qroots.assign((size_t)T, QRoot{kQLeafRank, 0u, 0u, 0u});
+    std::atomic<bool> ok{true};
+    auto rank_at = [&](const Node& nd) -> uint32_t {
+        const std::vector<double>& v = u[nd.feat];
+        return (uint32_t)(std::lower_bound(v.begin(), v.end(), nd.val) - v.begin());
+    };
+    auto fill = [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+            const Node& nd = f->nodes[i];
+            if (nd.feat >= F) { f->leaf_val[i] = nd.val; continue; }          // leaf: stays absorbing
+            if ((int64_t)i < roots) continue;                                  // internal root: QRoot below
+            const int64_t delta = (int64_t)nd.child - (int64_t)i;
+            if (delta <= 0 || delta >= (int64_t)kQMaxDelta) { ok = false; continue; }
+            const uint32_t w1 = ((uint32_t)delta << kQFeatBits) | (uint32_t)nd.feat;
+            f->qnodes[i] = ((uint64_t)w1 << 32) | rank_at(nd);
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        const size_t chunk = (n + hw - 1) / hw;
+        for (unsigned t = 0; t < hw; ++t) {
+            const size_t a = t * chunk, b = std::min(n, a + chunk);
+            if (a < b) th.emplace_back(fill, a, b);
+        }
+        for (auto& t : th) t.join();
+    }
+    for (int t = 0; t < T; ++t) {
+        const Node& nd = f->nodes[t];
+        if (nd.feat >= F) f->qroots[t] = QRoot{kQLeafRank, 0u, (uint32_t)t, 0u};   // single-leaf tree
+        else f->qroots[t] = QRoot{rank_at(nd), (uint32_t)nd.feat, (uint32_t)nd.child, 0u};
+    }
+    if (!ok) { f->qnodes.clear(); f->qroots.clear(); f->leaf_val.clear(); return; }
+    f->compact_ok = true;
 }
 
 }  // namespace
@@ -255,6 +363,7 @@ extern "C" int rfsi_forest_create(int32_t ntrees, const int64_t* node_offsets, c
     f->nodes.resize((size_t)next);
     f->leaf_rid.resize((size_t)next);
     if (rnv) f->leaf_sample.resize((size_t)next);
+    build_compact(f);
     *out = f;
     return RFSI_OK;
 }
@@ -268,6 +377,9 @@ extern "C" void rfsi_forest_destroy(rfsi_forest_t* f) {
             if (kv.second.nodes) cudaFree(kv.second.nodes);
             if (kv.second.leaf_sample) cudaFree(kv.second.leaf_sample);
             if (kv.second.leaf_rid) cudaFree(kv.second.leaf_rid);
+            cudaFree(const_cast<uint2*>(kv.second.q.nodes)); cudaFree(const_cast<QRoot*>(kv.second.q.roots));
+            cudaFree(const_cast<double*>(kv.second.q.leaf_val)); cudaFree(const_cast<double*>(kv.second.q.uvals));
+            cudaFree(const_cast<int32_t*>(kv.second.q.uoff));
         }
         cudaSetDevice(cur);
     }
@@ -289,8 +401,14 @@ extern "C" int64_t rfsi_forest_info(const rfsi_forest_t* f, int what) {
         case 2: return (int64_t)f->nodes.size();
         case 3: return f->max_depth;
         case 4: return f->leaf_sample.empty() ? 0 : 1;
-        case 5: return (int64_t)(f->nodes.size() * sizeof(Node) + f->leaf_sample.size() * sizeof(double));
+        case 5:
+            if (f->compact_ok && env_int("RFSI_B200_COMPACT", 1) != 0)
+                return (int64_t)(f->qnodes.size() * 8 + f->leaf_val.size() * 8 + f->uvals.size() * 8 +
+                                 f->qroots.size() * sizeof(QRoot) + f->leaf_sample.size() * sizeof(double));
+            return (int64_t)(f->nodes.size() * sizeof(Node) + f->leaf_sample.size() * sizeof(double));
         case 6: return f->n_internal;
+        case 7: return (f->compact_ok && env_int("RFSI_B200_COMPACT", 1) != 0) ? 1 : 0;
+        case 8: return (int64_t)f->uvals.size();
         default: return -1;
     }
 }
@@ -376,9 +494,11 @@ int launch_knn(const LocSpec& L, int64_t npix, const double2* st_xy, int S, int 
     return RFSI_OK;
 }
 
+// trees in flight per thread: measured best 12 for the 16-byte format, 8 for the compact one
+thread_local int g_default_J = 12;
 int forest_J() {
-    static int j = env_int("RFSI_B200_J", 12);
-    return j;
+    static int j = env_int("RFSI_B200_J", 0);
+    return j > 0 ? j : g_default_J;
 }
 
 // Tree ranges whose nodes total about RFSI_B200_CHUNK_MB each: one launch per range keeps
@@ -395,6 +515,31 @@ std::vector<int> tree_chunks(const rfsi_forest* f) {
     }
     b.push_back(f->ntrees);
     return b;
+}
+
+template <int P, int J>
+int launch_forest_xq_pj(const rfsi_forest* f, const QForest& q, const double* X, int64_t npix, int64_t ldx,
+                        const ForestOut& o, unsigned long long* visits, int* na_flag, cudaStream_t stream)
+{
+    const int T = f->ntrees, F = f->nfeat;
+    const size_t smem = forest_q_smem_bytes<P>(F);
+    const unsigned grid = (unsigned)((npix + P - 1) / P);
+    const std::vector<int> cb = tree_chunks(f);
+    for (size_t c = 0; c + 1 < cb.size(); ++c) {
+        ProfScope ps(PROF_FOREST_X, stream);
+        if (visits) {
+            auto kern = forest_xq_kernel<P, J, true>;
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, P, smem, stream>>>(q, cb[c], cb[c + 1], T, F, X, npix, ldx, o, visits, na_flag);
+        } else {
+            auto kern = forest_xq_kernel<P, J, false>;
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, P, smem, stream>>>(q, cb[c], cb[c + 1], T, F, X, npix, ldx, o, visits, na_flag);
+        }
+        count_launch();
+        CU_TRY(cudaGetLastError());
+    }
+    return RFSI_OK;
 }
 
 template <int P, int J>
@@ -433,11 +578,20 @@ int launch_forest_x_pj(const rfsi_forest* f, const Node* nodes, const double* X,
         return CALL_PREFIX<P, 2>(__VA_ARGS__);                 \
     } while (0)
 
-int launch_forest_x(const rfsi_forest* f, const Node* nodes, const double* X, int64_t npix, int64_t ldx,
+int launch_forest_x(const rfsi_forest* f, const rfsi_forest::Image& im, const double* X, int64_t npix, int64_t ldx,
                     const ForestOut& o, unsigned long long* visits, int* na_flag, cudaStream_t stream)
 {
     if (npix == 0) return RFSI_OK;
     const int F = f->nfeat;
+    const Node* nodes = im.nodes;
+    g_default_J = im.compact ? 8 : 12;
+    if (im.compact) {
+        if (forest_q_smem_bytes<256>(F) <= 110 * 1024)
+            RFSI_DISPATCH_J(launch_forest_xq_pj, 256, f, im.q, X, npix, ldx, o, visits, na_flag, stream);
+        if (forest_q_smem_bytes<128>(F) > 227 * 1024)
+            return fail(RFSI_E_ARG, "forest with %d features exceeds the shared-memory feature tile", F);
+        RFSI_DISPATCH_J(launch_forest_xq_pj, 128, f, im.q, X, npix, ldx, o, visits, na_flag, stream);
+    }
     const bool big = forest_smem_bytes<256>(F) <= 100 * 1024;
     if (!big && forest_smem_bytes<128>(F) > 227 * 1024)
         return fail(RFSI_E_ARG, "forest with %d features exceeds the shared-memory feature tile (max %d)", F,
@@ -603,7 +757,7 @@ extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, 
                                               align_up(sizeof(double) * (size_t)npix * f->ntrees, 256));
         CU_TRY(cudaMemcpyAsync(probs_dev, probs_host, sizeof(double) * nprobs, cudaMemcpyHostToDevice, st));
     }
-    RF_TRY(launch_forest_x(f, im.nodes, X, npix, ldx, o, visits, na_flag, st));
+    RF_TRY(launch_forest_x(f, im, X, npix, ldx, o, visits, na_flag, st));
     if (out_q) RF_TRY(launch_qrf(o.samples, nullptr, npix, f->ntrees, probs_dev, nprobs, out_q, npix, nullptr, st));
     return RFSI_OK;
 }
@@ -734,8 +888,8 @@ int validate_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
         if (f->leaf_sample.empty())
             return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
     }
-    if (forest_smem_bytes<kFusedP>(f->nfeat) > 100 * 1024 &&
-        fused_smem_bytes<kFallbackP>(f->nfeat, a->n_obs + 1, true) > 227 * 1024)
+    if (fused_smem_bytes<kFallbackP, false>(f->nfeat, a->n_obs + 1, true) > 227 * 1024 &&
+        !(f->compact_ok && fused_smem_bytes<kFallbackP, true>(f->nfeat, a->n_obs + 1, true) <= 227 * 1024))
         return fail(RFSI_E_ARG, "fused: %d features exceed the shared-memory feature tile", f->nfeat);
     return RFSI_OK;
 }
@@ -776,15 +930,16 @@ int kc_extra_default() {
     return v;
 }
 
-template <int P, int J, bool FALLBACK>
-int launch_fused_pj(const FusedParams& fp, unsigned grid, size_t smem, bool count, cudaStream_t st) {
+template <int P, int J, bool FALLBACK, bool Q>
+int launch_fused_pj(const FusedParams& fp, unsigned grid, int k, bool count, cudaStream_t st) {
+    const size_t smem = fused_smem_bytes<P, Q>(fp.F, k, FALLBACK);
     ProfScope ps(FALLBACK ? PROF_FALLBACK : PROF_FUSED, st);
     if (count) {
-        auto kern = fused_kernel<P, J, true, FALLBACK>;
+        auto kern = fused_kernel<P, J, true, FALLBACK, Q>;
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, P, smem, st>>>(fp);
     } else {
-        auto kern = fused_kernel<P, J, false, FALLBACK>;
+        auto kern = fused_kernel<P, J, false, FALLBACK, Q>;
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, P, smem, st>>>(fp);
     }
@@ -793,16 +948,16 @@ int launch_fused_pj(const FusedParams& fp, unsigned grid, size_t smem, bool coun
     return RFSI_OK;
 }
 
-template <int P, bool FALLBACK>
-int launch_fused_p(const FusedParams& fp, unsigned grid, size_t smem, bool count, cudaStream_t st) {
+template <int P, bool FALLBACK, bool Q>
+int launch_fused_p(const FusedParams& fp, unsigned grid, int k, bool count, cudaStream_t st) {
     const int J = forest_J();
     if (!FALLBACK) {
-        if (J >= 16) return launch_fused_pj<P, 16, FALLBACK>(fp, grid, smem, count, st);
-        if (J >= 12) return launch_fused_pj<P, 12, FALLBACK>(fp, grid, smem, count, st);
+        if (J >= 16) return launch_fused_pj<P, 16, FALLBACK, Q>(fp, grid, k, count, st);
+        if (J >= 12) return launch_fused_pj<P, 12, FALLBACK, Q>(fp, grid, k, count, st);
     }
-    if (J >= 8) return launch_fused_pj<P, 8, FALLBACK>(fp, grid, smem, count, st);
-    if (J >= 4) return launch_fused_pj<P, 4, FALLBACK>(fp, grid, smem, count, st);
-    return launch_fused_pj<P, 2, FALLBACK>(fp, grid, smem, count, st);
+    if (J >= 8) return launch_fused_pj<P, 8, FALLBACK, Q>(fp, grid, k, count, st);
+    if (J >= 4) return launch_fused_pj<P, 4, FALLBACK, Q>(fp, grid, k, count, st);
+    return launch_fused_pj<P, 2, FALLBACK, Q>(fp, grid, k, count, st);
 }
 
 // One pixel chunk, all days, everything already on the device.
@@ -857,14 +1012,18 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         else fp.cov_row[code] = (short)fi;  // a covariate feeds one model column
     }
     fp.pix_mask = a->pix_mask;
-    fp.nodes = im.nodes; fp.leaf_sample = im.leaf_sample; fp.leaf_rid = nullptr; fp.T = f->ntrees; fp.F = f->nfeat;
+    fp.nodes = im.nodes; fp.q = im.q; fp.leaf_sample = im.leaf_sample; fp.leaf_rid = nullptr;
+    fp.T = f->ntrees; fp.F = f->nfeat;
     fp.acc = acc;
     fp.fb_list = fb; fp.fb_count = fb_count; fp.fb_capacity = (unsigned int)std::min<int64_t>(pl.rows, 0xffffffffLL);
     fp.counters = counters; fp.na_flag = na_flag;
     fp.tile2d = (!a->loc_x && env_int("RFSI_B200_TILE2D", 1) && a->pix_begin % a->grid_ncol == 0 &&
                  a->grid_ncol >= 16) ? 1 : 0;
 
-    const bool main256 = forest_smem_bytes<kFusedP>(f->nfeat) <= 100 * 1024;
+    const bool Q = im.compact;
+    g_default_J = Q ? 8 : 12;
+    const bool main256 = Q ? (fused_smem_bytes<kFusedP, true>(f->nfeat, 0, false) <= 110 * 1024)
+                           : (fused_smem_bytes<kFusedP, false>(f->nfeat, 0, false) <= 100 * 1024);
     const int Pm = main256 ? kFusedP : kFallbackP;
     long long ntiles;
     if (fp.tile2d) {
@@ -889,11 +1048,18 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         const unsigned grid = (unsigned)(ntiles * nd);
         for (size_t c = 0; c + 1 < cb.size(); ++c) {  // one sweep of all tiles per L2-sized forest chunk
             fp.t_begin = cb[c]; fp.t_end = cb[c + 1];
-            if (main256) RF_TRY((launch_fused_p<kFusedP, false>(fp, grid, fused_smem_bytes<kFusedP>(f->nfeat, 0, false), count, st)));
-            else RF_TRY((launch_fused_p<kFallbackP, false>(fp, grid, fused_smem_bytes<kFallbackP>(f->nfeat, 0, false), count, st)));
+            const int k = a->n_obs + 1;
+            if (Q) {
+                if (main256) RF_TRY((launch_fused_p<kFusedP, false, true>(fp, grid, k, count, st)));
+                else RF_TRY((launch_fused_p<kFallbackP, false, true>(fp, grid, k, count, st)));
+            } else {
+                if (main256) RF_TRY((launch_fused_p<kFusedP, false, false>(fp, grid, k, count, st)));
+                else RF_TRY((launch_fused_p<kFallbackP, false, false>(fp, grid, k, count, st)));
+            }
             if (!fp.exhaustive) {
                 const unsigned fgrid = (unsigned)((rows + kFallbackP - 1) / kFallbackP);
-                RF_TRY((launch_fused_p<kFallbackP, true>(fp, fgrid, fused_smem_bytes<kFallbackP>(f->nfeat, a->n_obs + 1, true), count, st)));
+                if (Q) RF_TRY((launch_fused_p<kFallbackP, true, true>(fp, fgrid, k, count, st)));
+                else RF_TRY((launch_fused_p<kFallbackP, true, false>(fp, fgrid, k, count, st)));
             }
         }
         if (pl.want_q) {

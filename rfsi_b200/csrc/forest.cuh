@@ -20,6 +20,27 @@
 
 namespace rfsi {
 
+// device image of the compact format
+struct QForest {
+    const uint2* nodes;       // [n] {rank, delta<<12 | feat}
+    const QRoot* roots;       // [T]
+    const double* leaf_val;   // [n] prediction at leaf indices
+    const double* uvals;      // sorted unique thresholds, features concatenated
+    const int32_t* uoff;      // [F+1]
+};
+
+// number of thresholds of feature f strictly below x (x is never NaN here)
+__device__ __forceinline__ uint32_t rank_of(const QForest& q, int f, double x) {
+    const double* __restrict__ u = q.uvals + q.uoff[f];
+    int n = q.uoff[f + 1] - q.uoff[f];
+    int lo = 0;
+    while (n > 0) {
+        const int half = n >> 1;
+        if (__ldg(u + lo + half) < x) { lo += half + 1; n -= half + 1; } else { n = half; }
+    }
+    return (uint32_t)lo;
+}
+
 struct ForestOut {
     double* mean;             // [npix] (nullable)
     double* samples;          // [npix][T] pixel-major leaf samples for the quantile pass (nullable)
@@ -70,6 +91,89 @@ __device__ __forceinline__ double traverse_all(const Node* __restrict__ nodes, i
         }
     }
     return sum;
+}
+
+// Compact-format walk: rs[f*P] are this pixel's feature ranks (uint32).  Same structure as
+// traverse_all; per visit one 64-bit node load, one 32-bit shared load, one integer compare.
+template <int P, int J, bool COUNT>
+__device__ __forceinline__ double traverse_q(const QForest& q, int t_begin, int t_end, int T, double sum,
+                                             const uint32_t* __restrict__ rs, const ForestOut& o, long long row,
+                                             unsigned& nvisit)
+{
+    for (int t0 = t_begin; t0 < t_end; t0 += J) {
+        uint32_t idx[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int t = min(t0 + j, t_end - 1);
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(q.roots + t));  // {rank, feat, child, -}
+            const uint32_t xr = rs[r.y * P];
+            idx[j] = r.z + ((xr > r.x) ? 1u : 0u);
+            if (COUNT) nvisit += (r.x != kQLeafRank) ? 1u : 0u;
+        }
+        uint32_t any;
+        do {
+            uint2 w[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) w[j] = __ldg(q.nodes + idx[j]);
+            any = 0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const uint32_t xr = rs[(w[j].y & ((1u << kQFeatBits) - 1)) * P];
+                idx[j] += (w[j].y >> kQFeatBits) + ((xr > w[j].x) ? 1u : 0u);
+                any |= w[j].y;
+                if (COUNT) nvisit += (w[j].y != 0) ? 1u : 0u;
+            }
+        } while (any != 0);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            if (t0 + j < t_end) {
+                sum += __ldg(q.leaf_val + idx[j]);
+                if (o.samples) o.samples[row * T + t0 + j] = o.leaf_sample[idx[j]];
+                if (o.terminal) o.terminal[(long long)(t0 + j) * o.ld_term + row] = o.leaf_rid[idx[j]];
+            }
+        }
+    }
+    return sum;
+}
+
+template <int P>
+__host__ __device__ constexpr size_t forest_q_smem_bytes(int F) {
+    return (size_t)F * P * sizeof(uint32_t);
+}
+
+template <int P, int J, bool COUNT>
+__global__ void __launch_bounds__(P, (P * 64 * 4 <= 65536) ? 4 : 2)
+forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* __restrict__ X,
+                 long long npix, long long ldx, ForestOut o, unsigned long long* __restrict__ visits,
+                 int* __restrict__ na_flag)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* rs = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
+    const long long p = (long long)blockIdx.x * P + threadIdx.x;
+    const bool in_range = p < npix;
+    bool has_na = false;
+    if (in_range) {
+        for (int f = 0; f < F; ++f) {
+            const double v = X[(long long)f * ldx + p];
+            has_na |= (v != v);
+            rs[f * P] = rank_of(q, f, v);
+        }
+    }
+    unsigned nvisit = 0;
+    if (in_range) {
+        if (has_na) {
+            if (na_flag) *na_flag = 1;
+            if (o.mean) o.mean[p] = na_real();
+        } else {
+            double sum = (t_begin > 0 && o.mean) ? o.mean[p] : 0.0;
+            sum = traverse_q<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
+            if (o.mean) o.mean[p] = (t_end == T) ? sum / (double)T : sum;
+        }
+    }
+    if (COUNT && visits) {
+        const unsigned long long w = warp_sum_u64(nvisit);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(visits, w);
+    }
 }
 
 template <int P>

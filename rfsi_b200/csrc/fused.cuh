@@ -47,7 +47,8 @@ struct FusedParams {
     short obs_row[kMaxNObs];
     const unsigned char* pix_mask;
     // forest
-    const Node* nodes;
+    const Node* nodes;           // wide format (nullptr when the compact image is in use)
+    QForest q;                   // compact format
     const double* leaf_sample;
     const int32_t* leaf_rid;
     int T, F;
@@ -87,8 +88,20 @@ __device__ __forceinline__ int16_t centi_i16(double v) {
     return (int16_t)fmin(fmax(rint(c), -32767.0), 32767.0);
 }
 
-template <int P, int J, bool COUNT, bool FALLBACK>
-__global__ void __launch_bounds__(P, (P * (20 + 6 * J) <= 32768) ? 2 : 1)
+// feature row r of this thread's pixel: fp64 value (wide format) or its rank (compact format)
+template <int P, bool Q>
+__device__ __forceinline__ void put_feature(const FusedParams& a, unsigned char* smem_raw, int r, double v) {
+    if (Q) (reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x)[r * P] = rank_of(a.q, r, v);
+    else (reinterpret_cast<double*>(smem_raw) + threadIdx.x)[r * P] = v;
+}
+
+template <int P, bool Q>
+__host__ __device__ constexpr size_t fused_feature_bytes(int F) {
+    return Q ? (((size_t)F * P * sizeof(uint32_t) + 15) & ~(size_t)15) : (size_t)(F + 1) * P * sizeof(double);
+}
+
+template <int P, int J, bool COUNT, bool FALLBACK, bool Q>
+__global__ void __launch_bounds__(P, Q ? ((P * 64 * 4 <= 65536) ? 4 : 2) : ((P * (20 + 6 * J) <= 32768) ? 2 : 1))
 fused_kernel(const __grid_constant__ FusedParams a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,8 +149,8 @@ fused_kernel(const __grid_constant__ FusedParams a)
                     if (a.rm_dupl && d2 == 0.0) continue;  // the pixel IS this station
                 }
                 const int rd = a.dist_row[taken], ro = a.obs_row[taken];
-                if (rd >= 0) fs[rd * P] = __dsqrt_rn(d2);
-                if (ro >= 0) fs[ro * P] = z;
+                if (rd >= 0) put_feature<P, Q>(a, smem_raw, rd, __dsqrt_rn(d2));
+                if (ro >= 0) put_feature<P, Q>(a, smem_raw, ro, z);
                 if (++taken == a.n_obs) break;
             }
             if (taken < a.n_obs) {
@@ -157,9 +170,9 @@ fused_kernel(const __grid_constant__ FusedParams a)
     } else {
         // full scan of today's valid stations; lists live after the feature rows
         const int k = a.n_obs + 1;
-        double* ld2 = reinterpret_cast<double*>(smem_raw) + (size_t)(a.F + 1) * P + threadIdx.x;
-        int32_t* lid = reinterpret_cast<int32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)(a.F + 1 + k) * P) +
-                       threadIdx.x;
+        unsigned char* lists = smem_raw + fused_feature_bytes<P, Q>(a.F);
+        double* ld2 = reinterpret_cast<double*>(lists) + threadIdx.x;
+        int32_t* lid = reinterpret_cast<int32_t*>(reinterpret_cast<double*>(lists) + (size_t)k * P) + threadIdx.x;
         if (active) {
             double px, py;
             get_loc(a.loc, p, px, py);
@@ -181,8 +194,8 @@ fused_kernel(const __grid_constant__ FusedParams a)
                 const int32_t id = lid[(j + first) * P];
                 if (id == kIdxNone) break;
                 const int rd = a.dist_row[j], ro = a.obs_row[j];
-                if (rd >= 0) fs[rd * P] = __dsqrt_rn(ld2[(j + first) * P]);
-                if (ro >= 0) fs[ro * P] = __ldg(zday + id);
+                if (rd >= 0) put_feature<P, Q>(a, smem_raw, rd, __dsqrt_rn(ld2[(j + first) * P]));
+                if (ro >= 0) put_feature<P, Q>(a, smem_raw, ro, __ldg(zday + id));
                 ++taken;
             }
             if (a.counters && a.t_begin == 0) atomicAdd(&a.counters[2], 1ULL);
@@ -202,8 +215,8 @@ fused_kernel(const __grid_constant__ FusedParams a)
             const int r = a.cov_row[c];
             if (r < 0) continue;
             const double v = a.cov[c][(long long)d * a.cov_stride[c] + p];
-            fs[r * P] = v;
             has_na |= (v != v);
+            if (v == v) put_feature<P, Q>(a, smem_raw, r, v);
         }
         if (has_na) {  // ranger refuses NA in a used column: report it, emit NA
             ok = false;
@@ -223,9 +236,13 @@ fused_kernel(const __grid_constant__ FusedParams a)
         o.terminal = nullptr;
         o.leaf_rid = nullptr;
         o.ld_term = 0;
-        fs[a.F * P] = __longlong_as_double(0xFFF0000000000000LL);  // sentinel row: -inf
+        if (!Q) fs[a.F * P] = __longlong_as_double(0xFFF0000000000000LL);  // sentinel row: -inf
         double sum = a.t_begin > 0 ? a.acc[row] : 0.0;
-        sum = traverse_all<P, J, COUNT>(a.nodes, a.t_begin, a.t_end, a.T, a.F, sum, fs, o, row, nvisit);
+        if (Q)
+            sum = traverse_q<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
+                                          reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
+        else
+            sum = traverse_all<P, J, COUNT>(a.nodes, a.t_begin, a.t_end, a.T, a.F, sum, fs, o, row, nvisit);
         if (a.t_end == a.T) {
             const double mean = sum / (double)a.T;
             if (a.out_mean) a.out_mean[row] = mean;
@@ -245,10 +262,9 @@ fused_kernel(const __grid_constant__ FusedParams a)
     }
 }
 
-template <int P>
+template <int P, bool Q>
 __host__ __device__ constexpr size_t fused_smem_bytes(int F, int k, bool fallback) {
-    return (size_t)(F + 1) * P * sizeof(double) +
-           (fallback ? (size_t)k * P * (sizeof(double) + sizeof(int32_t)) : 0);
+    return fused_feature_bytes<P, Q>(F) + (fallback ? (size_t)k * P * (sizeof(double) + sizeof(int32_t)) : 0);
 }
 
 }  // namespace rfsi
