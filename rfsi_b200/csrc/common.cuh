@@ -24,20 +24,23 @@ static_assert(sizeof(Node) == 16, "node record must be 16 bytes");
 // replaced by their rank among the sorted unique thresholds of their feature, features by the
 // number of thresholds strictly below them, so x <= thr  <=>  rank(x) <= rank(thr): decisions
 // are bit-identical to the fp64 compare.
-//   w0 = threshold rank (leaf: 0xFFFFFFFF, never exceeded)
-//   w1 = (delta << 12) | feat, delta = left child index - own index (leaf: w1 = 0, so a leaf
-//        adds 0 to its own index: absorbing)
+//   w0 = ~(threshold rank), so "rank(x) > rank(thr)" is the carry of rank(x) + w0
+//        (leaf: rank 0xFFFFFFFF -> w0 = 0, never carries)
+//   w1 = (feat*4 << 20) | delta, delta = left child index - own index (leaf: w1 = 0, so a
+//        leaf adds 0 to its own index: absorbing).  feat*4 is the byte offset of the feature
+//        in the thread's rank vector in shared memory: one LEA.HI forms the LDS address.
 // The root of each tree jumps from the root region into the tree body, too far for a 20-bit
 // delta, so roots have their own record with an absolute child index.
 struct __align__(16) QRoot {
-    uint32_t rank;
+    uint32_t rank;   // complemented, like w0
     uint32_t feat;
     uint32_t child;
     uint32_t pad;
 };
 constexpr uint32_t kQLeafRank = 0xFFFFFFFFu;
-constexpr int kQFeatBits = 12;
-constexpr uint32_t kQMaxDelta = 1u << 20;
+constexpr int kQDeltaBits = 20;
+constexpr uint32_t kQMaxDelta = 1u << kQDeltaBits;
+constexpr int kQMaxFeat = 1 << (32 - kQDeltaBits - 2);  // feat*4 must fit the top 12 bits
 
 constexpr int32_t kIdxNone = 0x7fffffff;        // empty slot of a neighbour list
 constexpr unsigned long long kNaRealBits = 0x7FF00000000007A2ULL;  // R NA_real_

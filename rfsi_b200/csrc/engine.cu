@@ -213,7 +213,7 @@ void build_compact(rfsi_forest* f) {
     const int F = f->nfeat, T = f->ntrees;
     const size_t n = f->nodes.size();
     f->compact_ok = false;
-    if (F >= (1 << kQFeatBits)) return;
+    if (F > kQMaxFeat) return;
     const int64_t roots = (T + 1) & ~int64_t(1);
     // sorted unique thresholds per feature
     std::vector<std::vector<double>> u((size_t)F);
@@ -245,9 +245,9 @@ void build_compact(rfsi_forest* f) {
     f->uvals.resize((size_t)f->uoff[F]);
     for (int j = 0; j < F; ++j) std::copy(u[j].begin(), u[j].end(), f->uvals.begin() + f->uoff[j]);
 
-    f->qnodes.assign(n, (uint64_t)kQLeafRank);       // {rank = leaf, w1 = 0}
+    f->qnodes.assign(n, (uint64_t)0);                // leaf: {w0 = ~0xFFFFFFFF = 0, w1 = 0}
     f->leaf_val.assign(n, 0.0);
-    f->qroots.assign((size_t)T, QRoot{kQLeafRank, 0u, 0u, 0u});
+    f->qroots.assign((size_t)T, QRoot{~kQLeafRank, 0u, 0u, 0u});
     std::atomic<bool> ok{true};
     auto rank_at = [&](const Node& nd) -> uint32_t {
         const std::vector<double>& v = u[nd.feat];
@@ -260,8 +260,8 @@ void build_compact(rfsi_forest* f) {
             if ((int64_t)i < roots) continue;                                  // internal root: QRoot below
             const int64_t delta = (int64_t)nd.child - (int64_t)i;
             if (delta <= 0 || delta >= (int64_t)kQMaxDelta) { ok = false; continue; }
-            const uint32_t w1 = ((uint32_t)delta << kQFeatBits) | (uint32_t)nd.feat;
-            f->qnodes[i] = ((uint64_t)w1 << 32) | rank_at(nd);
+            const uint32_t w1 = ((uint32_t)nd.feat * 4u << kQDeltaBits) | (uint32_t)delta;
+            f->qnodes[i] = ((uint64_t)w1 << 32) | (uint32_t)~rank_at(nd);
         }
     };
     {
@@ -275,8 +275,8 @@ void build_compact(rfsi_forest* f) {
     }
     for (int t = 0; t < T; ++t) {
         const Node& nd = f->nodes[t];
-        if (nd.feat >= F) f->qroots[t] = QRoot{kQLeafRank, 0u, (uint32_t)t, 0u};   // single-leaf tree
-        else f->qroots[t] = QRoot{rank_at(nd), (uint32_t)nd.feat, (uint32_t)nd.child, 0u};
+        if (nd.feat >= F) f->qroots[t] = QRoot{~kQLeafRank, 0u, (uint32_t)t, 0u};   // single-leaf tree
+        else f->qroots[t] = QRoot{~rank_at(nd), (uint32_t)nd.feat * 4u, (uint32_t)nd.child, 0u};
     }
     if (!ok) { f->qnodes.clear(); f->qroots.clear(); f->leaf_val.clear(); return; }
     f->compact_ok = true;
