@@ -4,6 +4,7 @@
 // sm_100 device every compute call returns RFSI_E_NO_DEVICE.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -20,6 +21,7 @@
 #include "forest.cuh"
 #include "fused.cuh"
 #include "knn.cuh"
+#include "knn_cells.cuh"
 #include "qrf.cuh"
 
 using namespace rfsi;
@@ -71,6 +73,20 @@ int use_device(int device) {
     if (major != 10)
         return fail(RFSI_E_NO_DEVICE, "device %d is sm_%d0, this build is sm_100a only", device, major);
     CU_TRY(cudaSetDevice(device));
+    // temporaries come from the stream-ordered pool; keep freed blocks cached so repeated
+    // calls do not pay cudaMalloc/cudaFree (hundreds of ms for multi-GB scratch) every time
+    static std::mutex mu;
+    static std::vector<char> tuned;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)tuned.size() <= device) tuned.resize(device + 1, 0);
+    if (!tuned[device]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        tuned[device] = 1;
+    }
     return RFSI_OK;
 }
 
@@ -107,24 +123,45 @@ struct ProfScope {
     }
 };
 
+// Device temporary from the stream-ordered pool, allocated/freed on the legacy stream.
+// Callers host-synchronise their work streams before a DevBuf dies, and call
+// pool_ready() after their allocations before touching them from other streams.
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, nullptr); }
     int alloc(size_t bytes) {
-        if (p) { cudaFree(p); p = nullptr; }
-        CU_TRY(cudaMalloc(&p, bytes ? bytes : 1));
+        if (p) { cudaFreeAsync(p, nullptr); p = nullptr; }
+        CU_TRY(cudaMallocAsync(&p, bytes ? bytes : 1, nullptr));
         return RFSI_OK;
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+inline int pool_ready() {
+    CU_TRY(cudaStreamSynchronize(nullptr));
+    return RFSI_OK;
+}
 
 struct Stream {
     cudaStream_t s = nullptr;
-    ~Stream() { if (s) cudaStreamDestroy(s); }
+    ~Stream() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }  // declared after the DevBufs it uses
     int create() { CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return RFSI_OK; }
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// RFSI_B200_TRACE=1: host-side phase timings of the host-buffer entry points on stderr
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(env_int("RFSI_B200_TRACE", 0) != 0), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rfsi_b200 trace] %-28s %8.2f ms\n", what,
+                std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 }  // namespace
 
@@ -494,6 +531,68 @@ int launch_knn(const LocSpec& L, int64_t npix, const double2* st_xy, int S, int 
     return RFSI_OK;
 }
 
+// ---- cell-grid search for large station sets ---------------------------------------------
+struct CellsWs {
+    CellHeader* hdr = nullptr;
+    int32_t* cell_start = nullptr;
+    int32_t* cursor = nullptr;
+    double2* sxy = nullptr;
+    int32_t* sid = nullptr;
+};
+int cells_G(int S) { return std::max(1, std::min(1024, (int)std::ceil(std::sqrt((double)std::max(S, 1) / 3.0)))); }
+size_t cells_ws_bytes(int S) {
+    const size_t G2 = (size_t)cells_G(S) * cells_G(S);
+    return 256 + align_up((G2 + 1) * 4, 256) + align_up(G2 * 4, 256) + align_up((size_t)std::max(S, 1) * 16, 256) +
+           align_up((size_t)std::max(S, 1) * 4, 256);
+}
+CellsWs carve_cells(void* ws, int S) {
+    const size_t G2 = (size_t)cells_G(S) * cells_G(S);
+    char* p = reinterpret_cast<char*>(ws);
+    CellsWs c;
+    c.hdr = reinterpret_cast<CellHeader*>(p); p += 256;
+    c.cell_start = reinterpret_cast<int32_t*>(p); p += align_up((G2 + 1) * 4, 256);
+    c.cursor = reinterpret_cast<int32_t*>(p); p += align_up(G2 * 4, 256);
+    c.sxy = reinterpret_cast<double2*>(p); p += align_up((size_t)std::max(S, 1) * 16, 256);
+    c.sid = reinterpret_cast<int32_t*>(p);
+    return c;
+}
+int cells_min_S() { return env_int("RFSI_B200_CELLS_MIN", 1024); }
+int build_cells(const double2* xy, int S, const CellsWs& c, cudaStream_t st) {
+    build_cells_kernel<<<1, 1024, 0, st>>>(xy, S, cells_G(S), c.hdr, c.cell_start, c.cursor, c.sxy, c.sid);
+    count_launch();
+    CU_TRY(cudaGetLastError());
+    return RFSI_OK;
+}
+
+template <int MODE>
+int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, int k, const double* st_z, int rm_dupl,
+                     double* out_a, double* out_b, int32_t* out_i, int64_t ld, int* warn, int* na_flag,
+                     cudaStream_t stream)
+{
+    if (npix == 0) return RFSI_OK;
+    const size_t smem = knn_cells_smem_bytes<kKnnP>(k);
+    if (smem > 227 * 1024) return fail(RFSI_E_ARG, "n.obs = %d needs %zu B of shared memory (> 227 KB)", k - 1, smem);
+    auto kern = knn_cells_kernel<kKnnP, MODE>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tile2d = (!L.x && L.pix_begin % L.ncol == 0 && L.ncol >= 16) ? 1 : 0;
+    long long tiles_per_row = 0, ntiles;
+    if (tile2d) {
+        tiles_per_row = (L.ncol + 15) / 16;
+        const long long nrows = (npix + L.ncol - 1) / L.ncol;
+        ntiles = tiles_per_row * ((nrows + (kKnnP / 16) - 1) / (kKnnP / 16));
+    } else {
+        ntiles = (npix + kKnnP - 1) / kKnnP;
+    }
+    {
+        ProfScope ps(MODE == KNN_RAW ? PROF_KNN_RAW : PROF_KNN_FINAL, stream);
+        kern<<<(unsigned)ntiles, kKnnP, smem, stream>>>(L, npix, c.hdr, c.cell_start, c.sxy, c.sid, k, st_z, rm_dupl,
+                                                         out_a, out_b, out_i, ld, warn, na_flag, tile2d, tiles_per_row);
+    }
+    count_launch();
+    CU_TRY(cudaGetLastError());
+    return RFSI_OK;
+}
+
 // trees in flight per thread: measured best 12 for the 16-byte format, 8 for the compact one
 thread_local int g_default_J = 12;
 int forest_J() {
@@ -654,8 +753,20 @@ extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, i
         count_launch();
     }
     LocSpec L{loc_x, loc_y, 0, 0, 0, 0, 1, 0};
-    int rc = launch_knn<KNN_FINAL>(L, npix, xy, nobs, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx, npix,
+    int rc;
+    if (nobs >= cells_min_S()) {
+        void* cw = nullptr;
+        CU_TRY(cudaMallocAsync(&cw, cells_ws_bytes(nobs), st));
+        const CellsWs c = carve_cells(cw, nobs);
+        rc = build_cells(xy, nobs, c, st);
+        if (rc >= 0)
+            rc = launch_knn_cells<KNN_FINAL>(L, npix, c, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx, npix,
+                                             warn_flag, nullptr, st);
+        cudaFreeAsync(cw, st);
+    } else {
+        rc = launch_knn<KNN_FINAL>(L, npix, xy, nobs, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx, npix,
                                    warn_flag, nullptr, st);
+    }
     cudaFreeAsync(xy, st);
     return rc;
 }
@@ -682,10 +793,19 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
     CU_TRY(cudaMemcpy(d_xy.p, xy.data(), sizeof(double2) * xy.size(), cudaMemcpyHostToDevice));
     if (nobs > 0) CU_TRY(cudaMemcpy(d_z.p, obs_z, sizeof(double) * nobs, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemset(d_flags.p, 0, 2 * sizeof(int)));
+    const bool use_cells = nobs >= cells_min_S();
+    DevBuf d_cells;
+    CellsWs cells;
+    if (use_cells) {
+        RF_TRY(d_cells.alloc(cells_ws_bytes(nobs)));
+        cells = carve_cells(d_cells.p, nobs);
+        RF_TRY(build_cells(d_xy.as<double2>(), nobs, cells, nullptr));
+        CU_TRY(cudaStreamSynchronize(nullptr));
+    }
 
     const int64_t chunk = std::min<int64_t>(npix, 1 << 20);
-    Stream st[2];
     DevBuf d_lx[2], d_ly[2], d_dist[2], d_obs[2], d_idx[2];
+    Stream st[2];
     for (int s = 0; s < 2; ++s) {
         RF_TRY(st[s].create());
         RF_TRY(d_lx[s].alloc(sizeof(double) * chunk));
@@ -695,6 +815,7 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
         if (out_idx) RF_TRY(d_idx[s].alloc(sizeof(int32_t) * chunk * n_obs));
         if (npix <= chunk) break;
     }
+    RF_TRY(pool_ready());
     int slot = 0;
     for (int64_t p0 = 0; p0 < npix; p0 += chunk, slot ^= 1) {
         const int64_t cur = std::min(chunk, npix - p0);
@@ -702,10 +823,16 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
         CU_TRY(cudaMemcpyAsync(d_lx[slot].p, loc_x + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
         CU_TRY(cudaMemcpyAsync(d_ly[slot].p, loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
         LocSpec L{d_lx[slot].as<double>(), d_ly[slot].as<double>(), 0, 0, 0, 0, 1, 0};
-        RF_TRY(launch_knn<KNN_FINAL>(L, cur, d_xy.as<double2>(), nobs, n_obs + 1, d_z.as<double>(), rm_dupl,
-                                     d_dist[slot].as<double>(), d_obs[slot].as<double>(),
-                                     out_idx ? d_idx[slot].as<int32_t>() : nullptr, cur, d_flags.as<int>(),
-                                     d_flags.as<int>() + 1, s));
+        if (use_cells)
+            RF_TRY(launch_knn_cells<KNN_FINAL>(L, cur, cells, n_obs + 1, d_z.as<double>(), rm_dupl,
+                                               d_dist[slot].as<double>(), d_obs[slot].as<double>(),
+                                               out_idx ? d_idx[slot].as<int32_t>() : nullptr, cur, d_flags.as<int>(),
+                                               d_flags.as<int>() + 1, s));
+        else
+            RF_TRY(launch_knn<KNN_FINAL>(L, cur, d_xy.as<double2>(), nobs, n_obs + 1, d_z.as<double>(), rm_dupl,
+                                         d_dist[slot].as<double>(), d_obs[slot].as<double>(),
+                                         out_idx ? d_idx[slot].as<int32_t>() : nullptr, cur, d_flags.as<int>(),
+                                         d_flags.as<int>() + 1, s));
         CU_TRY(cudaMemcpy2DAsync(out_dist + p0, sizeof(double) * npix, d_dist[slot].p, sizeof(double) * cur,
                                  sizeof(double) * cur, n_obs, cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaMemcpy2DAsync(out_obs + p0, sizeof(double) * npix, d_obs[slot].p, sizeof(double) * cur,
@@ -784,8 +911,8 @@ int host_forest(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t l
     DevBuf d_flag;
     RF_TRY(d_flag.alloc(sizeof(int)));
     CU_TRY(cudaMemset(d_flag.p, 0, sizeof(int)));
-    Stream st[2];
     DevBuf d_X[2], d_mean[2], d_q[2], d_term[2], d_scr[2];
+    Stream st[2];
     for (int s = 0; s < 2; ++s) {
         RF_TRY(st[s].create());
         RF_TRY(d_X[s].alloc(sizeof(double) * chunk * F));
@@ -797,6 +924,7 @@ int host_forest(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t l
         if (out_term) RF_TRY(d_term[s].alloc(sizeof(int32_t) * chunk * T));
         if (npix <= chunk) break;
     }
+    RF_TRY(pool_ready());
     int slot = 0;
     for (int64_t p0 = 0; p0 < npix; p0 += chunk, slot ^= 1) {
         const int64_t cur = std::min(chunk, npix - p0);
@@ -860,7 +988,7 @@ struct FusedPlan {
     int64_t rows = 0;         // npix * db
     bool want_q = false;
     // workspace offsets
-    size_t off_cand_d2 = 0, off_cand_id = 0, off_xy = 0, off_fb = 0, off_acc = 0, off_misc = 0, off_samples = 0, off_skip = 0,
+    size_t off_cand_d2 = 0, off_cand_id = 0, off_xy = 0, off_cells = 0, off_fb = 0, off_acc = 0, off_misc = 0, off_samples = 0, off_skip = 0,
            off_probs = 0, total = 0;
 };
 
@@ -913,6 +1041,7 @@ FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_
     pl.off_cand_d2 = o; o += align_up(sizeof(double) * (size_t)pl.KC * npix, 256);
     pl.off_cand_id = o; o += align_up(sizeof(int32_t) * (size_t)pl.KC * npix, 256);
     pl.off_xy = o; o += align_up(sizeof(double2) * (size_t)std::max(a->nobs, 1), 256);
+    pl.off_cells = o; o += align_up(cells_ws_bytes(a->nobs), 256);
     pl.off_fb = o; o += align_up(sizeof(int2) * (size_t)pl.rows, 256);
     pl.off_acc = o; o += align_up(sizeof(double) * (size_t)pl.rows, 256);
     pl.off_misc = o; o += 256;  // fb_count, na_flag
@@ -987,8 +1116,15 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
             count_launch();
         }
         // geometry pass: the KC nearest of ALL stations, once per pixel
-        RF_TRY(launch_knn<KNN_RAW>(L, a->npix, xy, a->nobs, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id, a->npix,
-                                   nullptr, nullptr, st));
+        if (a->nobs >= cells_min_S()) {
+            const CellsWs c = carve_cells(ws + pl.off_cells, a->nobs);
+            RF_TRY(build_cells(xy, a->nobs, c, st));
+            RF_TRY(launch_knn_cells<KNN_RAW>(L, a->npix, c, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id, a->npix,
+                                             nullptr, nullptr, st));
+        } else {
+            RF_TRY(launch_knn<KNN_RAW>(L, a->npix, xy, a->nobs, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id, a->npix,
+                                       nullptr, nullptr, st));
+        }
     }
     if (pl.want_q)
         CU_TRY(cudaMemcpyAsync(probs_dev, a->probs, sizeof(double) * a->nprobs, cudaMemcpyHostToDevice, st));
@@ -1099,6 +1235,7 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
             return fail(RFSI_E_NA_INPUT, "fused: station %d has an NA coordinate", s + 1);
     RF_TRY(use_device(device));
     if (a->npix == 0) return RFSI_OK;
+    Trace tr;
     const int S = a->nobs, D = a->ndays;
     // candidates beyond n.obs+1: as many as the worst day has missing stations (capped)
     int worst_missing = 0;
@@ -1135,10 +1272,10 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
     FusedPlan pl = plan_fused(f, &proto, kc_extra);
     const int db = pl.db;
     struct Slot {
-        Stream st;
         DevBuf ws, lx, ly, mask, mean, q, mean16, iqr16;
         DevBuf cov[kMaxCov];
         int64_t cand_chunk = -1;
+        Stream st;  // last member: destroyed (and synchronised) before the buffers above
     } slot[2];
     const int nslots = (a->npix <= chunk && D <= db) ? 1 : 2;
     for (int s = 0; s < nslots; ++s) {
@@ -1155,6 +1292,8 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
         CU_TRY(cudaMemset(reinterpret_cast<char*>(slot[s].ws.p) + pl.off_misc, 0, 256));
     }
 
+    RF_TRY(pool_ready());
+    tr.mark("setup (alloc + stations)");
     int si = 0;
     for (int64_t p0 = 0; p0 < a->npix; p0 += chunk) {
         const int64_t cur = std::min(chunk, a->npix - p0);
@@ -1223,7 +1362,9 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
                                              sizeof(double) * cur, nd, cudaMemcpyDeviceToHost, s));
         }
     }
+    tr.mark("enqueue all work items");
     for (int s = 0; s < nslots; ++s) CU_TRY(cudaStreamSynchronize(slot[s].st.s));
+    tr.mark("stream sync");
     unsigned long long cnt[4];
     CU_TRY(cudaMemcpy(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost));
     int na = 0;

@@ -135,3 +135,32 @@ def test_chunked_large_call_matches_properties():
     sel = rng.choice(side * side, 20000, replace=False)
     ed, eo, ei, _ = oracle.near_obs(loc[sel], obs, z, 8, kdtree=True, nthreads=8)
     _same(d[sel], ed); _same(i[sel], ei)
+
+
+@pytest.mark.parametrize("case", ["shuffled", "outside", "collinear", "clustered", "forced_small"])
+def test_cell_grid_search_is_exact_in_awkward_geometries(case, monkeypatch):
+    """The pruned search (S >= 1024) must be the same function of the data as the full scan:
+    incoherent location order, locations far outside the station bbox, degenerate bboxes,
+    strong clustering, and the cell path forced onto a small lattice with ties."""
+    rng = np.random.default_rng(hash(case) % 1000)
+    S, n = 4000, 15
+    obs = rng.uniform(0, 5000, size=(S, 2))
+    loc = rng.uniform(0, 5000, size=(30000, 2))
+    if case == "outside":
+        loc = rng.uniform(-20000, 30000, size=(30000, 2))
+    elif case == "collinear":
+        obs[:, 1] = 17.0
+        obs[:100, 0] = 3.0                         # 100 coincident stations
+    elif case == "clustered":
+        obs[: S // 2] = rng.normal(2500, 5, size=(S // 2, 2))
+        loc[:15000] = rng.normal(2500, 8, size=(15000, 2))
+    elif case == "forced_small":
+        monkeypatch.setenv("RFSI_B200_CELLS_MIN", "1")
+        side = 90
+        loc = synth.lattice(side, side)
+        obs = loc[rng.choice(side * side, 700, replace=False)]
+        S = 700
+    z = rng.normal(size=S)
+    d, o, i = _gpu(loc, obs, z, n)
+    ed, eo, ei, _ = oracle.near_obs(loc, obs, z, n, kdtree=True, nthreads=8)
+    _same(d, ed); _same(i, ei); _same(o, eo)
