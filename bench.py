@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--qrf", action="store_true", help="also time mean + 3 quantiles (IQR maps) on a smaller band")
     return ap.parse_args()
 
 
@@ -234,7 +235,7 @@ def main_ours(args):
         return a[:, :n], a[:, n:]
 
     if rank == 0:
-        flat = grow(case, gpu_near_obs, args.trees)
+        flat = grow(case, gpu_near_obs, args.trees, quantreg=args.qrf and world == 1)
         parts = [flat.node_offsets, flat.left, flat.right, flat.split_var, flat.split_val]
     else:
         flat, parts = None, None
@@ -421,6 +422,43 @@ def main_ours(args):
                "ms_per_step": 1e3 * float(t_e.item()) / args.steps,
                "api": "rfsi_predict_fused (pinned host buffers in, pinned host buffer out)"}
 
+    # ---- quantile forest (IQR maps), reported separately -------------------
+    qrf = None
+    if args.qrf and world == 1:
+        Pq, Dq = min(P, 20 * ncol), min(D, 2)
+        out_q = torch.empty((3, Dq, Pq), dtype=torch.float64, device=dev)
+        out_m = torch.empty((Dq, Pq), dtype=torch.float64, device=dev)
+        probs_c = (C.c_double * 3)(0.25, 0.5, 0.75)
+
+        def qargs(step):
+            a = make_args(step)
+            a.npix, a.ndays = Pq, Dq
+            a.probs = C.cast(probs_c, C.POINTER(C.c_double)); a.nprobs = 3
+            a.out_mean, a.out_q = out_m.data_ptr(), out_q.data_ptr()
+            return a
+        aq = qargs(0)
+        wsq = torch.empty(lib.rfsi_dev_fused_workspace_bytes(model.handle, C.byref(aq)), dtype=torch.uint8, device=dev)
+        for i in range(2):
+            _lib.check(lib.rfsi_dev_predict_fused(model.handle, C.byref(qargs(i)), wsq.data_ptr(), None, local, None))
+        torch.cuda.synchronize(dev)
+        lib.rfsi_profile_enable(1)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(stream)
+        for i in range(args.steps):
+            _lib.check(lib.rfsi_dev_predict_fused(model.handle, C.byref(qargs(2 + i)), wsq.data_ptr(), None, local, None))
+        q1.record(stream)
+        torch.cuda.synchronize(dev)
+        lib.rfsi_profile_enable(0)
+        qms = q0.elapsed_time(q1)
+        tq, nq = C.c_double(0), C.c_uint64(0)
+        lib.rfsi_profile_read(4, C.byref(tq), C.byref(nq))
+        tf, nf = C.c_double(0), C.c_uint64(0)
+        lib.rfsi_profile_read(2, C.byref(tf), C.byref(nf))
+        qrf = {"value": Pq * Dq * args.steps / (qms * 1e-3), "unit": UNIT, "what": "mean + quantiles (.25,.5,.75)",
+               "pixels": Pq, "days": Dq, "quantile_kernel_ms_per_step": tq.value / args.steps,
+               "fused_kernel_ms_per_step": tf.value / args.steps}
+        del out_q, out_m, wsq
+
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -442,6 +480,8 @@ def main_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if qrf is not None:
+            line["qrf"] = qrf
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

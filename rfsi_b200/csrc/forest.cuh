@@ -93,12 +93,12 @@ __device__ __forceinline__ double traverse_all(const Node* __restrict__ nodes, i
     return sum;
 }
 
-// Compact-format walk.  rs = this thread's rank vector in shared memory (pixel-major:
-// thread i owns words [i*Fpad, i*Fpad+F), Fpad odd so a warp reading one feature is
-// conflict-free).  Per visit: one 64-bit node load, one LEA.HI + LDS.32, one AND, and an
-// add-with-carry pair that folds "rank(x) > rank(thr)" into the index update
+// Compact-format walk.  rs = this thread's column of the rank tile in shared memory
+// (feature-major: feature f of pixel i at word f*P + i, so any mix of features across a
+// warp is bank-conflict free; a pixel-major layout saved an instruction but cost 40 %
+// extra shared-memory wavefronts when lanes read different features -- profiles/r01_e).
+// Per visit: one 64-bit node load, shift + IMAD + LDS.32, one AND, and an add-with-carry pair that folds "rank(x) > rank(thr)" into the index update
 // (add.cc of x's rank and the node's complemented rank sets the carry, addc consumes it) -- no predicates, no branches.
-__host__ __device__ constexpr int q_fpad(int F) { return F | 1; }
 
 // nrank = ~rank is what the node stores: xr + ~rank carries out of 32 bits exactly when
 // xr > rank, and addc folds that carry into idx + delta.
@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t q_step(uint32_t idx, uint32_t delta, uint32_
     return out;  // idx + delta + (xr > rank)
 }
 
-template <int J, bool COUNT>
+template <int P, int J, bool COUNT>
 __device__ __forceinline__ double traverse_q(const QForest& q, int t_begin, int t_end, int T, double sum,
                                              const uint32_t* __restrict__ rs, const ForestOut& o, long long row,
                                              unsigned& nvisit)
@@ -121,7 +121,7 @@ __device__ __forceinline__ double traverse_q(const QForest& q, int t_begin, int 
         for (int j = 0; j < J; ++j) {
             const int t = min(t0 + j, t_end - 1);
             const uint4 r = __ldg(reinterpret_cast<const uint4*>(q.roots + t));  // {rank, feat*4, child, -}
-            const uint32_t xr = *reinterpret_cast<const uint32_t*>(rsb + r.y);
+            const uint32_t xr = *reinterpret_cast<const uint32_t*>(rsb + r.y * P);
             idx[j] = q_step(r.z, 0u, r.x, xr);
             if (COUNT) nvisit += (r.x != ~kQLeafRank) ? 1u : 0u;
         }
@@ -133,7 +133,7 @@ __device__ __forceinline__ double traverse_q(const QForest& q, int t_begin, int 
             any = 0;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                const uint32_t xr = *reinterpret_cast<const uint32_t*>(rsb + (w[j].y >> kQDeltaBits));
+                const uint32_t xr = *reinterpret_cast<const uint32_t*>(rsb + (w[j].y >> kQDeltaBits) * P);
                 idx[j] = q_step(idx[j], w[j].y & (kQMaxDelta - 1), w[j].x, xr);
                 any |= w[j].y;
                 if (COUNT) nvisit += (w[j].y != 0) ? 1u : 0u;
@@ -153,7 +153,7 @@ __device__ __forceinline__ double traverse_q(const QForest& q, int t_begin, int 
 
 template <int P>
 __host__ __device__ constexpr size_t forest_q_smem_bytes(int F) {
-    return (size_t)q_fpad(F) * P * sizeof(uint32_t);
+    return (size_t)F * P * sizeof(uint32_t);
 }
 
 template <int P, int J, bool COUNT>
@@ -163,7 +163,7 @@ forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* 
                  int* __restrict__ na_flag)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* rs = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)threadIdx.x * q_fpad(F);
+    uint32_t* rs = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
     const long long p = (long long)blockIdx.x * P + threadIdx.x;
     const bool in_range = p < npix;
     bool has_na = false;
@@ -171,7 +171,7 @@ forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* 
         for (int f = 0; f < F; ++f) {
             const double v = X[(long long)f * ldx + p];
             has_na |= (v != v);
-            rs[f] = rank_of(q, f, v);
+            rs[f * P] = rank_of(q, f, v);
         }
     }
     unsigned nvisit = 0;
@@ -181,7 +181,7 @@ forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* 
             if (o.mean) o.mean[p] = na_real();
         } else {
             double sum = (t_begin > 0 && o.mean) ? o.mean[p] : 0.0;
-            sum = traverse_q<J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
+            sum = traverse_q<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
             if (o.mean) o.mean[p] = (t_end == T) ? sum / (double)T : sum;
         }
     }

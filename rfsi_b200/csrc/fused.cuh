@@ -91,13 +91,13 @@ __device__ __forceinline__ int16_t centi_i16(double v) {
 // feature row r of this thread's pixel: fp64 value (wide format) or its rank (compact format)
 template <int P, bool Q>
 __device__ __forceinline__ void put_feature(const FusedParams& a, unsigned char* smem_raw, int r, double v) {
-    if (Q) (reinterpret_cast<uint32_t*>(smem_raw) + (size_t)threadIdx.x * q_fpad(a.F))[r] = rank_of(a.q, r, v);
+    if (Q) (reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x)[r * P] = rank_of(a.q, r, v);
     else (reinterpret_cast<double*>(smem_raw) + threadIdx.x)[r * P] = v;
 }
 
 template <int P, bool Q>
 __host__ __device__ constexpr size_t fused_feature_bytes(int F) {
-    return Q ? (((size_t)q_fpad(F) * P * sizeof(uint32_t) + 15) & ~(size_t)15) : (size_t)(F + 1) * P * sizeof(double);
+    return Q ? (((size_t)F * P * sizeof(uint32_t) + 15) & ~(size_t)15) : (size_t)(F + 1) * P * sizeof(double);
 }
 
 template <int P, int J, bool COUNT, bool FALLBACK, bool Q>
@@ -239,9 +239,8 @@ fused_kernel(const __grid_constant__ FusedParams a)
         if (!Q) fs[a.F * P] = __longlong_as_double(0xFFF0000000000000LL);  // sentinel row: -inf
         double sum = a.t_begin > 0 ? a.acc[row] : 0.0;
         if (Q)
-            sum = traverse_q<J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
-                                       reinterpret_cast<const uint32_t*>(smem_raw) + (size_t)threadIdx.x * q_fpad(a.F),
-                                       o, row, nvisit);
+            sum = traverse_q<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
+                                          reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
         else
             sum = traverse_all<P, J, COUNT>(a.nodes, a.t_begin, a.t_end, a.T, a.F, sum, fs, o, row, nvisit);
         if (a.t_end == a.T) {
