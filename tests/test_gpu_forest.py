@@ -11,6 +11,7 @@ import oracle
 import rfsi_b200 as rb
 from rfsi_b200 import synth
 from rfsi_b200.forest import FlatForest
+from tests.util import same_mean, sum_mode  # noqa: F401  (runs every test in both summation modes)
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
@@ -29,8 +30,7 @@ def test_golden_mean_terminal_nodes_quantiles():
     model = rb.RangerForest(flat)
     X = f["X"]
     mean = rb.predict(model, X).predictions
-    np.testing.assert_allclose(mean, f["mean"], rtol=RTOL, atol=0)
-    np.testing.assert_array_equal(mean, f["mean"])                       # tree-order sum: bit-exact
+    same_mean(mean, f["mean"])
     np.testing.assert_array_equal(rb.predict(model, X, type="terminalNodes").predictions, f["term"])
     q = rb.predict(model, X, type="quantiles", quantiles=f["probs"]).predictions
     np.testing.assert_allclose(q, f["q"], rtol=RTOL, atol=0)
@@ -43,7 +43,7 @@ def test_predict_matches_columns_by_name_like_ranger():
     X = f["X"]
     df = pd.DataFrame({n: X[:, j] for j, n in enumerate(flat.feature_names)})
     df = df[df.columns[::-1]].assign(sim1=0.0, fold=True)               # shuffled + extra columns
-    np.testing.assert_array_equal(rb.predict(model, df).predictions, f["mean"])
+    same_mean(rb.predict(model, df).predictions, f["mean"])
     assert rb.predict(model, df, type="quantiles").predictions.shape == (X.shape[0], 3)   # default 0.1/0.5/0.9
 
 
@@ -77,7 +77,7 @@ def test_parity_many_shapes(F, T, npix):
     model = rb.RangerForest(flat)
     X = rng.normal(size=(npix, F))
     fo = flat.as_dict()
-    np.testing.assert_array_equal(rb.predict(model, X).predictions, oracle.forest_predict(fo, X, threads=8))
+    same_mean(rb.predict(model, X).predictions, oracle.forest_predict(fo, X, threads=8))
     np.testing.assert_array_equal(rb.predict(model, X, type="terminalNodes").predictions,
                                   oracle.forest_terminal_nodes(fo, X))
     probs = [0.0, 0.1, 0.25, 0.5, 0.75, 0.9, 1.0]
@@ -135,7 +135,7 @@ def test_forest_properties_at_simulation_size():
     assert mean.min() >= leaf_vals.min() and mean.max() <= leaf_vals.max()
     assert np.all(np.diff(q, axis=1) >= 0)                       # quantiles monotone in p
     sel = rng.choice(250_000, 5000, replace=False)
-    np.testing.assert_array_equal(mean[sel], oracle.forest_predict(flat.as_dict(), X[sel], threads=8))
+    same_mean(mean[sel], oracle.forest_predict(flat.as_dict(), X[sel], threads=8))
     np.testing.assert_array_equal(q[sel], oracle.forest_quantiles(flat.as_dict(), X[sel], [0.25, 0.5, 0.75], threads=8))
     # idempotence / determinism
     np.testing.assert_array_equal(mean, rb.predict(model, X).predictions)
@@ -153,7 +153,7 @@ def test_wide_and_compact_node_formats_agree(monkeypatch):
         monkeypatch.setenv("RFSI_B200_COMPACT", compact)
         model = rb.RangerForest(flat)
         assert model.info()["nodes"] > 0
-        np.testing.assert_array_equal(rb.predict(model, X).predictions, exp)
+        same_mean(rb.predict(model, X).predictions, exp)
         np.testing.assert_array_equal(rb.predict(model, X, type="quantiles", quantiles=probs).predictions, expq)
         np.testing.assert_array_equal(rb.predict(model, X, type="terminalNodes").predictions,
                                       oracle.forest_terminal_nodes(flat.as_dict(), X))
