@@ -50,6 +50,24 @@ struct ForestOut {
     long long ld_term;
 };
 
+// Quantile path: the leaf samples of one group of J trees, written as 128-bit stores when
+// the group is whole and 16-byte aligned (each thread owns a contiguous row of T samples).
+template <int J, class Idx>
+__device__ __forceinline__ void store_samples(const ForestOut& o, long long base, int remaining, const Idx (&idx)[J]) {
+    double sv[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) sv[j] = (j < remaining) ? __ldg(o.leaf_sample + idx[j]) : 0.0;
+    if (J % 2 == 0 && remaining >= J && (base & 1) == 0) {
+#pragma unroll
+        for (int j = 0; j < J; j += 2)
+            *reinterpret_cast<double2*>(o.samples + base + j) = make_double2(sv[j], sv[j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (j < remaining) o.samples[base + j] = sv[j];
+    }
+}
+
 // Walk trees [t_begin, t_end) for one pixel whose features are fs[f*P]; `sum` carries the
 // tree-order partial sum of the trees before and the updated sum is returned.
 //
@@ -85,10 +103,10 @@ __device__ __forceinline__ double traverse_all(const Node* __restrict__ nodes, i
         for (int j = 0; j < J; ++j) {
             if (t0 + j < t_end) {
                 sum += nd[j].val;
-                if (o.samples) o.samples[row * T + t0 + j] = o.leaf_sample[idx[j]];
                 if (o.terminal) o.terminal[(long long)(t0 + j) * o.ld_term + row] = o.leaf_rid[idx[j]];
             }
         }
+        if (o.samples) store_samples<J>(o, row * T + t0, t_end - t0, idx);
     }
     return sum;
 }
@@ -143,10 +161,10 @@ __device__ __forceinline__ double traverse_q(const QForest& q, int t_begin, int 
         for (int j = 0; j < J; ++j) {
             if (t0 + j < t_end) {
                 sum += __ldg(q.leaf_val + idx[j]);
-                if (o.samples) o.samples[row * T + t0 + j] = o.leaf_sample[idx[j]];
                 if (o.terminal) o.terminal[(long long)(t0 + j) * o.ld_term + row] = o.leaf_rid[idx[j]];
             }
         }
+        if (o.samples) store_samples<J>(o, row * T + t0, t_end - t0, idx);
     }
     return sum;
 }
