@@ -538,14 +538,21 @@ struct CellsWs {
     int32_t* cursor = nullptr;
     double2* sxy = nullptr;
     int32_t* sid = nullptr;
+    // location sort (explicit coordinates only)
+    int32_t* lcount = nullptr;
+    int32_t* lcursor = nullptr;
+    int32_t* perm = nullptr;
 };
 int cells_G(int S) { return std::max(1, std::min(1024, (int)std::ceil(std::sqrt((double)std::max(S, 1) / 3.0)))); }
-size_t cells_ws_bytes(int S) {
+// npix_sort: number of explicit locations that will be cell-sorted with this workspace (0 = none)
+size_t cells_ws_bytes(int S, int64_t npix_sort) {
     const size_t G2 = (size_t)cells_G(S) * cells_G(S);
-    return 256 + align_up((G2 + 1) * 4, 256) + align_up(G2 * 4, 256) + align_up((size_t)std::max(S, 1) * 16, 256) +
-           align_up((size_t)std::max(S, 1) * 4, 256);
+    size_t b = 256 + align_up((G2 + 1) * 4, 256) + align_up(G2 * 4, 256) + align_up((size_t)std::max(S, 1) * 16, 256) +
+               align_up((size_t)std::max(S, 1) * 4, 256);
+    if (npix_sort > 0) b += align_up((G2 + 1) * 4, 256) + align_up(G2 * 4, 256) + align_up((size_t)npix_sort * 4, 256);
+    return b;
 }
-CellsWs carve_cells(void* ws, int S) {
+CellsWs carve_cells(void* ws, int S, int64_t npix_sort) {
     const size_t G2 = (size_t)cells_G(S) * cells_G(S);
     char* p = reinterpret_cast<char*>(ws);
     CellsWs c;
@@ -553,7 +560,12 @@ CellsWs carve_cells(void* ws, int S) {
     c.cell_start = reinterpret_cast<int32_t*>(p); p += align_up((G2 + 1) * 4, 256);
     c.cursor = reinterpret_cast<int32_t*>(p); p += align_up(G2 * 4, 256);
     c.sxy = reinterpret_cast<double2*>(p); p += align_up((size_t)std::max(S, 1) * 16, 256);
-    c.sid = reinterpret_cast<int32_t*>(p);
+    c.sid = reinterpret_cast<int32_t*>(p); p += align_up((size_t)std::max(S, 1) * 4, 256);
+    if (npix_sort > 0) {
+        c.lcount = reinterpret_cast<int32_t*>(p); p += align_up((G2 + 1) * 4, 256);
+        c.lcursor = reinterpret_cast<int32_t*>(p); p += align_up(G2 * 4, 256);
+        c.perm = reinterpret_cast<int32_t*>(p);
+    }
     return c;
 }
 int cells_min_S() { return env_int("RFSI_B200_CELLS_MIN", 1024); }
@@ -565,7 +577,7 @@ int build_cells(const double2* xy, int S, const CellsWs& c, cudaStream_t st) {
 }
 
 template <int MODE>
-int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, int k, const double* st_z, int rm_dupl,
+int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, int c_S, int k, const double* st_z, int rm_dupl,
                      double* out_a, double* out_b, int32_t* out_i, int64_t ld, int* warn, int* na_flag,
                      cudaStream_t stream)
 {
@@ -575,6 +587,18 @@ int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, int k, co
     auto kern = knn_cells_kernel<kKnnP, MODE>;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tile2d = (!L.x && L.pix_begin % L.ncol == 0 && L.ncol >= 16) ? 1 : 0;
+    const int32_t* perm = nullptr;
+    if (L.x && c.perm && npix <= 0x7fffffff) {  // unordered explicit locations: visit them cell by cell
+        const size_t G2 = (size_t)cells_G(c_S) * cells_G(c_S);
+        CU_TRY(cudaMemsetAsync(c.lcount, 0, (G2 + 1) * 4, stream));
+        const unsigned g = (unsigned)((npix + 255) / 256);
+        loc_cell_count_kernel<<<g, 256, 0, stream>>>(L, npix, c.hdr, c.lcount);
+        scan_cells_kernel<<<1, 1024, 0, stream>>>(c.lcount, c.hdr, c.lcursor);
+        loc_cell_scatter_kernel<<<g, 256, 0, stream>>>(L, npix, c.hdr, c.lcursor, c.perm);
+        g_launches.fetch_add(3, std::memory_order_relaxed);
+        CU_TRY(cudaGetLastError());
+        perm = c.perm;
+    }
     long long tiles_per_row = 0, ntiles;
     if (tile2d) {
         tiles_per_row = (L.ncol + 15) / 16;
@@ -586,7 +610,8 @@ int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, int k, co
     {
         ProfScope ps(MODE == KNN_RAW ? PROF_KNN_RAW : PROF_KNN_FINAL, stream);
         kern<<<(unsigned)ntiles, kKnnP, smem, stream>>>(L, npix, c.hdr, c.cell_start, c.sxy, c.sid, k, st_z, rm_dupl,
-                                                         out_a, out_b, out_i, ld, warn, na_flag, tile2d, tiles_per_row);
+                                                         out_a, out_b, out_i, ld, warn, na_flag, tile2d, tiles_per_row,
+                                                         perm);
     }
     count_launch();
     CU_TRY(cudaGetLastError());
@@ -763,12 +788,12 @@ extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, i
     int rc;
     if (nobs >= cells_min_S()) {
         void* cw = nullptr;
-        CU_TRY(cudaMallocAsync(&cw, cells_ws_bytes(nobs), st));
-        const CellsWs c = carve_cells(cw, nobs);
+        CU_TRY(cudaMallocAsync(&cw, cells_ws_bytes(nobs, npix), st));
+        const CellsWs c = carve_cells(cw, nobs, npix);
         rc = build_cells(xy, nobs, c, st);
         if (rc >= 0)
-            rc = launch_knn_cells<KNN_FINAL>(L, npix, c, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx, npix,
-                                             warn_flag, nullptr, st);
+            rc = launch_knn_cells<KNN_FINAL>(L, npix, c, nobs, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx,
+                                             npix, warn_flag, nullptr, st);
         cudaFreeAsync(cw, st);
     } else {
         rc = launch_knn<KNN_FINAL>(L, npix, xy, nobs, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx, npix,
@@ -801,16 +826,18 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
     if (nobs > 0) CU_TRY(cudaMemcpy(d_z.p, obs_z, sizeof(double) * nobs, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemset(d_flags.p, 0, 2 * sizeof(int)));
     const bool use_cells = nobs >= cells_min_S();
-    DevBuf d_cells;
-    CellsWs cells;
+    const int64_t chunk = std::min<int64_t>(npix, 1 << 20);
+    DevBuf d_cells[2];
+    CellsWs cells[2];
     if (use_cells) {
-        RF_TRY(d_cells.alloc(cells_ws_bytes(nobs)));
-        cells = carve_cells(d_cells.p, nobs);
-        RF_TRY(build_cells(d_xy.as<double2>(), nobs, cells, nullptr));
+        for (int s = 0; s < (npix <= chunk ? 1 : 2); ++s) {   // one per stream slot: the location sort is per chunk
+            RF_TRY(d_cells[s].alloc(cells_ws_bytes(nobs, chunk)));
+            cells[s] = carve_cells(d_cells[s].p, nobs, chunk);
+            RF_TRY(build_cells(d_xy.as<double2>(), nobs, cells[s], nullptr));
+        }
         CU_TRY(cudaStreamSynchronize(nullptr));
     }
 
-    const int64_t chunk = std::min<int64_t>(npix, 1 << 20);
     DevBuf d_lx[2], d_ly[2], d_dist[2], d_obs[2], d_idx[2];
     Stream st[2];
     for (int s = 0; s < 2; ++s) {
@@ -831,7 +858,7 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
         CU_TRY(cudaMemcpyAsync(d_ly[slot].p, loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
         LocSpec L{d_lx[slot].as<double>(), d_ly[slot].as<double>(), 0, 0, 0, 0, 1, 0};
         if (use_cells)
-            RF_TRY(launch_knn_cells<KNN_FINAL>(L, cur, cells, n_obs + 1, d_z.as<double>(), rm_dupl,
+            RF_TRY(launch_knn_cells<KNN_FINAL>(L, cur, cells[slot], nobs, n_obs + 1, d_z.as<double>(), rm_dupl,
                                                d_dist[slot].as<double>(), d_obs[slot].as<double>(),
                                                out_idx ? d_idx[slot].as<int32_t>() : nullptr, cur, d_flags.as<int>(),
                                                d_flags.as<int>() + 1, s));
@@ -993,6 +1020,7 @@ struct FusedPlan {
     int KC = 0;
     int db = 1;               // days per launch
     int64_t rows = 0;         // npix * db
+    int64_t npix_plan = 0;    // pixels the workspace was sized for
     bool want_q = false;
     // workspace offsets
     size_t off_cand_d2 = 0, off_cand_id = 0, off_xy = 0, off_cells = 0, off_fb = 0, off_acc = 0, off_misc = 0, off_samples = 0, off_skip = 0,
@@ -1044,11 +1072,12 @@ FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_
     while (db > 1 && ((npix + kFusedP - 1) / kFusedP + 64) * db > (int64_t)0x7fffffff) --db;
     pl.db = db;
     pl.rows = npix * db;
+    pl.npix_plan = npix;
     size_t o = 0;
     pl.off_cand_d2 = o; o += align_up(sizeof(double) * (size_t)pl.KC * npix, 256);
     pl.off_cand_id = o; o += align_up(sizeof(int32_t) * (size_t)pl.KC * npix, 256);
     pl.off_xy = o; o += align_up(sizeof(double2) * (size_t)std::max(a->nobs, 1), 256);
-    pl.off_cells = o; o += align_up(cells_ws_bytes(a->nobs), 256);
+    pl.off_cells = o; o += align_up(cells_ws_bytes(a->nobs, a->loc_x ? npix : 0), 256);
     pl.off_fb = o; o += align_up(sizeof(int2) * (size_t)pl.rows, 256);
     pl.off_acc = o; o += align_up(sizeof(double) * (size_t)pl.rows, 256);
     pl.off_misc = o; o += 256;  // fb_count, na_flag
@@ -1124,10 +1153,10 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         }
         // geometry pass: the KC nearest of ALL stations, once per pixel
         if (a->nobs >= cells_min_S()) {
-            const CellsWs c = carve_cells(ws + pl.off_cells, a->nobs);
+            const CellsWs c = carve_cells(ws + pl.off_cells, a->nobs, a->loc_x ? pl.npix_plan : 0);
             RF_TRY(build_cells(xy, a->nobs, c, st));
-            RF_TRY(launch_knn_cells<KNN_RAW>(L, a->npix, c, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id, a->npix,
-                                             nullptr, nullptr, st));
+            RF_TRY(launch_knn_cells<KNN_RAW>(L, a->npix, c, a->nobs, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id,
+                                             a->npix, nullptr, nullptr, st));
         } else {
             RF_TRY(launch_knn<KNN_RAW>(L, a->npix, xy, a->nobs, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id, a->npix,
                                        nullptr, nullptr, st));

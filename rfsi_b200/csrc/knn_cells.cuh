@@ -110,6 +110,64 @@ build_cells_kernel(const double2* __restrict__ xy, int S, int Gmax, CellHeader* 
     }
 }
 
+// ---- explicit locations in arbitrary order: visit them cell by cell ------------------------
+// A tile of 128 consecutive locations of an unordered list can span the whole grid, which
+// would turn the ring search into a full scan.  Locations are therefore counting-sorted by
+// their grid cell first (perm), and tiles are cut from the sorted order; outputs still go
+// to the original positions.
+__global__ void loc_cell_count_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
+                                      int32_t* __restrict__ counts /* [G2+1], zeroed */)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const CellHeader h = *hdr;
+    double px, py;
+    get_loc(L, p, px, py);
+    const int c = cell_coord(py, h.y0, h.inv_cs, h.G) * h.G + cell_coord(px, h.x0, h.inv_cs, h.G);
+    atomicAdd(&counts[c + 1], 1);
+}
+
+// single CTA: counts[1..n] -> inclusive prefix sums (counts[0] stays 0); cursor[i] = counts[i]
+__global__ void __launch_bounds__(1024)
+scan_cells_kernel(int32_t* __restrict__ counts, const CellHeader* __restrict__ hdr, int32_t* __restrict__ cursor)
+{
+    __shared__ int sbuf[1024];
+    __shared__ int carry;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int n = hdr->G * hdr->G;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 1; base <= n; base += nt) {
+        const int i = base + tid;
+        sbuf[tid] = (i <= n) ? counts[i] : 0;
+        __syncthreads();
+        for (int o = 1; o < nt; o <<= 1) {
+            const int t = (tid >= o) ? sbuf[tid - o] : 0;
+            __syncthreads();
+            sbuf[tid] += t;
+            __syncthreads();
+        }
+        const int incl = sbuf[tid] + carry;
+        if (i <= n) counts[i] = incl;
+        __syncthreads();
+        if (tid == nt - 1) carry = incl;
+        __syncthreads();
+    }
+    for (int c = tid; c < n; c += nt) cursor[c] = counts[c];
+}
+
+__global__ void loc_cell_scatter_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
+                                        int32_t* __restrict__ cursor, int32_t* __restrict__ perm)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const CellHeader h = *hdr;
+    double px, py;
+    get_loc(L, p, px, py);
+    const int c = cell_coord(py, h.y0, h.inv_cs, h.G) * h.G + cell_coord(px, h.x0, h.inv_cs, h.G);
+    perm[atomicAdd(&cursor[c], 1)] = (int32_t)p;
+}
+
 template <int P>
 __host__ __device__ constexpr size_t knn_cells_smem_bytes(int k) {
     return (size_t)k * P * (sizeof(double) + sizeof(int32_t));
@@ -119,8 +177,11 @@ __host__ __device__ constexpr size_t knn_cells_smem_bytes(int k) {
 // explicit form -> consecutive locations.
 template <int P>
 __device__ __forceinline__ long long knn_pixel_of_thread(const LocSpec& L, long long npix, int tile2d,
-                                                         long long tiles_per_row) {
-    if (!tile2d) return (long long)blockIdx.x * P + threadIdx.x;
+                                                         long long tiles_per_row, const int32_t* __restrict__ perm) {
+    if (!tile2d) {
+        const long long i = (long long)blockIdx.x * P + threadIdx.x;
+        return (perm != nullptr && i < npix) ? (long long)perm[i] : i;
+    }
     const long long tile = blockIdx.x;
     const long long tr = tile / tiles_per_row, tc = tile - tr * tiles_per_row;
     const long long first_row = L.pix_begin / L.ncol;
@@ -137,7 +198,7 @@ knn_cells_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
                  const int32_t* __restrict__ sid, int k, const double* __restrict__ st_z, int rm_dupl,
                  double* __restrict__ out_a, double* __restrict__ out_b, int32_t* __restrict__ out_i,
                  long long ld, int* __restrict__ warn, int* __restrict__ na_flag, int tile2d,
-                 long long tiles_per_row)
+                 long long tiles_per_row, const int32_t* __restrict__ perm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* ld2 = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
@@ -147,7 +208,7 @@ knn_cells_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
 
     const CellHeader h = *hdr;
     const int G = h.G;
-    const long long p = knn_pixel_of_thread<P>(L, npix, tile2d, tiles_per_row);
+    const long long p = knn_pixel_of_thread<P>(L, npix, tile2d, tiles_per_row, perm);
     const bool in_range = p >= 0 && p < npix;
     double px = 0.0, py = 0.0;
     if (in_range) get_loc(L, p, px, py);
