@@ -189,6 +189,13 @@ class RangerForest:
     def from_ranger(cls, model: dict) -> "RangerForest":
         return cls(flatten_ranger(model))
 
+    @classmethod
+    def from_rda(cls, path, name: Optional[str] = None) -> "RangerForest":
+        """load("../models/RFSI.rda") without R (temp_croatia/2_predictions.R:59): the ranger
+        object saved in an .rda/.RData/.rds file, by variable name or the only one in the file."""
+        from . import rda
+        return cls(flatten_ranger(rda.load_ranger(path, name)))
+
     @property
     def handle(self):
         if self._h is None:

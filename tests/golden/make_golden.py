@@ -68,7 +68,32 @@ def forest_small():
                         **{k: v for k, v in fo.items() if v is not None})
 
 
+def knn_croatia_real():
+    """Real station geometry: temp_croatia/temp_data/stfdf.rda (157 stations, UTM33 metres) on
+    day 5 (the first mapped slice, 2_predictions.R:65), stations with TEMP observed that day
+    (2_predictions.R:122-125), against 8 rows of the dem.tif grid (490 columns, 1 km cells,
+    tie-point 359641 / 5156149), n.obs = 10 (2_predictions.R:159).  Inputs come from the
+    reference's data file through rfsi_b200/rda.py; expected outputs from the oracle."""
+    from rfsi_b200 import rda
+    ref = Path("/root/reference/temp_croatia/temp_data/stfdf.rda")
+    st = rda.read_rda(ref)["stfdf"]
+    xy = np.asarray(st.attrs["sp"].attrs["coords"], dtype=np.float64)
+    temp = np.asarray(st.attrs["data"]["TEMP"], dtype=np.float64).reshape(366, 157)   # space index runs fastest
+    day = 4
+    ok = ~np.isnan(temp[day])
+    grid = (359641.0 + 500.0, 5156149.0 - 500.0, 1000.0, -1000.0, 490)
+    p = np.arange(200 * 490, 208 * 490)
+    loc = np.stack([grid[0] + (p % 490) * grid[2], grid[1] + (p // 490) * grid[3]], axis=1)
+    d, o, i, _ = oracle.near_obs(loc, xy[ok], temp[day][ok], 10)
+    d2, _, i2, _ = oracle.near_obs(loc, xy[ok], temp[day][ok], 10, kdtree=True, nthreads=2)
+    assert np.array_equal(d, d2) and np.array_equal(i, i2)
+    np.savez_compressed(OUT / "knn_croatia_real.npz", grid=np.array(grid), pix_begin=200 * 490, npix=len(p),
+                        obs_xy=xy, temp_days=temp[:8], day=day, n_obs=10, dist=d, obs=o, idx=i)
+
+
 if __name__ == "__main__":
+    if Path("/root/reference").exists():
+        knn_croatia_real()
     knn_lattice()
     knn_realgeom()
     forest_small()

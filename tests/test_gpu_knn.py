@@ -164,3 +164,16 @@ def test_cell_grid_search_is_exact_in_awkward_geometries(case, monkeypatch):
     d, o, i = _gpu(loc, obs, z, n)
     ed, eo, ei, _ = oracle.near_obs(loc, obs, z, n, kdtree=True, nthreads=8)
     _same(d, ed); _same(i, ei); _same(o, eo)
+
+
+def test_golden_real_croatia_station_geometry():
+    """Real inputs (stfdf.rda stations, dem.tif grid geometry, day 5), oracle outputs."""
+    g = np.load(GOLD / "knn_croatia_real.npz")
+    x0, y0, dx, dy, ncol = g["grid"]
+    p = np.arange(int(g["pix_begin"]), int(g["pix_begin"]) + int(g["npix"]))
+    loc = np.stack([x0 + (p % int(ncol)) * dx, y0 + (p // int(ncol)) * dy], axis=1)
+    z = g["temp_days"][int(g["day"])]
+    ok = ~np.isnan(z)
+    assert 140 <= ok.sum() <= 157
+    d, o, i = _gpu(loc, g["obs_xy"][ok], z[ok], int(g["n_obs"]))
+    _same(d, g["dist"]); _same(i, g["idx"]); _same(o, g["obs"])

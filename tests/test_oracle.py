@@ -201,3 +201,16 @@ def test_oracle_reproduces_golden_vectors():
     np.testing.assert_array_equal(oracle.forest_terminal_nodes(fo, f["X"]), f["term"])
     np.testing.assert_array_equal(oracle.forest_quantiles(fo, f["X"], f["probs"]), f["q"])
     np.testing.assert_array_equal(oracle.forest_quantiles(fo, f["X"], f["probs"], threads=2), f["q"])
+
+
+def test_oracle_reproduces_real_geometry_golden():
+    g = np.load(GOLD / "knn_croatia_real.npz")
+    x0, y0, dx, dy, ncol = g["grid"]
+    p = np.arange(int(g["pix_begin"]), int(g["pix_begin"]) + int(g["npix"]))
+    loc = np.stack([x0 + (p % int(ncol)) * dx, y0 + (p // int(ncol)) * dy], axis=1)
+    z = g["temp_days"][int(g["day"])]
+    ok = ~np.isnan(z)
+    d, o, i, _ = oracle.near_obs(loc, g["obs_xy"][ok], z[ok], int(g["n_obs"]), kdtree=True, nthreads=2)
+    np.testing.assert_array_equal(d, g["dist"]); np.testing.assert_array_equal(i, g["idx"])
+    # median nearest-station distance of the real network is ~12.7 km
+    assert 5e3 < np.median(g["dist"][:, 0]) < 4e4
