@@ -146,10 +146,12 @@ def workload_config(args, case, flat, cpu=False):
     return {
         "workload": "c5 scale-up: 10^4 stations, 10^4x10^4 raster (band of rows per step), n.obs=20, "
                     f"{args.trees} trees, F=43 (3 daily covariates + 20 dist + 20 obs), 2% stations missing/day",
-        "pixels_per_step_per_gpu": args.rows * case.ncol if not cpu else None,
-        "days_per_step": args.days if not cpu else 1,
+        "pixels_per_step_per_gpu": args.rows * case.ncol,
+        "days_per_step": args.days,
         "forest_nodes": int(flat.node_offsets[-1]),
         "cpu_port": "kd-tree near.obs + threaded ranger-style descent (oracle/cpu_baseline.cpp); R/ranger not installable here",
+        **({"reference_step": "a bounded sample of this workload (see cpu_baseline.sample): 1 day of a band of rows"}
+           if cpu else {}),
     }
 
 

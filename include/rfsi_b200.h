@@ -79,6 +79,19 @@ int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix
                           int32_t* warn_flag /* device int, nullable */,
                           int device, void* stream);
 
+/* near.obs for EVERY day of a station table in one call -- the per-day feature table, above
+ * all the training tables built with
+ *   foreach(t=time) near.obs(locations=day_df, observations=day_df, zcol, n.obs)
+ * temp_croatia/1_models.R:1034-1047, prcp_catalonia/4_prcp_case_study_catalonia_RK.R:1699-1712.
+ * obs_z is ndays x nobs (row d = day d, NA = no observation).  Per day only that day's
+ * observed stations are searched (the scripts' !is.na filter).  loc_x == NULL: locations are
+ * the stations themselves (npix = nobs; a row whose own station is silent that day is NA).
+ * out_dist / out_obs / out_idx (nullable, 1-based ORIGINAL station index): [ndays][n_obs][npix]. */
+int rfsi_near_obs_days_f64(const double* loc_x, const double* loc_y, int64_t npix,
+                           const double* obs_x, const double* obs_y, const double* obs_z,
+                           int32_t nobs, int32_t ndays, int32_t n_obs, int32_t rm_dupl,
+                           double* out_dist, double* out_obs, int32_t* out_idx, int device);
+
 /* ---- forest import --------------------------------------------------------------
  * The ranger model object saved at temp_croatia/1_models.R:1056-1063 and loaded at
  * temp_croatia/2_predictions.R:59 / prcp_catalonia/5_prcp_prediction.R:233, flattened

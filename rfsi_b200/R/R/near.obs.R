@@ -20,3 +20,17 @@ near.obs <- function(locations, locations.x.y = c(1, 2), observations, observati
   ob <- as.data.frame(res$obs); names(ob) <- paste0("obs", seq_len(n.obs))
   cbind(dist, ob)
 }
+
+# near.obs.days -- all days of a station table in one engine call: what
+#   foreach(t = time) %dopar% near.obs(locations = day_df, observations = day_df, zcol, n.obs)
+# builds day by day (temp_croatia/1_models.R:1034-1047).  z: stations x days matrix (NA = no
+# observation that day).  locations = NULL: the stations themselves (own observation excluded).
+# Returns list(dist, obs): arrays [location, neighbour, day].
+near.obs.days <- function(observations.xy, z, n.obs = 10, locations.xy = NULL, device = 0L) {
+  oxy <- unname(as.matrix(observations.xy)); storage.mode(oxy) <- "double"
+  z <- unname(as.matrix(z)); storage.mode(z) <- "double"
+  lxy <- if (is.null(locations.xy)) NULL else { m <- unname(as.matrix(locations.xy)); storage.mode(m) <- "double"; m }
+  res <- .Call(C_rfsi_near_obs_days, lxy, oxy, z, as.integer(n.obs), as.integer(device))
+  npix <- if (is.null(lxy)) nrow(oxy) else nrow(lxy)
+  list(dist = array(res[[1]], c(npix, n.obs, ncol(z))), obs = array(res[[2]], c(npix, n.obs, ncol(z))))
+}

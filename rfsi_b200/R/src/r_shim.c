@@ -58,6 +58,27 @@ SEXP C_rfsi_near_obs(SEXP loc_xy, SEXP obs_xy, SEXP obs_z, SEXP n_obs, SEXP rm_d
     return out;
 }
 
+/* near.obs for every day at once (training tables, temp_croatia/1_models.R:1034-1047):
+ * loc_xy NULL -> locations are the stations; obs_z nobs x ndays (column d = day d, NA = silent)
+ * -> list(dist, obs) each a numeric array npix x n.obs x ndays */
+SEXP C_rfsi_near_obs_days(SEXP loc_xy, SEXP obs_xy, SEXP obs_z, SEXP n_obs, SEXP device)
+{
+    const R_xlen_t nobs = Rf_nrows(obs_xy);
+    const R_xlen_t npix = (loc_xy == R_NilValue) ? nobs : Rf_nrows(loc_xy);
+    const int ndays = Rf_ncols(obs_z), n = Rf_asInteger(n_obs);
+    SEXP dist = PROTECT(Rf_allocVector(REALSXP, npix * n * ndays));   /* [day][j][pixel] == npix x n x ndays */
+    SEXP obs = PROTECT(Rf_allocVector(REALSXP, npix * n * ndays));
+    const double* l = (loc_xy == R_NilValue) ? NULL : REAL(loc_xy);
+    const double* o = REAL(obs_xy);
+    check_rc(rfsi_near_obs_days_f64(l, l ? l + npix : NULL, (int64_t)npix, o, o + nobs, REAL(obs_z), (int32_t)nobs,
+                                    ndays, n, 1, REAL(dist), REAL(obs), NULL, Rf_asInteger(device)));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, dist);
+    SET_VECTOR_ELT(out, 1, obs);
+    UNPROTECT(3);
+    return out;
+}
+
 static void forest_finalizer(SEXP ptr) {
     rfsi_forest_t* f = (rfsi_forest_t*)R_ExternalPtrAddr(ptr);
     if (f) {
@@ -165,6 +186,7 @@ SEXP C_rfsi_pred_fused(SEXP h, SEXP loc_xy, SEXP obs_xy, SEXP obs_z, SEXP n_obs,
 
 static const R_CallMethodDef call_methods[] = {
     {"C_rfsi_near_obs", (DL_FUNC)&C_rfsi_near_obs, 6},
+    {"C_rfsi_near_obs_days", (DL_FUNC)&C_rfsi_near_obs_days, 5},
     {"C_rfsi_forest_new", (DL_FUNC)&C_rfsi_forest_new, 7},
     {"C_rfsi_predict", (DL_FUNC)&C_rfsi_predict, 4},
     {"C_rfsi_pred_fused", (DL_FUNC)&C_rfsi_pred_fused, 9},

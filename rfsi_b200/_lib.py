@@ -76,6 +76,8 @@ _SIGNATURES = [
     ("rfsi_near_obs_f64", C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int]),
     ("rfsi_dev_near_obs_f64", C.c_int,
      [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int, _P]),
+    ("rfsi_near_obs_days_f64", C.c_int,
+     [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int]),
     ("rfsi_forest_create", C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(_P)]),
     ("rfsi_forest_destroy", None, [_P]),
     ("rfsi_forest_upload", C.c_int, [_P, C.c_int]),

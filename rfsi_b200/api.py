@@ -92,6 +92,36 @@ def near_obs(locations, observations, zcol=2, n_obs: int = 10, locations_x_y=(0,
     return (out, idx.T) if return_idx else out
 
 
+def near_obs_days(obs_xy, obs_z, n_obs: int, locations=None, rm_dupl: bool = True, return_idx: bool = False,
+                  device: int = 0):
+    """near.obs for every day of a station table in one call (rfsi_near_obs_days_f64).
+
+    obs_z: (ndays, nobs), NaN = no observation that day.  locations=None: the stations
+    themselves (the training-table shape of temp_croatia/1_models.R:1034-1047: each row's
+    own observation is excluded; rows of silent stations are NA).
+    Returns dist, obs of shape (ndays, npix, n_obs) (+ idx, 1-based original station index).
+    """
+    obs_xy = np.asarray(obs_xy, dtype=np.float64)
+    obs_z = _f64(np.atleast_2d(obs_z))
+    ndays, nobs = obs_z.shape
+    if obs_xy.shape[0] != nobs:
+        raise ValueError("obs_z must be (ndays, nobs) with nobs == len(obs_xy)")
+    ox, oy = _f64(obs_xy[:, 0]), _f64(obs_xy[:, 1])
+    lx = ly = None
+    npix = nobs
+    if locations is not None:
+        loc = np.asarray(locations, dtype=np.float64)
+        lx, ly = _f64(loc[:, 0]), _f64(loc[:, 1])
+        npix = loc.shape[0]
+    dist = np.empty((ndays, n_obs, npix)); val = np.empty((ndays, n_obs, npix))
+    idx = np.empty((ndays, n_obs, npix), dtype=np.int32) if return_idx else None
+    rc = _lib.load().rfsi_near_obs_days_f64(_ptr(lx), _ptr(ly), npix, _ptr(ox), _ptr(oy), _ptr(obs_z), nobs, ndays,
+                                           int(n_obs), 1 if rm_dupl else 0, _ptr(dist), _ptr(val), _ptr(idx), device)
+    _lib.check(rc)          # too-few rows are simply NA here (complete.cases drops them, 1_models.R:1003)
+    out = (dist.transpose(0, 2, 1), val.transpose(0, 2, 1))
+    return out + (idx.transpose(0, 2, 1),) if return_idx else out
+
+
 class Prediction:
     """What predict.ranger returns: a list with $predictions (vector or npix x Q matrix)."""
 

@@ -18,6 +18,7 @@
 
 #include "../../include/rfsi_b200.h"
 #include "common.cuh"
+#include "features.cuh"
 #include "forest.cuh"
 #include "fused.cuh"
 #include "knn.cuh"
@@ -882,6 +883,107 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
     if (flags[1]) return fail(RFSI_E_NA_INPUT, "near_obs: a location has an NA coordinate");
     if (flags[0]) {
         g_err = "near_obs: fewer observations than n.obs(+1); missing neighbours are NA";
+        return RFSI_W_TOO_FEW_OBS;
+    }
+    return RFSI_OK;
+}
+
+// near.obs for all days of a station table (the per-day feature / training table)
+extern "C" int rfsi_near_obs_days_f64(const double* loc_x, const double* loc_y, int64_t npix, const double* obs_x,
+                                      const double* obs_y, const double* obs_z, int32_t nobs, int32_t ndays,
+                                      int32_t n_obs, int32_t rm_dupl, double* out_dist, double* out_obs,
+                                      int32_t* out_idx, int device)
+{
+    const bool loc_is_obs = (loc_x == nullptr);
+    if (loc_is_obs) { if (loc_y) return fail(RFSI_E_ARG, "near_obs_days: loc_x/loc_y go together"); npix = nobs; }
+    if (npix < 0 || nobs < 0 || ndays < 1 || n_obs < 1 || n_obs > 64)
+        return fail(RFSI_E_ARG, "near_obs_days: need npix, nobs >= 0, ndays >= 1, 1 <= n.obs <= 64");
+    if (npix > 0 && (!out_dist || !out_obs)) return fail(RFSI_E_ARG, "near_obs_days: NULL output");
+    if (nobs > 0 && (!obs_x || !obs_y || !obs_z)) return fail(RFSI_E_ARG, "near_obs_days: NULL observations");
+    for (int32_t s = 0; s < nobs; ++s)
+        if (obs_x[s] != obs_x[s] || obs_y[s] != obs_y[s])
+            return fail(RFSI_E_NA_INPUT, "near_obs_days: observation %d has an NA coordinate", s + 1);
+    RF_TRY(use_device(device));
+    if (npix == 0) return RFSI_OK;
+    const int S = nobs;
+    int worst_missing = 0;
+    for (int d = 0; d < ndays; ++d) {
+        int miss = 0;
+        for (int s = 0; s < S; ++s) miss += std::isnan(obs_z[(size_t)d * S + s]) ? 1 : 0;
+        worst_missing = std::max(worst_missing, miss);
+    }
+    const int k = n_obs + 1;
+    const int KC = std::max(1, std::min(std::max(S, 1), k + std::min(worst_missing, 16)));
+    std::vector<double2> xy((size_t)std::max(S, 1));
+    for (int32_t s = 0; s < S; ++s) xy[s] = make_double2(obs_x[s], obs_y[s]);
+    const int64_t chunk = std::min<int64_t>(npix, 1 << 18);
+    const int db = (int)std::max<int64_t>(1, std::min<int64_t>(ndays, (int64_t(256) << 20) / (chunk * n_obs * 20)));
+    DevBuf d_xy, d_z, d_lx, d_ly, d_cd2, d_cid, d_cells, d_dist, d_obs, d_idx, d_flags;
+    Stream st;
+    RF_TRY(st.create());
+    RF_TRY(d_xy.alloc(sizeof(double2) * xy.size()));
+    RF_TRY(d_z.alloc(sizeof(double) * (size_t)std::max(S, 1) * ndays));
+    RF_TRY(d_lx.alloc(sizeof(double) * chunk)); RF_TRY(d_ly.alloc(sizeof(double) * chunk));
+    RF_TRY(d_cd2.alloc(sizeof(double) * chunk * KC)); RF_TRY(d_cid.alloc(sizeof(int32_t) * chunk * KC));
+    RF_TRY(d_dist.alloc(sizeof(double) * chunk * n_obs * db)); RF_TRY(d_obs.alloc(sizeof(double) * chunk * n_obs * db));
+    if (out_idx) RF_TRY(d_idx.alloc(sizeof(int32_t) * chunk * n_obs * db));
+    RF_TRY(d_flags.alloc(16));
+    const bool use_cells = S >= cells_min_S();
+    CellsWs cells;
+    if (use_cells) { RF_TRY(d_cells.alloc(cells_ws_bytes(S, chunk))); cells = carve_cells(d_cells.p, S, chunk); }
+    CU_TRY(cudaMemcpy(d_xy.p, xy.data(), sizeof(double2) * xy.size(), cudaMemcpyHostToDevice));
+    if (S > 0) CU_TRY(cudaMemcpy(d_z.p, obs_z, sizeof(double) * (size_t)S * ndays, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemset(d_flags.p, 0, 16));
+    RF_TRY(pool_ready());
+    cudaStream_t s = st.s;
+    if (use_cells) RF_TRY(build_cells(d_xy.as<double2>(), S, cells, s));
+    for (int64_t p0 = 0; p0 < npix; p0 += chunk) {
+        const int64_t cur = std::min(chunk, npix - p0);
+        CU_TRY(cudaMemcpyAsync(d_lx.p, (loc_is_obs ? obs_x : loc_x) + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(d_ly.p, (loc_is_obs ? obs_y : loc_y) + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+        LocSpec L{d_lx.as<double>(), d_ly.as<double>(), 0, 0, 0, 0, 1, 0};
+        if (use_cells)
+            RF_TRY(launch_knn_cells<KNN_RAW>(L, cur, cells, S, KC, nullptr, 0, d_cd2.as<double>(), nullptr,
+                                             d_cid.as<int32_t>(), cur, nullptr, d_flags.as<int>() + 1, s));
+        else
+            RF_TRY(launch_knn<KNN_RAW>(L, cur, d_xy.as<double2>(), S, KC, nullptr, 0, d_cd2.as<double>(), nullptr,
+                                       d_cid.as<int32_t>(), cur, nullptr, d_flags.as<int>() + 1, s));
+        for (int d0 = 0; d0 < ndays; d0 += db) {
+            const int nd = std::min(db, ndays - d0);
+            FeatureParams fp;
+            memset(&fp, 0, sizeof fp);
+            fp.loc = L; fp.npix = cur; fp.ndays = nd;
+            fp.cand_d2 = d_cd2.as<double>(); fp.cand_id = d_cid.as<int32_t>(); fp.ld_cand = cur;
+            fp.KC = KC; fp.exhaustive = KC >= S;
+            fp.st_xy = d_xy.as<double2>();
+            fp.obs_z = d_z.as<double>() + (size_t)d0 * S;
+            fp.S = S; fp.n_obs = n_obs; fp.rm_dupl = rm_dupl;
+            fp.loc_is_obs = loc_is_obs ? 1 : 0;
+            fp.loc_obs_offset = p0;
+            fp.out_dist = d_dist.as<double>(); fp.out_obs = d_obs.as<double>();
+            fp.out_idx = out_idx ? d_idx.as<int32_t>() : nullptr;
+            fp.warn = d_flags.as<int>(); fp.fallbacks = nullptr;
+            const unsigned grid = (unsigned)(((cur + 127) / 128) * nd);
+            features_kernel<<<grid, 128, 0, s>>>(fp);
+            count_launch();
+            CU_TRY(cudaGetLastError());
+            // device [dl][j][cur] -> host [(d0+dl)][j][npix] at column p0
+            const size_t rows = (size_t)nd * n_obs;
+            CU_TRY(cudaMemcpy2DAsync(out_dist + (size_t)d0 * n_obs * npix + p0, sizeof(double) * npix, d_dist.p,
+                                     sizeof(double) * cur, sizeof(double) * cur, rows, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaMemcpy2DAsync(out_obs + (size_t)d0 * n_obs * npix + p0, sizeof(double) * npix, d_obs.p,
+                                     sizeof(double) * cur, sizeof(double) * cur, rows, cudaMemcpyDeviceToHost, s));
+            if (out_idx)
+                CU_TRY(cudaMemcpy2DAsync(out_idx + (size_t)d0 * n_obs * npix + p0, sizeof(int32_t) * npix, d_idx.p,
+                                         sizeof(int32_t) * cur, sizeof(int32_t) * cur, rows, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));   // the staging buffers are reused by the next batch
+        }
+    }
+    int flags[2] = {0, 0};
+    CU_TRY(cudaMemcpy(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost));
+    if (flags[1]) return fail(RFSI_E_NA_INPUT, "near_obs_days: a location has an NA coordinate");
+    if (flags[0]) {
+        g_err = "near_obs_days: some rows have fewer valid observations than n.obs(+1); missing neighbours are NA";
         return RFSI_W_TOO_FEW_OBS;
     }
     return RFSI_OK;

@@ -54,14 +54,28 @@ def rfsi(formula: str, data: pd.DataFrame, data_staid_x_y_z: Sequence = (0, 1, 2
         raise NotImplementedError("rfsi: only zero.tol = 0 is supported")
     response, covs = _parse_formula(formula)
     sid, xc, yc, tc = [None if c is None else _col(data, c) for c in data_staid_x_y_z]
-    groups = [data] if tc is None else [g for _, g in data.groupby(tc, sort=True)]
     parts = []
-    for g in groups:
-        g = g[~g[response].isna()]
-        if len(g) < 2:
-            continue
+    if tc is None:
+        g = data[~data[response].isna()]
         no = api.near_obs(g[[xc, yc]], g[[xc, yc, response]], zcol=2, n_obs=n_obs, device=device)
         parts.append(pd.concat([g[[response] + covs].reset_index(drop=True), no], axis=1))
+    else:
+        # every day in ONE engine call (rfsi_near_obs_days_f64): stations x days table, NaN = silent
+        stations = data[[sid, xc, yc]].drop_duplicates(sid).reset_index(drop=True)
+        pos = {s: i for i, s in enumerate(stations[sid])}
+        days = sorted(data[tc].unique())
+        di = np.searchsorted(np.asarray(days), data[tc].to_numpy())
+        si = data[sid].map(pos).to_numpy()
+        z = np.full((len(days), len(stations)), np.nan)
+        z[di, si] = data[response].to_numpy(dtype=np.float64)
+        dist, obs = api.near_obs_days(stations[[xc, yc]].to_numpy(dtype=np.float64), z, n_obs, device=device)
+        keep = ~data[response].isna().to_numpy()
+        tab = data.loc[keep, [response] + covs].reset_index(drop=True)
+        for j in range(n_obs):
+            tab[f"dist{j + 1}"] = dist[di[keep], si[keep], j]
+        for j in range(n_obs):
+            tab[f"obs{j + 1}"] = obs[di[keep], si[keep], j]
+        parts.append(tab)
     table = pd.concat(parts, ignore_index=True).dropna()          # complete.cases (1_models.R:1003)
     names = covs + [f"dist{j + 1}" for j in range(n_obs)] + [f"obs{j + 1}" for j in range(n_obs)]
     flat = grow.grow_forest(table[names].to_numpy(), table[response].to_numpy(), names, num_trees=num_trees,

@@ -177,3 +177,30 @@ def test_golden_real_croatia_station_geometry():
     assert 140 <= ok.sum() <= 157
     d, o, i = _gpu(loc, g["obs_xy"][ok], z[ok], int(g["n_obs"]))
     _same(d, g["dist"]); _same(i, g["idx"]); _same(o, g["obs"])
+
+
+def test_near_obs_days_training_table_and_prediction_shapes():
+    """All days in one call == the scripts' per-day loop (1_models.R:1034-1047): training
+    shape (locations are the stations, own observation excluded, silent stations NA) and
+    prediction shape (explicit locations), with enough missing stations on one day to force
+    the in-kernel full-scan fallback."""
+    rng = np.random.default_rng(8)
+    S, D, n = 157, 6, 10
+    xy = rng.uniform(0, 4e5, size=(S, 2))
+    z = rng.normal(size=(D, S))
+    for d in range(D):
+        z[d, rng.choice(S, rng.integers(3, 9), replace=False)] = np.nan
+    z[3, rng.choice(S, 120, replace=False)] = np.nan            # 37 stations left on day 3
+    dist, obs, idx = rb.near_obs_days(xy, z, n, return_idx=True)
+    assert dist.shape == (D, S, n)
+    loc = rng.uniform(0, 4e5, size=(5000, 2))
+    pd_, po_ = rb.near_obs_days(xy, z, n, locations=loc)
+    for d in range(D):
+        ok = ~np.isnan(z[d])
+        ed, eo, ei, _ = oracle.near_obs(xy[ok], xy[ok], z[d][ok], n)
+        _same(dist[d][ok], ed); _same(obs[d][ok], eo)
+        np.testing.assert_array_equal(idx[d][ok], np.flatnonzero(ok)[ei - 1] + 1)   # original station numbering
+        assert np.isnan(dist[d][~ok]).all() and (idx[d][~ok] == np.iinfo(np.int32).min).all()
+        assert (dist[d][ok][:, 0] > 0).all()
+        ed, eo, _, _ = oracle.near_obs(loc, xy[ok], z[d][ok], n)
+        _same(pd_[d], ed); _same(po_[d], eo)
