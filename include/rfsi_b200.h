@@ -148,6 +148,32 @@ int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, int64_t npi
  * prcp_catalonia/5_prcp_prediction.R:244-309): filter that day's stations
  * (!is.na(value)), near.obs, cbind the covariates, predict mean and/or quantiles --
  * for every day of the batch, without materialising the feature table. */
+/* ---- covariate rasters -------------------------------------------------------------
+ * raster::extract(r, points) with the default method ("simple": the value of the cell a
+ * point falls in), as the mapping scripts do for every covariate of every day before near.obs
+ * (prcp_catalonia/5_prcp_prediction.R:253-276: tmax/tmin on the DEM grid in tenths of a
+ * degree, IMERG on a 0.1-degree global grid).  North-up raster: layer l, row r (0 = top),
+ * column c at data[(l*nrow + r)*ncol + c]; cell (r, c) spans x_ul + c*dx .. x_ul + (c+1)*dx
+ * and y_ul - (r+1)*dy .. y_ul - r*dy.  value = raw*scale + offset; raw == nodata or a point
+ * outside the raster gives NA. */
+enum { RFSI_F64 = 0, RFSI_F32 = 1, RFSI_I32 = 2, RFSI_I16 = 3, RFSI_U16 = 4, RFSI_U8 = 5 };
+typedef struct rfsi_raster {
+    const void* data;
+    int32_t dtype;   /* RFSI_F64 ... RFSI_U8 */
+    int32_t nlayers; /* 1 = static; otherwise one layer per day */
+    int64_t ncol, nrow;
+    double x_ul, y_ul, dx, dy; /* outer corner of the top-left cell; cell size (both > 0) */
+    double nodata;             /* NaN = no nodata value */
+    double scale, offset;
+} rfsi_raster_t;
+
+/* out[p] = extract(layer `layer` of r, location p); locations explicit (loc_x/loc_y) or, when
+ * loc_x == NULL, the cells [pix_begin, pix_begin + npix) of the row-major grid
+ * (grid_x0 + col*grid_dx, grid_y0 + row*grid_dy), as in rfsi_fused_args_t. */
+int rfsi_raster_extract(const rfsi_raster_t* r, int32_t layer, const double* loc_x, const double* loc_y,
+                        int64_t npix, double grid_x0, double grid_y0, double grid_dx, double grid_dy,
+                        int64_t grid_ncol, int64_t pix_begin, double* out, int device);
+
 typedef struct rfsi_fused_args {
     size_t struct_size; /* = sizeof(rfsi_fused_args_t) */
     /* prediction locations: explicit (loc_x/loc_y, npix) or, when loc_x == NULL, the
@@ -186,6 +212,10 @@ typedef struct rfsi_fused_args {
     int16_t* out_iqr_i16;
     /* optional pixel validity mask (nullable): 0 = skip pixel, outputs NA / -32767 */
     const uint8_t* pix_mask;
+    /* optional (nullable) array of ncov raster descriptors: where cov_raster[c].data != NULL
+     * covariate c is sampled on the device from that raster at the prediction locations
+     * (cov[c] is then ignored) -- host-buffer entry point only */
+    const rfsi_raster_t* cov_raster;
 } rfsi_fused_args_t;
 
 int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device);

@@ -32,6 +32,17 @@ class RfsiError(RuntimeError):
         self.code = code
 
 
+class Raster(C.Structure):
+    _fields_ = [
+        ("data", C.c_void_p), ("dtype", C.c_int32), ("nlayers", C.c_int32), ("ncol", C.c_int64), ("nrow", C.c_int64),
+        ("x_ul", C.c_double), ("y_ul", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
+        ("nodata", C.c_double), ("scale", C.c_double), ("offset", C.c_double),
+    ]
+
+
+RASTER_DTYPES = {"float64": 0, "float32": 1, "int32": 2, "int16": 3, "uint16": 4, "uint8": 5}
+
+
 class FusedArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_size_t),
@@ -62,6 +73,7 @@ class FusedArgs(C.Structure):
         ("out_mean_i16", C.c_void_p),
         ("out_iqr_i16", C.c_void_p),
         ("pix_mask", C.c_void_p),
+        ("cov_raster", C.POINTER(Raster)),
     ]
 
 
@@ -78,6 +90,9 @@ _SIGNATURES = [
      [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int, _P]),
     ("rfsi_near_obs_days_f64", C.c_int,
      [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int]),
+    ("rfsi_raster_extract", C.c_int,
+     [C.POINTER(Raster), C.c_int32, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64,
+      C.c_int64, _P, C.c_int]),
     ("rfsi_forest_create", C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(_P)]),
     ("rfsi_forest_destroy", None, [_P]),
     ("rfsi_forest_upload", C.c_int, [_P, C.c_int]),

@@ -22,7 +22,9 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import FEAT_DIST, FEAT_OBS, FusedArgs, RfsiError
+from dataclasses import dataclass
+
+from ._lib import FEAT_DIST, FEAT_OBS, RASTER_DTYPES, FusedArgs, Raster as _CRaster, RfsiError
 from .forest import FlatForest, RangerForest, flatten_ranger, from_sklearn
 
 try:  # pandas plays the role of R's data.frame
@@ -179,6 +181,55 @@ def predict(model: RangerForest, data, type: str = "response", quantiles: Sequen
     raise ValueError(f"predict: unknown type {type!r}")
 
 
+@dataclass
+class Raster:
+    """A north-up covariate raster: data (nrow, ncol) or (nlayers, nrow, ncol) of float64 /
+    float32 / int32 / int16 / uint16 / uint8; (x_ul, y_ul) the outer corner of the top-left
+    cell; value = raw*scale + offset; raw == nodata -> NA.  Sampled on the device like
+    raster::extract(r, points) (prcp_catalonia/5_prcp_prediction.R:253-276)."""
+    data: np.ndarray
+    x_ul: float
+    y_ul: float
+    dx: float
+    dy: float
+    nodata: float = float("nan")
+    scale: float = 1.0
+    offset: float = 0.0
+
+    def _c(self):
+        d = np.ascontiguousarray(self.data)
+        if d.ndim == 2:
+            d = d[None]
+        if d.dtype.name not in RASTER_DTYPES:
+            raise ValueError(f"raster dtype {d.dtype} unsupported (use one of {list(RASTER_DTYPES)})")
+        r = _CRaster(d.ctypes.data, RASTER_DTYPES[d.dtype.name], d.shape[0], d.shape[2], d.shape[1],
+                     float(self.x_ul), float(self.y_ul), float(self.dx), float(self.dy), float(self.nodata),
+                     float(self.scale), float(self.offset))
+        return r, d
+
+
+def raster_extract(raster: Raster, locations=None, grid=None, pix_begin: int = 0, npix: Optional[int] = None,
+                   layer: int = 0, device: int = 0) -> np.ndarray:
+    """raster::extract(r, points): the value of the cell each location falls in (NA outside)."""
+    r, keep = raster._c()
+    lx = ly = None
+    g = (0.0, 0.0, 0.0, 0.0, 1)
+    if locations is not None:
+        loc = np.asarray(locations, dtype=np.float64)
+        lx, ly = _f64(loc[:, 0]), _f64(loc[:, 1])
+        npix = loc.shape[0]
+    else:
+        if grid is None or npix is None:
+            raise ValueError("give locations, or grid=(x0, y0, dx, dy, ncol) and npix")
+        g = grid
+    out = np.empty(int(npix), dtype=np.float64)
+    rc = _lib.load().rfsi_raster_extract(C.byref(r), int(layer), _ptr(lx), _ptr(ly), int(npix), float(g[0]), float(g[1]),
+                                         float(g[2]), float(g[3]), int(g[4]), int(pix_begin), _ptr(out), device)
+    _lib.check(rc)
+    del keep
+    return out
+
+
 def feature_map(feature_names: Sequence[str], cov_names: Sequence[str], n_obs: int) -> np.ndarray:
     """Model column -> RFSI_FEAT_* code: 'dist{j}' / 'obs{j}' (1-based) or a covariate name."""
     codes = []
@@ -235,23 +286,32 @@ def predict_fused(model: RangerForest, *, obs_xy, obs_z, n_obs: int, locations=N
     a.obs_x, a.obs_y, a.obs_z = _ptr(ox), _ptr(oy), _ptr(obs_z)
     a.nobs, a.ndays, a.n_obs, a.rm_dupl = nobs, ndays, int(n_obs), 1 if rm_dupl else 0
     cov_names = list(covariates)
-    cov_arrs, strides = [], []
-    for name in cov_names:
-        v = _f64(covariates[name])
-        if v.shape == (npix,):
-            strides.append(0)
-        elif v.shape == (ndays, npix):
-            strides.append(npix)
-        else:
-            raise ValueError(f"covariate {name!r} must have shape (npix,) or (ndays, npix)")
-        cov_arrs.append(v)
-    keep += cov_arrs
     ncov = len(cov_names)
-    cov_ptrs = (C.c_void_p * max(ncov, 1))(*[v.ctypes.data for v in cov_arrs])
-    cov_strides = (C.c_int64 * max(ncov, 1))(*strides)
+    cov_ptrs = (C.c_void_p * max(ncov, 1))()
+    cov_strides = (C.c_int64 * max(ncov, 1))()
+    rasters = (_CRaster * max(ncov, 1))()
+    any_raster = False
+    for i, name in enumerate(cov_names):
+        cv = covariates[name]
+        if isinstance(cv, Raster):      # sampled on the device at the prediction locations
+            rasters[i], d = cv._c()
+            keep.append(d)
+            any_raster = True
+            continue
+        v = _f64(cv)
+        if v.shape == (npix,):
+            cov_strides[i] = 0
+        elif v.shape == (ndays, npix):
+            cov_strides[i] = npix
+        else:
+            raise ValueError(f"covariate {name!r} must have shape (npix,) or (ndays, npix), or be a Raster")
+        cov_ptrs[i] = v.ctypes.data
+        keep.append(v)
     a.ncov = ncov
     a.cov = C.cast(cov_ptrs, C.POINTER(C.c_void_p))
     a.cov_day_stride = C.cast(cov_strides, C.POINTER(C.c_int64))
+    if any_raster:
+        a.cov_raster = C.cast(rasters, C.POINTER(_CRaster))
     fmap = feature_map(model.feature_names, cov_names, int(n_obs))
     a.feat_map = fmap.ctypes.data_as(C.POINTER(C.c_int32))
     out = {}

@@ -24,6 +24,7 @@
 #include "knn.cuh"
 #include "knn_cells.cuh"
 #include "qrf.cuh"
+#include "raster.cuh"
 
 using namespace rfsi;
 
@@ -1111,6 +1112,69 @@ extern "C" int rfsi_forest_terminal_nodes(const rfsi_forest_t* f, const double* 
 }
 
 // ------------------------------------------------------------------------------------
+// covariate rasters
+// ------------------------------------------------------------------------------------
+namespace {
+
+size_t raster_cell_bytes(int dtype) {
+    switch (dtype) { case RFSI_F64: return 8; case RFSI_F32: case RFSI_I32: return 4;
+                     case RFSI_I16: case RFSI_U16: return 2; case RFSI_U8: return 1; default: return 0; }
+}
+
+int check_raster(const rfsi_raster_t* r, const char* who) {
+    if (!r || !r->data) return fail(RFSI_E_ARG, "%s: raster or its data is NULL", who);
+    if (raster_cell_bytes(r->dtype) == 0) return fail(RFSI_E_ARG, "%s: unknown raster dtype %d", who, r->dtype);
+    if (r->ncol < 1 || r->nrow < 1 || r->nlayers < 1 || !(r->dx > 0) || !(r->dy > 0))
+        return fail(RFSI_E_ARG, "%s: raster needs ncol, nrow, nlayers >= 1 and dx, dy > 0", who);
+    return RFSI_OK;
+}
+
+RasterDev raster_dev(const rfsi_raster_t& r, const void* dev_data) {
+    return RasterDev{dev_data, r.dtype, r.nlayers, r.ncol, r.nrow, r.x_ul, r.y_ul, r.dx, r.dy, r.nodata, r.scale, r.offset};
+}
+
+int launch_raster_extract(const RasterDev& r, int layer0, int nl, const LocSpec& L, int64_t npix, double* out,
+                          int64_t ld, cudaStream_t st) {
+    if (npix == 0) return RFSI_OK;
+    raster_extract_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(r, layer0, nl, L, npix, out, ld);
+    count_launch();
+    CU_TRY(cudaGetLastError());
+    return RFSI_OK;
+}
+
+}  // namespace
+
+extern "C" int rfsi_raster_extract(const rfsi_raster_t* r, int32_t layer, const double* loc_x, const double* loc_y,
+                                   int64_t npix, double grid_x0, double grid_y0, double grid_dx, double grid_dy,
+                                   int64_t grid_ncol, int64_t pix_begin, double* out, int device)
+{
+    RF_TRY(check_raster(r, "raster_extract"));
+    if (layer < 0 || layer >= r->nlayers) return fail(RFSI_E_ARG, "raster_extract: layer %d outside [0,%d)", layer, r->nlayers);
+    if (npix < 0 || (npix > 0 && !out)) return fail(RFSI_E_ARG, "raster_extract: bad npix/out");
+    if ((loc_x == nullptr) != (loc_y == nullptr)) return fail(RFSI_E_ARG, "raster_extract: loc_x/loc_y go together");
+    if (!loc_x && grid_ncol < 1) return fail(RFSI_E_ARG, "raster_extract: raster form needs grid_ncol >= 1");
+    RF_TRY(use_device(device));
+    if (npix == 0) return RFSI_OK;
+    const size_t layer_bytes = (size_t)r->ncol * r->nrow * raster_cell_bytes(r->dtype);
+    DevBuf d_r, d_lx, d_ly, d_out;
+    RF_TRY(d_r.alloc(layer_bytes));
+    RF_TRY(d_out.alloc(sizeof(double) * npix));
+    CU_TRY(cudaMemcpy(d_r.p, reinterpret_cast<const char*>(r->data) + layer_bytes * layer, layer_bytes, cudaMemcpyHostToDevice));
+    LocSpec L{nullptr, nullptr, grid_x0, grid_y0, grid_dx, grid_dy, loc_x ? 1 : grid_ncol, loc_x ? 0 : pix_begin};
+    if (loc_x) {
+        RF_TRY(d_lx.alloc(sizeof(double) * npix)); RF_TRY(d_ly.alloc(sizeof(double) * npix));
+        CU_TRY(cudaMemcpy(d_lx.p, loc_x, sizeof(double) * npix, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(d_ly.p, loc_y, sizeof(double) * npix, cudaMemcpyHostToDevice));
+        L.x = d_lx.as<double>(); L.y = d_ly.as<double>();
+    }
+    rfsi_raster_t one = *r;
+    one.nlayers = 1;
+    RF_TRY(launch_raster_extract(raster_dev(one, d_r.p), 0, 1, L, npix, d_out.as<double>(), npix, nullptr));
+    CU_TRY(cudaMemcpy(out, d_out.p, sizeof(double) * npix, cudaMemcpyDeviceToHost));
+    return RFSI_OK;
+}
+
+// ------------------------------------------------------------------------------------
 // fused API
 // ------------------------------------------------------------------------------------
 namespace {
@@ -1148,6 +1212,14 @@ int validate_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
                         (c >= 0x20000 && c < 0x20000 + a->n_obs);
         if (!ok) return fail(RFSI_E_ARG, "fused: feat_map[%d] = 0x%x is not a covariate/dist/obs code", fidx, c);
     }
+    if (a->cov_raster)
+        for (int c = 0; c < a->ncov; ++c)
+            if (a->cov_raster[c].data) {
+                RF_TRY(check_raster(&a->cov_raster[c], "fused"));
+                if (a->cov_raster[c].nlayers != 1 && a->cov_raster[c].nlayers < a->ndays)
+                    return fail(RFSI_E_ARG, "fused: covariate raster %d has %d layers for %d days", c,
+                                a->cov_raster[c].nlayers, a->ndays);
+            }
     if ((a->out_q || a->out_iqr_i16)) {
         RF_TRY(check_probs(a->probs, a->nprobs));
         if (f->leaf_sample.empty())
@@ -1358,6 +1430,7 @@ extern "C" int rfsi_dev_predict_fused(const rfsi_forest_t* f, const rfsi_fused_a
                                       unsigned long long* counters, int device, void* stream)
 {
     RF_TRY(validate_fused(f, a));
+    if (a->cov_raster) return fail(RFSI_E_ARG, "fused (device form): sample rasters first; cov_raster is host-entry only");
     if (!workspace) return fail(RFSI_E_ARG, "fused: workspace is NULL");
     RF_TRY(use_device(device));
     const FusedPlan pl = plan_fused(f, a, kc_extra_default());
@@ -1405,6 +1478,21 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
     RF_TRY(d_cnt.alloc(4 * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(d_cnt.p, 0, 4 * sizeof(unsigned long long)));
 
+    // covariate rasters are uploaded whole, once, and sampled on the device per work item
+    DevBuf d_rast[kMaxCov];
+    bool is_rast[kMaxCov] = {false};
+    for (int c = 0; c < a->ncov; ++c) {
+        if (!(a->cov_raster && a->cov_raster[c].data)) continue;
+        const rfsi_raster_t& r = a->cov_raster[c];
+        const size_t bytes = (size_t)r.ncol * r.nrow * r.nlayers * raster_cell_bytes(r.dtype);
+        RF_TRY(d_rast[c].alloc(bytes));
+        CU_TRY(cudaMemcpy(d_rast[c].p, r.data, bytes, cudaMemcpyHostToDevice));
+        is_rast[c] = true;
+    }
+    auto cov_dynamic = [&](int c) {
+        return is_rast[c] ? a->cov_raster[c].nlayers != 1 : a->cov_day_stride[c] != 0;
+    };
+
     // per-slot device buffers: a work item is (pixel chunk, day batch)
     rfsi_fused_args_t proto = *a;
     proto.npix = chunk;
@@ -1427,7 +1515,7 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
         if (a->out_mean_i16) RF_TRY(slot[s].mean16.alloc(sizeof(int16_t) * chunk * db));
         if (a->out_iqr_i16) RF_TRY(slot[s].iqr16.alloc(sizeof(int16_t) * chunk * db));
         for (int c = 0; c < a->ncov; ++c)
-            RF_TRY(slot[s].cov[c].alloc(sizeof(double) * chunk * (a->cov_day_stride[c] ? db : 1)));
+            RF_TRY(slot[s].cov[c].alloc(sizeof(double) * chunk * (cov_dynamic(c) ? db : 1)));
         CU_TRY(cudaMemset(reinterpret_cast<char*>(slot[s].ws.p) + pl.off_misc, 0, 256));
     }
 
@@ -1462,6 +1550,20 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
             const double* covp[kMaxCov];
             int64_t covs[kMaxCov];
             for (int c = 0; c < a->ncov; ++c) {
+                if (is_rast[c]) {  // sample the raster at this chunk's locations, this batch's days
+                    LocSpec Lc{b.loc_x, b.loc_y, a->grid_x0, a->grid_y0, a->grid_dx, a->grid_dy,
+                               a->loc_x ? 1 : a->grid_ncol, a->loc_x ? 0 : b.pix_begin};
+                    const RasterDev rd = raster_dev(a->cov_raster[c], d_rast[c].p);
+                    if (!cov_dynamic(c)) {
+                        if (!reuse) RF_TRY(launch_raster_extract(rd, 0, 1, Lc, cur, sl.cov[c].as<double>(), cur, s));
+                        covs[c] = 0;
+                    } else {
+                        RF_TRY(launch_raster_extract(rd, d0, nd, Lc, cur, sl.cov[c].as<double>(), cur, s));
+                        covs[c] = cur;
+                    }
+                    covp[c] = sl.cov[c].as<double>();
+                    continue;
+                }
                 const int64_t hs = a->cov_day_stride[c];
                 if (hs == 0) {
                     if (!reuse)
@@ -1474,7 +1576,7 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
                 }
                 covp[c] = sl.cov[c].as<double>();
             }
-            b.cov = covp; b.cov_day_stride = covs;
+            b.cov = covp; b.cov_day_stride = covs; b.cov_raster = nullptr;
             b.out_mean = a->out_mean ? sl.mean.as<double>() : nullptr;
             b.out_q = a->out_q ? sl.q.as<double>() : nullptr;
             b.out_mean_i16 = a->out_mean_i16 ? sl.mean16.as<int16_t>() : nullptr;
