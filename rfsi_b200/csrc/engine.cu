@@ -781,16 +781,22 @@ extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, i
     cudaStream_t st = (cudaStream_t)stream;
     // interleave the station coordinates so one 128-bit broadcast feeds a distance
     double2* xy = nullptr;
-    CU_TRY(cudaMallocAsync(&xy, sizeof(double2) * (size_t)std::max(nobs, 1), st));
+    void* cw = nullptr;
+    const bool use_cells = nobs >= cells_min_S();
+    cudaError_t e = cudaMallocAsync(&xy, sizeof(double2) * (size_t)std::max(nobs, 1), st);
+    if (e == cudaSuccess && use_cells) e = cudaMallocAsync(&cw, cells_ws_bytes(nobs, npix), st);
+    if (e != cudaSuccess) {
+        if (xy) cudaFreeAsync(xy, st);
+        return fail(e == cudaErrorMemoryAllocation ? RFSI_E_OOM : RFSI_E_CUDA, "near_obs: device scratch: %s",
+                    cudaGetErrorString(e));
+    }
     if (nobs > 0) {
         interleave_xy_kernel<<<(nobs + 255) / 256, 256, 0, st>>>(obs_x, obs_y, nobs, xy);
         count_launch();
     }
     LocSpec L{loc_x, loc_y, 0, 0, 0, 0, 1, 0};
     int rc;
-    if (nobs >= cells_min_S()) {
-        void* cw = nullptr;
-        CU_TRY(cudaMallocAsync(&cw, cells_ws_bytes(nobs, npix), st));
+    if (use_cells) {
         const CellsWs c = carve_cells(cw, nobs, npix);
         rc = build_cells(xy, nobs, c, st);
         if (rc >= 0)
@@ -801,7 +807,7 @@ extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, i
         rc = launch_knn<KNN_FINAL>(L, npix, xy, nobs, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx, npix,
                                    warn_flag, nullptr, st);
     }
-    cudaFreeAsync(xy, st);
+    cudaFreeAsync(xy, st);   // stream-ordered: released after the kernels above have run
     return rc;
 }
 
@@ -1211,6 +1217,9 @@ int validate_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
         const bool ok = (c >= 0 && c < a->ncov) || (c >= 0x10000 && c < 0x10000 + a->n_obs) ||
                         (c >= 0x20000 && c < 0x20000 + a->n_obs);
         if (!ok) return fail(RFSI_E_ARG, "fused: feat_map[%d] = 0x%x is not a covariate/dist/obs code", fidx, c);
+        for (int g = 0; g < fidx; ++g)   // each source feeds exactly one model column (names are unique in R)
+            if (a->feat_map[g] == c)
+                return fail(RFSI_E_ARG, "fused: feat_map[%d] and feat_map[%d] name the same source 0x%x", g, fidx, c);
     }
     if (a->cov_raster)
         for (int c = 0; c < a->ncov; ++c)
