@@ -139,7 +139,7 @@ def test_chunked_large_call_matches_properties():
 
 @pytest.mark.parametrize("case", ["shuffled", "outside", "collinear", "clustered", "forced_small"])
 def test_cell_grid_search_is_exact_in_awkward_geometries(case, monkeypatch):
-    """The pruned search (S >= 1024) must be the same function of the data as the full scan:
+    """The pruned search (default for S >= 128) must be the same function of the data as the full scan:
     incoherent location order, locations far outside the station bbox, degenerate bboxes,
     strong clustering, and the cell path forced onto a small lattice with ties."""
     rng = np.random.default_rng(hash(case) % 1000)
