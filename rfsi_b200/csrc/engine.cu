@@ -16,6 +16,8 @@
 #include <thread>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/rfsi_b200.h"
 #include "common.cuh"
 #include "features.cuh"
@@ -540,21 +542,50 @@ struct CellsWs {
     int32_t* cursor = nullptr;
     double2* sxy = nullptr;
     int32_t* sid = nullptr;
-    // location sort (explicit coordinates only)
-    int32_t* lcount = nullptr;
-    int32_t* lcursor = nullptr;
-    int32_t* perm = nullptr;
 };
-int cells_G(int S) { return std::max(1, std::min(1024, (int)std::ceil(std::sqrt((double)std::max(S, 1) / 3.0)))); }
-// npix_sort: number of explicit locations that will be cell-sorted with this workspace (0 = none)
-size_t cells_ws_bytes(int S, int64_t npix_sort) {
-    const size_t G2 = (size_t)cells_G(S) * cells_G(S);
-    size_t b = 256 + align_up((G2 + 1) * 4, 256) + align_up(G2 * 4, 256) + align_up((size_t)std::max(S, 1) * 16, 256) +
-               align_up((size_t)std::max(S, 1) * 4, 256);
-    if (npix_sort > 0) b += align_up((G2 + 1) * 4, 256) + align_up(G2 * 4, 256) + align_up((size_t)npix_sort * 4, 256);
-    return b;
+
+// Morton-order permutation of unordered explicit locations (knn_cells.cuh)
+size_t loc_perm_bytes(int64_t npix) {
+    if (npix <= 0) return 0;
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)npix, 0, 42);
+    return 256 + 2 * align_up((size_t)npix * 8, 256) + 2 * align_up((size_t)npix * 4, 256) + align_up(temp, 256);
 }
-CellsWs carve_cells(void* ws, int S, int64_t npix_sort) {
+// returns the permutation (inside `scratch`) or nullptr when npix does not fit an int
+int build_loc_perm(const LocSpec& L, int64_t npix, void* scratch, const int32_t** perm_out, cudaStream_t st) {
+    *perm_out = nullptr;
+    if (npix <= 0 || npix > 0x7fffffff || !scratch) return RFSI_OK;
+    char* p = reinterpret_cast<char*>(scratch);
+    unsigned long long* bbox = reinterpret_cast<unsigned long long*>(p); p += 256;
+    unsigned long long* k_in = reinterpret_cast<unsigned long long*>(p); p += align_up((size_t)npix * 8, 256);
+    unsigned long long* k_out = reinterpret_cast<unsigned long long*>(p); p += align_up((size_t)npix * 8, 256);
+    int32_t* v_in = reinterpret_cast<int32_t*>(p); p += align_up((size_t)npix * 4, 256);
+    int32_t* v_out = reinterpret_cast<int32_t*>(p); p += align_up((size_t)npix * 4, 256);
+    const unsigned long long init[4] = {~0ULL, 0ULL, ~0ULL, 0ULL};
+    CU_TRY(cudaMemcpyAsync(bbox, init, sizeof init, cudaMemcpyHostToDevice, st));
+    const unsigned g = (unsigned)std::min<int64_t>((npix + 255) / 256, 148 * 8);
+    loc_bbox_kernel<<<g, 256, 0, st>>>(L, npix, bbox);
+    loc_morton_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(L, npix, bbox, k_in, v_in);
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, k_in, k_out, v_in, v_out, (int)npix, 0, 42, st);
+    CU_TRY(cub::DeviceRadixSort::SortPairs(p, temp, k_in, k_out, v_in, v_out, (int)npix, 0, 42, st));
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    CU_TRY(cudaGetLastError());
+    *perm_out = v_out;
+    return RFSI_OK;
+}
+
+bool loc_rows(const LocSpec& L, int64_t npix) {   // thread -> pixel mapping can use compact 2-D tiles
+    return L.ncol >= 16 && L.pix_begin % L.ncol == 0 && (!L.x || npix % L.ncol == 0);
+}
+int cells_G(int S) { return std::max(1, std::min(1024, (int)std::ceil(std::sqrt((double)std::max(S, 1) / 3.0)))); }
+size_t cells_ws_bytes(int S) {
+    const size_t G2 = (size_t)cells_G(S) * cells_G(S);
+    return 256 + align_up((G2 + 1) * 4, 256) + align_up(G2 * 4, 256) + align_up((size_t)std::max(S, 1) * 16, 256) +
+           align_up((size_t)std::max(S, 1) * 4, 256);
+}
+CellsWs carve_cells(void* ws, int S) {
     const size_t G2 = (size_t)cells_G(S) * cells_G(S);
     char* p = reinterpret_cast<char*>(ws);
     CellsWs c;
@@ -562,12 +593,7 @@ CellsWs carve_cells(void* ws, int S, int64_t npix_sort) {
     c.cell_start = reinterpret_cast<int32_t*>(p); p += align_up((G2 + 1) * 4, 256);
     c.cursor = reinterpret_cast<int32_t*>(p); p += align_up(G2 * 4, 256);
     c.sxy = reinterpret_cast<double2*>(p); p += align_up((size_t)std::max(S, 1) * 16, 256);
-    c.sid = reinterpret_cast<int32_t*>(p); p += align_up((size_t)std::max(S, 1) * 4, 256);
-    if (npix_sort > 0) {
-        c.lcount = reinterpret_cast<int32_t*>(p); p += align_up((G2 + 1) * 4, 256);
-        c.lcursor = reinterpret_cast<int32_t*>(p); p += align_up(G2 * 4, 256);
-        c.perm = reinterpret_cast<int32_t*>(p);
-    }
+    c.sid = reinterpret_cast<int32_t*>(p);
     return c;
 }
 int cells_min_S() { return env_int("RFSI_B200_CELLS_MIN", 128); }  // measured: the cell-grid search wins from ~100 stations up
@@ -578,9 +604,10 @@ int build_cells(const double2* xy, int S, const CellsWs& c, cudaStream_t st) {
     return RFSI_OK;
 }
 
+// perm: Morton permutation for unordered explicit locations (build_loc_perm), or nullptr
 template <int MODE>
-int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, int c_S, int k, const double* st_z, int rm_dupl,
-                     double* out_a, double* out_b, int32_t* out_i, int64_t ld, int* warn, int* na_flag,
+int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, const int32_t* perm, int k, const double* st_z,
+                     int rm_dupl, double* out_a, double* out_b, int32_t* out_i, int64_t ld, int* warn, int* na_flag,
                      cudaStream_t stream)
 {
     if (npix == 0) return RFSI_OK;
@@ -588,19 +615,9 @@ int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, int c_S, 
     if (smem > 227 * 1024) return fail(RFSI_E_ARG, "n.obs = %d needs %zu B of shared memory (> 227 KB)", k - 1, smem);
     auto kern = knn_cells_kernel<kKnnP, MODE>;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tile2d = (!L.x && L.pix_begin % L.ncol == 0 && L.ncol >= 16) ? 1 : 0;
-    const int32_t* perm = nullptr;
-    if (L.x && c.perm && npix <= 0x7fffffff) {  // unordered explicit locations: visit them cell by cell
-        const size_t G2 = (size_t)cells_G(c_S) * cells_G(c_S);
-        CU_TRY(cudaMemsetAsync(c.lcount, 0, (G2 + 1) * 4, stream));
-        const unsigned g = (unsigned)((npix + 255) / 256);
-        loc_cell_count_kernel<<<g, 256, 0, stream>>>(L, npix, c.hdr, c.lcount);
-        scan_cells_kernel<<<1, 1024, 0, stream>>>(c.lcount, c.hdr, c.lcursor);
-        loc_cell_scatter_kernel<<<g, 256, 0, stream>>>(L, npix, c.hdr, c.lcursor, c.perm);
-        g_launches.fetch_add(3, std::memory_order_relaxed);
-        CU_TRY(cudaGetLastError());
-        perm = c.perm;
-    }
+    // 2-D tiles need rows of L.ncol locations: the raster form, or explicit coordinates stored row by row
+    const int tile2d = loc_rows(L, npix) ? 1 : 0;
+    if (tile2d) perm = nullptr;
     long long tiles_per_row = 0, ntiles;
     if (tile2d) {
         tiles_per_row = (L.ncol + 15) / 16;
@@ -782,11 +799,15 @@ extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, i
     // interleave the station coordinates so one 128-bit broadcast feeds a distance
     double2* xy = nullptr;
     void* cw = nullptr;
+    void* pw = nullptr;
     const bool use_cells = nobs >= cells_min_S();
+    LocSpec L{loc_x, loc_y, 0, 0, 0, 0, 1, 0};
     cudaError_t e = cudaMallocAsync(&xy, sizeof(double2) * (size_t)std::max(nobs, 1), st);
-    if (e == cudaSuccess && use_cells) e = cudaMallocAsync(&cw, cells_ws_bytes(nobs, npix), st);
+    if (e == cudaSuccess && use_cells) e = cudaMallocAsync(&cw, cells_ws_bytes(nobs), st);
+    if (e == cudaSuccess && use_cells && npix > 0) e = cudaMallocAsync(&pw, loc_perm_bytes(npix), st);
     if (e != cudaSuccess) {
         if (xy) cudaFreeAsync(xy, st);
+        if (cw) cudaFreeAsync(cw, st);
         return fail(e == cudaErrorMemoryAllocation ? RFSI_E_OOM : RFSI_E_CUDA, "near_obs: device scratch: %s",
                     cudaGetErrorString(e));
     }
@@ -794,15 +815,17 @@ extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, i
         interleave_xy_kernel<<<(nobs + 255) / 256, 256, 0, st>>>(obs_x, obs_y, nobs, xy);
         count_launch();
     }
-    LocSpec L{loc_x, loc_y, 0, 0, 0, 0, 1, 0};
     int rc;
     if (use_cells) {
-        const CellsWs c = carve_cells(cw, nobs, npix);
+        const CellsWs c = carve_cells(cw, nobs);
+        const int32_t* perm = nullptr;
         rc = build_cells(xy, nobs, c, st);
+        if (rc >= 0) rc = build_loc_perm(L, npix, pw, &perm, st);
         if (rc >= 0)
-            rc = launch_knn_cells<KNN_FINAL>(L, npix, c, nobs, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx,
+            rc = launch_knn_cells<KNN_FINAL>(L, npix, c, perm, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx,
                                              npix, warn_flag, nullptr, st);
         cudaFreeAsync(cw, st);
+        if (pw) cudaFreeAsync(pw, st);
     } else {
         rc = launch_knn<KNN_FINAL>(L, npix, xy, nobs, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx, npix,
                                    warn_flag, nullptr, st);
@@ -835,14 +858,13 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
     CU_TRY(cudaMemset(d_flags.p, 0, 2 * sizeof(int)));
     const bool use_cells = nobs >= cells_min_S();
     const int64_t chunk = std::min<int64_t>(npix, 1 << 20);
-    DevBuf d_cells[2];
-    CellsWs cells[2];
+    DevBuf d_cells, d_perm[2];
+    CellsWs cells;
     if (use_cells) {
-        for (int s = 0; s < (npix <= chunk ? 1 : 2); ++s) {   // one per stream slot: the location sort is per chunk
-            RF_TRY(d_cells[s].alloc(cells_ws_bytes(nobs, chunk)));
-            cells[s] = carve_cells(d_cells[s].p, nobs, chunk);
-            RF_TRY(build_cells(d_xy.as<double2>(), nobs, cells[s], nullptr));
-        }
+        RF_TRY(d_cells.alloc(cells_ws_bytes(nobs)));
+        cells = carve_cells(d_cells.p, nobs);
+        RF_TRY(build_cells(d_xy.as<double2>(), nobs, cells, nullptr));
+        for (int s = 0; s < (npix <= chunk ? 1 : 2); ++s) RF_TRY(d_perm[s].alloc(loc_perm_bytes(chunk)));
         CU_TRY(cudaStreamSynchronize(nullptr));
     }
 
@@ -865,8 +887,10 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
         CU_TRY(cudaMemcpyAsync(d_lx[slot].p, loc_x + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
         CU_TRY(cudaMemcpyAsync(d_ly[slot].p, loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
         LocSpec L{d_lx[slot].as<double>(), d_ly[slot].as<double>(), 0, 0, 0, 0, 1, 0};
+        const int32_t* perm = nullptr;
+        if (use_cells) RF_TRY(build_loc_perm(L, cur, d_perm[slot].p, &perm, s));
         if (use_cells)
-            RF_TRY(launch_knn_cells<KNN_FINAL>(L, cur, cells[slot], nobs, n_obs + 1, d_z.as<double>(), rm_dupl,
+            RF_TRY(launch_knn_cells<KNN_FINAL>(L, cur, cells, perm, n_obs + 1, d_z.as<double>(), rm_dupl,
                                                d_dist[slot].as<double>(), d_obs[slot].as<double>(),
                                                out_idx ? d_idx[slot].as<int32_t>() : nullptr, cur, d_flags.as<int>(),
                                                d_flags.as<int>() + 1, s));
@@ -937,7 +961,12 @@ extern "C" int rfsi_near_obs_days_f64(const double* loc_x, const double* loc_y, 
     RF_TRY(d_flags.alloc(16));
     const bool use_cells = S >= cells_min_S();
     CellsWs cells;
-    if (use_cells) { RF_TRY(d_cells.alloc(cells_ws_bytes(S, chunk))); cells = carve_cells(d_cells.p, S, chunk); }
+    DevBuf d_perm;
+    if (use_cells) {
+        RF_TRY(d_cells.alloc(cells_ws_bytes(S)));
+        cells = carve_cells(d_cells.p, S);
+        RF_TRY(d_perm.alloc(loc_perm_bytes(chunk)));
+    }
     CU_TRY(cudaMemcpy(d_xy.p, xy.data(), sizeof(double2) * xy.size(), cudaMemcpyHostToDevice));
     if (S > 0) CU_TRY(cudaMemcpy(d_z.p, obs_z, sizeof(double) * (size_t)S * ndays, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemset(d_flags.p, 0, 16));
@@ -949,8 +978,10 @@ extern "C" int rfsi_near_obs_days_f64(const double* loc_x, const double* loc_y, 
         CU_TRY(cudaMemcpyAsync(d_lx.p, (loc_is_obs ? obs_x : loc_x) + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
         CU_TRY(cudaMemcpyAsync(d_ly.p, (loc_is_obs ? obs_y : loc_y) + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
         LocSpec L{d_lx.as<double>(), d_ly.as<double>(), 0, 0, 0, 0, 1, 0};
+        const int32_t* perm = nullptr;
+        if (use_cells) RF_TRY(build_loc_perm(L, cur, d_perm.p, &perm, s));
         if (use_cells)
-            RF_TRY(launch_knn_cells<KNN_RAW>(L, cur, cells, S, KC, nullptr, 0, d_cd2.as<double>(), nullptr,
+            RF_TRY(launch_knn_cells<KNN_RAW>(L, cur, cells, perm, KC, nullptr, 0, d_cd2.as<double>(), nullptr,
                                              d_cid.as<int32_t>(), cur, nullptr, d_flags.as<int>() + 1, s));
         else
             RF_TRY(launch_knn<KNN_RAW>(L, cur, d_xy.as<double2>(), S, KC, nullptr, 0, d_cd2.as<double>(), nullptr,
@@ -1195,7 +1226,7 @@ struct FusedPlan {
     int64_t npix_plan = 0;    // pixels the workspace was sized for
     bool want_q = false;
     // workspace offsets
-    size_t off_cand_d2 = 0, off_cand_id = 0, off_xy = 0, off_cells = 0, off_fb = 0, off_acc = 0, off_misc = 0, off_samples = 0, off_skip = 0,
+    size_t off_cand_d2 = 0, off_cand_id = 0, off_xy = 0, off_cells = 0, off_perm = 0, off_fb = 0, off_acc = 0, off_misc = 0, off_samples = 0, off_skip = 0,
            off_probs = 0, total = 0;
 };
 
@@ -1260,7 +1291,8 @@ FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_
     pl.off_cand_d2 = o; o += align_up(sizeof(double) * (size_t)pl.KC * npix, 256);
     pl.off_cand_id = o; o += align_up(sizeof(int32_t) * (size_t)pl.KC * npix, 256);
     pl.off_xy = o; o += align_up(sizeof(double2) * (size_t)std::max(a->nobs, 1), 256);
-    pl.off_cells = o; o += align_up(cells_ws_bytes(a->nobs, a->loc_x ? npix : 0), 256);
+    pl.off_cells = o; o += align_up(cells_ws_bytes(a->nobs), 256);
+    pl.off_perm = o; o += align_up(a->loc_x ? loc_perm_bytes(npix) : 0, 256);
     pl.off_fb = o; o += align_up(sizeof(int2) * (size_t)pl.rows, 256);
     pl.off_acc = o; o += align_up(sizeof(double) * (size_t)pl.rows, 256);
     pl.off_misc = o; o += 256;  // fb_count, na_flag
@@ -1327,18 +1359,31 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
     double* samples = pl.want_q ? reinterpret_cast<double*>(ws + pl.off_samples) : nullptr;
     unsigned char* skip = pl.want_q ? reinterpret_cast<unsigned char*>(ws + pl.off_skip) : nullptr;
 
+    // explicit coordinates: grid_ncol > 1 is the row length of a row-by-row ordering (a mapping hint only)
     LocSpec L{a->loc_x, a->loc_y, a->grid_x0, a->grid_y0, a->grid_dx, a->grid_dy,
-              a->loc_x ? 1 : a->grid_ncol, a->loc_x ? 0 : a->pix_begin};
+              a->loc_x ? std::max<int64_t>(1, a->grid_ncol) : a->grid_ncol, a->loc_x ? 0 : a->pix_begin};
+    // unordered explicit locations are visited along a Morton curve (kNN tiles and forest warps
+    // stay spatially compact); the permutation lives in the workspace next to the candidates
+    const bool want_perm = a->loc_x && !loc_rows(L, a->npix) && a->npix <= 0x7fffffff && env_int("RFSI_B200_MORTON", 1);
+    const int32_t* perm = want_perm
+        ? reinterpret_cast<const int32_t*>(ws + pl.off_perm + 256 + 2 * align_up((size_t)a->npix * 8, 256) +
+                                           align_up((size_t)a->npix * 4, 256))
+        : nullptr;
     if (!reuse_candidates) {
         if (a->nobs > 0) {
             interleave_xy_kernel<<<(a->nobs + 255) / 256, 256, 0, st>>>(a->obs_x, a->obs_y, a->nobs, xy);
             count_launch();
         }
+        if (want_perm) {
+            const int32_t* built = nullptr;
+            RF_TRY(build_loc_perm(L, a->npix, ws + pl.off_perm, &built, st));
+            if (built != perm) return fail(RFSI_E_CUDA, "fused: permutation layout mismatch");
+        }
         // geometry pass: the KC nearest of ALL stations, once per pixel
         if (a->nobs >= cells_min_S()) {
-            const CellsWs c = carve_cells(ws + pl.off_cells, a->nobs, a->loc_x ? pl.npix_plan : 0);
+            const CellsWs c = carve_cells(ws + pl.off_cells, a->nobs);
             RF_TRY(build_cells(xy, a->nobs, c, st));
-            RF_TRY(launch_knn_cells<KNN_RAW>(L, a->npix, c, a->nobs, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id,
+            RF_TRY(launch_knn_cells<KNN_RAW>(L, a->npix, c, perm, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id,
                                              a->npix, nullptr, nullptr, st));
         } else {
             RF_TRY(launch_knn<KNN_RAW>(L, a->npix, xy, a->nobs, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id, a->npix,
@@ -1373,8 +1418,8 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
     fp.refill = use_refill();
     fp.fb_list = fb; fp.fb_count = fb_count; fp.fb_capacity = (unsigned int)std::min<int64_t>(pl.rows, 0xffffffffLL);
     fp.counters = counters; fp.na_flag = na_flag;
-    fp.tile2d = (!a->loc_x && env_int("RFSI_B200_TILE2D", 1) && a->pix_begin % a->grid_ncol == 0 &&
-                 a->grid_ncol >= 16) ? 1 : 0;
+    fp.tile2d = (env_int("RFSI_B200_TILE2D", 1) && loc_rows(L, a->npix)) ? 1 : 0;
+    fp.perm = fp.tile2d ? nullptr : perm;
 
     const bool Q = im.compact;
     g_default_J = Q ? 8 : 12;
@@ -1383,8 +1428,8 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
     const int Pm = main256 ? kFusedP : kFallbackP;
     long long ntiles;
     if (fp.tile2d) {
-        fp.tiles_per_row = (a->grid_ncol + 15) / 16;
-        const long long nrows = (a->npix + a->grid_ncol - 1) / a->grid_ncol;
+        fp.tiles_per_row = (L.ncol + 15) / 16;
+        const long long nrows = (a->npix + L.ncol - 1) / L.ncol;
         ntiles = fp.tiles_per_row * ((nrows + (Pm / 16) - 1) / (Pm / 16));
     } else {
         ntiles = (a->npix + Pm - 1) / Pm;
@@ -1467,6 +1512,18 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
     }
     const int kc_extra = std::min(worst_missing, std::max(kc_extra_default(), 0) + 5);
 
+    // explicit coordinates that are really raster cells stored row by row (the usual R input:
+    // coordinates(SpatialPixels) / a grid data.frame): find the row length so threads can be
+    // mapped to compact 2-D tiles.  Only a mapping hint -- results do not depend on it.
+    int64_t row_len = a->loc_x ? a->grid_ncol : 0;
+    if (a->loc_x && row_len <= 1) {
+        int64_t i = 1;
+        while (i < a->npix && a->loc_y[i] == a->loc_y[0]) ++i;
+        if (i >= 16 && i < a->npix && a->npix % i == 0 && a->npix / i >= 4 && a->loc_y[i - 1] == a->loc_y[0] &&
+            a->loc_y[2 * i - 1] == a->loc_y[i] && a->loc_x[i] == a->loc_x[0])
+            row_len = i;
+    }
+
     // pixel chunking: bound per-chunk device memory
     const bool want_q = a->out_q || a->out_iqr_i16;
     int64_t chunk = 1 << 20;
@@ -1474,6 +1531,7 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
     chunk = std::min(chunk, a->npix);
     if (!a->loc_x && a->pix_begin % a->grid_ncol == 0 && chunk < a->npix && chunk >= a->grid_ncol)
         chunk = chunk / a->grid_ncol * a->grid_ncol;  // whole raster rows per chunk keeps 2-D tiles
+    if (a->loc_x && row_len > 1 && chunk < a->npix && chunk >= row_len) chunk = chunk / row_len * row_len;
 
     DevBuf d_ox, d_oy, d_oz, d_cnt;
     RF_TRY(d_ox.alloc(sizeof(double) * std::max(S, 1)));
@@ -1549,6 +1607,7 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
                     CU_TRY(cudaMemcpyAsync(sl.ly.p, a->loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
                 }
                 b.loc_x = sl.lx.as<double>(); b.loc_y = sl.ly.as<double>();
+                b.grid_ncol = (row_len > 1 && cur % row_len == 0) ? row_len : 1;
             } else {
                 b.pix_begin = a->pix_begin + p0;
             }

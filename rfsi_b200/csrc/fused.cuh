@@ -66,13 +66,17 @@ struct FusedParams {
     unsigned int fb_capacity;
     unsigned long long* counters;  // {visits, pixel-days, fallback pixel-days, too-few pixel-days}
     int* na_flag;
+    const int32_t* perm;         // unordered explicit locations: Morton-order permutation (else nullptr)
     int tile2d;                  // raster form: 16x16 pixel tiles of 8x4 warp patches
     long long tiles_per_row;     // tile2d only
 };
 
 template <int P>
 __device__ __forceinline__ long long fused_pixel_of_thread(const FusedParams& a, long long tile) {
-    if (!a.tile2d) return tile * P + threadIdx.x;
+    if (!a.tile2d) {
+        const long long i = tile * P + threadIdx.x;
+        return (a.perm != nullptr && i < a.npix) ? (long long)a.perm[i] : i;
+    }
     // 16 x (P/16) pixel tile; a warp covers an 8 x 4 patch
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const long long tr = tile / a.tiles_per_row, tc = tile - tr * a.tiles_per_row;
