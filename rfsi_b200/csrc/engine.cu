@@ -1423,8 +1423,9 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
 
     const bool Q = im.compact;
     g_default_J = Q ? 8 : 12;
-    const bool main256 = Q ? (fused_smem_bytes<kFusedP, true>(f->nfeat, 0, false) <= 110 * 1024)
-                           : (fused_smem_bytes<kFusedP, false>(f->nfeat, 0, false) <= 100 * 1024);
+    const bool main256 = env_int("RFSI_B200_P", 256) >= 256 &&
+                         (Q ? (fused_smem_bytes<kFusedP, true>(f->nfeat, 0, false) <= 110 * 1024)
+                            : (fused_smem_bytes<kFusedP, false>(f->nfeat, 0, false) <= 100 * 1024));
     const int Pm = main256 ? kFusedP : kFallbackP;
     long long ntiles;
     if (fp.tile2d) {

@@ -8,9 +8,13 @@
 // scale-up config) in seconds, and (b) the rfsi() wrapper of README.md:93-110 needs a trainer
 // behind it.  It grows CART regression trees the way ranger's defaults do -- bootstrap
 // sample, mtry random candidate variables per node, variance-reduction split, x <= split
-// goes left, min.node.size stop rule, leaf = in-bag mean, children appended in pairs -- but
-// searches split points on a per-variable grid of up to 255 quantile cut points (histogram
-// CART) instead of every midpoint.  Output is ranger's forest layout.
+// goes left, min.node.size stop rule, leaf = in-bag mean, children appended in pairs.  Big nodes
+// (>= kExactBelow in-bag rows) search split points on a per-variable grid of up to 255 quantile
+// cut points (histogram CART: plenty of rows per bin there); smaller nodes sort their rows and
+// try every midpoint between distinct values, exactly as ranger does.  (With the grid alone a
+// node whose rows share a bin cannot be split on that variable: on the reference's Croatian
+// data that cost 13 % RMSE, 1.58 vs 1.37 for exact CART -- tests/test_gpu_croatia_llocv.py.)
+// Output is ranger's forest layout.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -73,6 +77,8 @@ Binned make_bins(const double* X, int64_t n, int F, int max_bins) {
     return b;
 }
 
+constexpr int64_t kExactBelow = 4096;
+
 struct Tree {
     std::vector<int32_t> left, right, var;
     std::vector<double> val;
@@ -94,19 +100,42 @@ void grow_tree(const Binned& B, const double* X, const double* y, int mtry, int 
     std::vector<int> feats(F);
     std::iota(feats.begin(), feats.end(), 0);
     double hs[256]; int32_t hc[256];
+    std::vector<std::pair<double, double>> xy;   // (value, response) of a small node, one variable
     for (size_t node = 0; node < work.size(); ++node) {  // children are appended: index order == ranger's
         const Work w = work[node];
         const int64_t cnt = w.hi - w.lo;
         double sum = 0.0;
         for (int64_t i = w.lo; i < w.hi; ++i) sum += y[idx[i]];
         bool split = cnt > min_node_size && (max_depth <= 0 || w.depth < max_depth);
-        int best_f = -1, best_bin = -1;
-        double best_gain = 0.0;
+        int best_f = -1;
+        double best_gain = 0.0, best_thr = 0.0;
+        const bool exact = cnt < kExactBelow;
         if (split) {
             for (int m = 0; m < std::min(mtry, F); ++m) {  // mtry distinct candidate variables
                 const int j = m + (int)rng.below((uint32_t)(F - m));
                 std::swap(feats[m], feats[j]);
                 const int f = feats[m];
+                if (exact) {   // every midpoint between distinct sorted values
+                    const double* xf = X + (size_t)f * n;
+                    xy.resize((size_t)cnt);
+                    for (int64_t i = 0; i < cnt; ++i) { const int32_t r = idx[w.lo + i]; xy[i] = {xf[r], y[r]}; }
+                    std::sort(xy.begin(), xy.end(), [](const std::pair<double, double>& a, const std::pair<double, double>& b) { return a.first < b.first; });
+                    double ls = 0.0;
+                    for (int64_t i = 0; i + 1 < cnt; ++i) {
+                        ls += xy[i].second;
+                        if (!(xy[i].first < xy[i + 1].first)) continue;
+                        const int64_t lc = i + 1, rc = cnt - lc;
+                        const double rs = sum - ls;
+                        const double gain = ls * ls / (double)lc + rs * rs / (double)rc;
+                        if (gain > best_gain) {
+                            best_gain = gain; best_f = f;
+                            double mid = (xy[i].first + xy[i + 1].first) / 2.0;
+                            if (mid == xy[i + 1].first) mid = xy[i].first;   // ranger's guard
+                            best_thr = mid;
+                        }
+                    }
+                    continue;
+                }
                 const int nb = (int)B.cuts[f].size();
                 if (nb == 0) continue;
                 const uint8_t* bf = B.bins.data() + (size_t)f * n;
@@ -120,7 +149,7 @@ void grow_tree(const Binned& B, const double* X, const double* y, int mtry, int 
                     if (lc == 0 || rc == 0) continue;
                     const double rs = sum - ls;
                     const double gain = ls * ls / (double)lc + rs * rs / (double)rc;  // ranger's decrease
-                    if (gain > best_gain) { best_gain = gain; best_f = f; best_bin = b; }
+                    if (gain > best_gain) { best_gain = gain; best_f = f; best_thr = B.cuts[f][b]; }
                 }
             }
             // no improvement over the unsplit node (sum^2/cnt) -> terminal
@@ -130,11 +159,12 @@ void grow_tree(const Binned& B, const double* X, const double* y, int mtry, int 
             tr.val[node] = sum / (double)cnt;
             continue;
         }
-        const uint8_t* bf = B.bins.data() + (size_t)best_f * n;
+        const double* xb = X + (size_t)best_f * n;
         const int64_t mid = std::partition(idx.begin() + w.lo, idx.begin() + w.hi,
-                                           [&](int32_t r) { return bf[r] <= best_bin; }) - idx.begin();
+                                           [&](int32_t r) { return xb[r] <= best_thr; }) - idx.begin();
+        if (mid == w.lo || mid == w.hi) { tr.val[node] = sum / (double)cnt; continue; }   // degenerate: keep a leaf
         const int32_t l = (int32_t)tr.left.size();
-        tr.left[node] = l; tr.right[node] = l + 1; tr.var[node] = best_f; tr.val[node] = B.cuts[best_f][best_bin];
+        tr.left[node] = l; tr.right[node] = l + 1; tr.var[node] = best_f; tr.val[node] = best_thr;
         for (int c = 0; c < 2; ++c) { tr.left.push_back(0); tr.right.push_back(0); tr.var.push_back(0); tr.val.push_back(0.0); }
         work.push_back({w.lo, mid, w.depth + 1});
         work.push_back({mid, w.hi, w.depth + 1});

@@ -91,9 +91,37 @@ def knn_croatia_real():
                         obs_xy=xy, temp_days=temp[:8], day=day, n_obs=10, dist=d, obs=o, idx=i)
 
 
+def croatia_llocv_inputs():
+    """The real inputs of the Croatian case study (temp_croatia/temp_data/stfdf.rda + folds.rda):
+    157 stations x 366 days of TEMP and the covariates of 1_models.R:73, and the 10 station
+    folds of the nested LLOCV (1_models.R:1094-1233).  Used by the end-to-end accuracy test,
+    whose anchor is the reference's own stored result: RMSE 1.3988, CCC 0.9827
+    (1_models.R:1245-1249; temp_data/rfsi_10f_{obs,pred}.rda)."""
+    from rfsi_b200 import rda
+    base = Path("/root/reference/temp_croatia/temp_data")
+    st = rda.read_rda(base / "stfdf.rda")["stfdf"]
+    sp = st.attrs["sp"]
+    spd, d = sp.attrs["data"], st.attrs["data"]
+    daily = {n: np.asarray(d[n], dtype=np.float64).reshape(366, 157) for n in ("TEMP", "INSOL", "ctd", "MODIS.LST")}
+    static = {n: np.asarray(spd[n], dtype=np.float64) for n in ("HRdem", "HRdsea", "Lat", "Lon", "HRtwi")}
+    folds = rda.read_rda(base / "folds.rda")["strat"]["obs.fold.list"]
+    fold_of = np.zeros(157, dtype=np.int8)
+    for k, f in enumerate(folds):
+        fold_of[np.asarray(f) - 1] = k + 1
+    obs = np.asarray(list(rda.read_rda(base / "rfsi_10f_obs.rda").values())[0], dtype=np.float64)
+    pred = np.asarray(list(rda.read_rda(base / "rfsi_10f_pred.rda").values())[0], dtype=np.float64)
+    ok = ~np.isnan(obs)
+    np.savez_compressed(OUT / "croatia_llocv.npz", xy=np.asarray(sp.attrs["coords"], dtype=np.float64),
+                        TEMP=daily["TEMP"], INSOL=daily["INSOL"].astype(np.float32), ctd=daily["ctd"].astype(np.float32),
+                        MODIS_LST=daily["MODIS.LST"].astype(np.float32),
+                        **{k: v.astype(np.float32) for k, v in static.items()}, fold=fold_of,
+                        ref_rmse=np.sqrt(np.mean((obs[ok] - pred[ok]) ** 2)), ref_n=int(ok.sum()))
+
+
 if __name__ == "__main__":
     if Path("/root/reference").exists():
         knn_croatia_real()
+        croatia_llocv_inputs()
     knn_lattice()
     knn_realgeom()
     forest_small()
