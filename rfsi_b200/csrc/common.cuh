@@ -42,6 +42,18 @@ constexpr int kQDeltaBits = 20;
 constexpr uint32_t kQMaxDelta = 1u << kQDeltaBits;
 constexpr int kQMaxFeat = 1 << (32 - kQDeltaBits - 2);  // feat*4 must fit the top 12 bits
 
+// rank_of() narrows its binary search with a per-feature table of kRankBuckets monotone
+// buckets between the feature's smallest and largest threshold (forest.cuh)
+constexpr int kRankBuckets = 4096;
+__host__ __device__ __forceinline__ int rank_bucket(double x, double lo_half, double scale) {
+#ifdef __CUDA_ARCH__
+    const double t = __dmul_rn(__dsub_rn(__dmul_rn(x, 0.5), lo_half), scale);
+#else
+    const double t = (x * 0.5 - lo_half) * scale;   // host build: no FMA contraction on x86-64 SSE2
+#endif
+    return t >= (double)(kRankBuckets - 1) ? kRankBuckets - 1 : (t > 0.0 ? (int)t : 0);
+}
+
 constexpr int32_t kIdxNone = 0x7fffffff;        // empty slot of a neighbour list
 constexpr unsigned long long kNaRealBits = 0x7FF00000000007A2ULL;  // R NA_real_
 constexpr int32_t kNaInteger = INT32_MIN;                          // R NA_integer_

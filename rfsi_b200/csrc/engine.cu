@@ -187,12 +187,14 @@ struct rfsi_forest {
     std::vector<double> leaf_val;
     std::vector<double> uvals;
     std::vector<int32_t> uoff;
+    std::vector<double> rpar;         // [F][2] bucket function of rank_of()
+    std::vector<int32_t> rtab;        // [F][kRankBuckets+1]
     struct Image {
         Node* nodes = nullptr;
         double* leaf_sample = nullptr;
         int32_t* leaf_rid = nullptr;
         bool compact = false;
-        QForest q{nullptr, nullptr, nullptr, nullptr, nullptr};
+        QForest q{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     };
     mutable std::mutex mu;
     mutable std::map<int, Image> images;
@@ -219,6 +221,8 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
         RF_TRY(up(f->leaf_val.data(), f->leaf_val.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.leaf_val)));
         RF_TRY(up(f->uvals.data(), f->uvals.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.uvals)));
         RF_TRY(up(f->uoff.data(), f->uoff.size() * sizeof(int32_t), reinterpret_cast<const void**>(&im.q.uoff)));
+        RF_TRY(up(f->rpar.data(), f->rpar.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.rpar)));
+        RF_TRY(up(f->rtab.data(), f->rtab.size() * sizeof(int32_t), reinterpret_cast<const void**>(&im.q.rtab)));
     } else {
         CU_TRY(cudaMalloc(&im.nodes, f->nodes.size() * sizeof(Node)));
         CU_TRY(cudaMemcpy(im.nodes, f->nodes.data(), f->nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
@@ -285,6 +289,19 @@ void build_compact(rfsi_forest* f) {
     }
     f->uvals.resize((size_t)f->uoff[F]);
     for (int j = 0; j < F; ++j) std::copy(u[j].begin(), u[j].end(), f->uvals.begin() + f->uoff[j]);
+    // bucket tables for rank_of(): counts of thresholds per monotone bucket, prefix-summed
+    f->rpar.assign((size_t)F * 2, 0.0);
+    f->rtab.assign((size_t)F * (kRankBuckets + 1), 0);
+    for (int j = 0; j < F; ++j) {
+        int32_t* tab = f->rtab.data() + (size_t)j * (kRankBuckets + 1);
+        if (u[j].empty()) continue;
+        const double lo_half = u[j].front() * 0.5;
+        double scale = (double)kRankBuckets / (u[j].back() * 0.5 - lo_half);
+        if (!(scale < 1.0e300)) scale = 1.0e300;   // one threshold, or a tiny range: still monotone
+        f->rpar[2 * j] = lo_half; f->rpar[2 * j + 1] = scale;
+        for (double v : u[j]) ++tab[rank_bucket(v, lo_half, scale) + 1];
+        for (int b = 0; b < kRankBuckets; ++b) tab[b + 1] += tab[b];
+    }
 
     f->qnodes.assign(n, (uint64_t)0);                // leaf: {w0 = ~0xFFFFFFFF = 0, w1 = 0}
     f->leaf_val.assign(n, 0.0);
@@ -421,6 +438,7 @@ extern "C" void rfsi_forest_destroy(rfsi_forest_t* f) {
             cudaFree(const_cast<uint2*>(kv.second.q.nodes)); cudaFree(const_cast<QRoot*>(kv.second.q.roots));
             cudaFree(const_cast<double*>(kv.second.q.leaf_val)); cudaFree(const_cast<double*>(kv.second.q.uvals));
             cudaFree(const_cast<int32_t*>(kv.second.q.uoff));
+            cudaFree(const_cast<double*>(kv.second.q.rpar)); cudaFree(const_cast<int32_t*>(kv.second.q.rtab));
         }
         cudaSetDevice(cur);
     }
@@ -444,7 +462,7 @@ extern "C" int64_t rfsi_forest_info(const rfsi_forest_t* f, int what) {
         case 4: return f->leaf_sample.empty() ? 0 : 1;
         case 5:
             if (f->compact_ok && env_int("RFSI_B200_COMPACT", 1) != 0)
-                return (int64_t)(f->qnodes.size() * 8 + f->leaf_val.size() * 8 + f->uvals.size() * 8 +
+                return (int64_t)(f->qnodes.size() * 8 + f->leaf_val.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
                                  f->qroots.size() * sizeof(QRoot) + f->leaf_sample.size() * sizeof(double));
             return (int64_t)(f->nodes.size() * sizeof(Node) + f->leaf_sample.size() * sizeof(double));
         case 6: return f->n_internal;

@@ -27,13 +27,19 @@ struct QForest {
     const double* leaf_val;   // [n] prediction at leaf indices
     const double* uvals;      // sorted unique thresholds, features concatenated
     const int32_t* uoff;      // [F+1]
+    const double* rpar;       // [F][2] {lo/2, scale} of the bucket function of feature f
+    const int32_t* rtab;      // [F][kRankBuckets+1] number of thresholds in buckets < b
 };
 
-// number of thresholds of feature f strictly below x (x is never NaN here)
+// number of thresholds of feature f strictly below x (x is never NaN here).  The bucket
+// function is monotone, so every threshold in an earlier bucket is < x and every one in a later
+// bucket is > x: only x's own bucket (a few dozen thresholds) needs the binary search.
 __device__ __forceinline__ uint32_t rank_of(const QForest& q, int f, double x) {
     const double* __restrict__ u = q.uvals + q.uoff[f];
-    int n = q.uoff[f + 1] - q.uoff[f];
-    int lo = 0;
+    const int b = rank_bucket(x, __ldg(q.rpar + 2 * f), __ldg(q.rpar + 2 * f + 1));
+    const int32_t* __restrict__ tab = q.rtab + (size_t)f * (kRankBuckets + 1);
+    int lo = __ldg(tab + b);
+    int n = __ldg(tab + b + 1) - lo;
     while (n > 0) {
         const int half = n >> 1;
         if (__ldg(u + lo + half) < x) { lo += half + 1; n -= half + 1; } else { n = half; }
