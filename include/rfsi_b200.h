@@ -72,6 +72,14 @@ int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix,
                       int32_t nobs, int32_t n_obs, int32_t rm_dupl,
                       double* out_dist, double* out_obs, int32_t* out_idx, int device);
 
+/* fp32 twin (float buffers): coordinates are widened to fp64 on the device and searched with
+ * the fp64 kernels, so indices equal those of the fp64 call on the same coordinates and
+ * dist/obs are its results rounded to float (1e-5 relative, north_star's fp32 mode). */
+int rfsi_near_obs_f32(const float* loc_x, const float* loc_y, int64_t npix,
+                      const float* obs_x, const float* obs_y, const float* obs_z,
+                      int32_t nobs, int32_t n_obs, int32_t rm_dupl,
+                      float* out_dist, float* out_obs, int32_t* out_idx, int device);
+
 int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix,
                           const double* obs_x, const double* obs_y, const double* obs_z,
                           int32_t nobs, int32_t n_obs, int32_t rm_dupl,

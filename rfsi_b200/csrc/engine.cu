@@ -937,6 +937,83 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
     return RFSI_OK;
 }
 
+// fp32 twin of near.obs: float buffers in and out; coordinates are widened to fp64 on the
+// device and the search itself is the fp64 one, so neighbour indices are those of the fp64
+// call on the same (float-representable) coordinates and dist/obs are its results rounded to
+// float (north_star: 1e-5 relative in fp32 mode).
+namespace {
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];   // NA_real_ stays a NaN
+}
+}  // namespace
+
+extern "C" int rfsi_near_obs_f32(const float* loc_x, const float* loc_y, int64_t npix, const float* obs_x,
+                                 const float* obs_y, const float* obs_z, int32_t nobs, int32_t n_obs, int32_t rm_dupl,
+                                 float* out_dist, float* out_obs, int32_t* out_idx, int device)
+{
+    if (npix < 0 || nobs < 0 || n_obs < 1) return fail(RFSI_E_ARG, "near_obs_f32: npix/nobs must be >= 0, n.obs >= 1");
+    if (npix > 0 && (!loc_x || !loc_y || !out_dist || !out_obs)) return fail(RFSI_E_ARG, "near_obs_f32: NULL buffer");
+    if (nobs > 0 && (!obs_x || !obs_y || !obs_z)) return fail(RFSI_E_ARG, "near_obs_f32: NULL observations");
+    for (int32_t s = 0; s < nobs; ++s)
+        if (obs_x[s] != obs_x[s] || obs_y[s] != obs_y[s])
+            return fail(RFSI_E_NA_INPUT, "near_obs_f32: observation %d has an NA coordinate", s + 1);
+    RF_TRY(use_device(device));
+    if (npix == 0) return RFSI_OK;
+    const int64_t chunk = std::min<int64_t>(npix, 1 << 20);
+    const int64_t nmax = std::max<int64_t>(chunk * n_obs, std::max<int64_t>(nobs, 1));
+    DevBuf f_in, d_lx, d_ly, d_ox, d_oy, d_oz, d_dist, d_obs, d_idx, f_out, d_warn;
+    RF_TRY(f_in.alloc(sizeof(float) * std::max<int64_t>(chunk, std::max<int64_t>(nobs, 1))));
+    RF_TRY(d_lx.alloc(sizeof(double) * chunk)); RF_TRY(d_ly.alloc(sizeof(double) * chunk));
+    RF_TRY(d_ox.alloc(sizeof(double) * std::max(nobs, 1))); RF_TRY(d_oy.alloc(sizeof(double) * std::max(nobs, 1)));
+    RF_TRY(d_oz.alloc(sizeof(double) * std::max(nobs, 1)));
+    RF_TRY(d_dist.alloc(sizeof(double) * chunk * n_obs)); RF_TRY(d_obs.alloc(sizeof(double) * chunk * n_obs));
+    if (out_idx) RF_TRY(d_idx.alloc(sizeof(int32_t) * chunk * n_obs));
+    RF_TRY(f_out.alloc(sizeof(float) * nmax));
+    RF_TRY(d_warn.alloc(sizeof(int)));
+    CU_TRY(cudaMemset(d_warn.p, 0, sizeof(int)));
+    auto widen = [&](const float* host, double* dev, int64_t n) -> int {
+        if (n == 0) return RFSI_OK;
+        CU_TRY(cudaMemcpy(f_in.p, host, sizeof(float) * n, cudaMemcpyHostToDevice));
+        f32_to_f64_kernel<<<(unsigned)((n + 255) / 256), 256>>>(f_in.as<float>(), dev, n);
+        count_launch();
+        CU_TRY(cudaGetLastError());
+        return RFSI_OK;
+    };
+    auto narrow = [&](const double* dev, float* host, int64_t cur, int64_t p0) -> int {
+        f64_to_f32_kernel<<<(unsigned)((cur * n_obs + 255) / 256), 256>>>(dev, f_out.as<float>(), cur * n_obs);
+        count_launch();
+        CU_TRY(cudaMemcpy2D(host + p0, sizeof(float) * npix, f_out.p, sizeof(float) * cur, sizeof(float) * cur, n_obs,
+                            cudaMemcpyDeviceToHost));
+        return RFSI_OK;
+    };
+    RF_TRY(widen(obs_x, d_ox.as<double>(), nobs)); RF_TRY(widen(obs_y, d_oy.as<double>(), nobs));
+    RF_TRY(widen(obs_z, d_oz.as<double>(), nobs));
+    for (int64_t p0 = 0; p0 < npix; p0 += chunk) {
+        const int64_t cur = std::min(chunk, npix - p0);
+        RF_TRY(widen(loc_x + p0, d_lx.as<double>(), cur)); RF_TRY(widen(loc_y + p0, d_ly.as<double>(), cur));
+        RF_TRY(rfsi_dev_near_obs_f64(d_lx.as<double>(), d_ly.as<double>(), cur, d_ox.as<double>(), d_oy.as<double>(),
+                                     d_oz.as<double>(), nobs, n_obs, rm_dupl, d_dist.as<double>(), d_obs.as<double>(),
+                                     out_idx ? d_idx.as<int32_t>() : nullptr, d_warn.as<int>(), device, nullptr));
+        RF_TRY(narrow(d_dist.as<double>(), out_dist, cur, p0));
+        RF_TRY(narrow(d_obs.as<double>(), out_obs, cur, p0));
+        if (out_idx)
+            CU_TRY(cudaMemcpy2D(out_idx + p0, sizeof(int32_t) * npix, d_idx.p, sizeof(int32_t) * cur,
+                                sizeof(int32_t) * cur, n_obs, cudaMemcpyDeviceToHost));
+    }
+    int warn = 0;
+    CU_TRY(cudaMemcpy(&warn, d_warn.p, sizeof warn, cudaMemcpyDeviceToHost));
+    if (warn) {
+        g_err = "near_obs_f32: fewer observations than n.obs(+1); missing neighbours are NA";
+        return RFSI_W_TOO_FEW_OBS;
+    }
+    return RFSI_OK;
+}
+
 // near.obs for all days of a station table (the per-day feature / training table)
 extern "C" int rfsi_near_obs_days_f64(const double* loc_x, const double* loc_y, int64_t npix, const double* obs_x,
                                       const double* obs_y, const double* obs_z, int32_t nobs, int32_t ndays,

@@ -204,3 +204,26 @@ def test_near_obs_days_training_table_and_prediction_shapes():
         assert (dist[d][ok][:, 0] > 0).all()
         ed, eo, _, _ = oracle.near_obs(loc, xy[ok], z[d][ok], n)
         _same(pd_[d], ed); _same(po_[d], eo)
+
+
+def test_near_obs_f32_twin():
+    """float buffers in/out: same neighbours as the fp64 call on the same coordinates,
+    distances/observations within 1e-5 relative (north_star's fp32 mode)."""
+    import ctypes as C
+    from rfsi_b200 import _lib
+    rng = np.random.default_rng(4)
+    loc = rng.uniform(0, 1000, size=(5000, 2)).astype(np.float32)
+    obs = rng.uniform(0, 1000, size=(300, 2)).astype(np.float32)
+    z = rng.normal(size=300).astype(np.float32)
+    n = 9
+    dist = np.empty((n, 5000), dtype=np.float32); val = np.empty((n, 5000), dtype=np.float32)
+    idx = np.empty((n, 5000), dtype=np.int32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    lx, ly = np.ascontiguousarray(loc[:, 0]), np.ascontiguousarray(loc[:, 1])
+    ox, oy = np.ascontiguousarray(obs[:, 0]), np.ascontiguousarray(obs[:, 1])
+    rc = _lib.load().rfsi_near_obs_f32(P(lx), P(ly), 5000, P(ox), P(oy), P(z), 300, n, 1, P(dist), P(val), P(idx), 0)
+    assert rc == 0
+    ed, eo, ei, _ = oracle.near_obs(loc.astype(np.float64), obs.astype(np.float64), z.astype(np.float64), n)
+    np.testing.assert_array_equal(idx.T, ei)
+    np.testing.assert_allclose(dist.T, ed, rtol=1e-5)
+    np.testing.assert_array_equal(val.T, eo.astype(np.float32))
