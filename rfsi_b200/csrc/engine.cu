@@ -655,13 +655,6 @@ int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, const int
     return RFSI_OK;
 }
 
-// Default: leaf values are summed in sequential tree order (bit-identical to the CPU oracle).
-// RFSI_B200_REFILL=1 selects the per-warp slot-refill walk (traverse_q_refill: per-slot partial
-// sums, <= 1e-13 rel).  It does ~25 % fewer node loads but measured SLOWER on B200 (107 vs
-// 117 M pixel-days/s on the C5 bench: the extra REDUX/branch/partial-sum work costs more than
-// the saved L1 hits), so it is opt-in and kept for the tests that cover it.
-int use_refill() { return env_int("RFSI_B200_REFILL", 0) ? 1 : 0; }
-
 // trees in flight per thread: measured best 12 for the 16-byte format, 8 for the compact one
 thread_local int g_default_J = 12;
 int forest_J() {
@@ -698,11 +691,11 @@ int launch_forest_xq_pj(const rfsi_forest* f, const QForest& q, const double* X,
         if (visits) {
             auto kern = forest_xq_kernel<P, J, true>;
             CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, P, smem, stream>>>(q, cb[c], cb[c + 1], T, F, X, npix, ldx, o, visits, na_flag, use_refill());
+            kern<<<grid, P, smem, stream>>>(q, cb[c], cb[c + 1], T, F, X, npix, ldx, o, visits, na_flag);
         } else {
             auto kern = forest_xq_kernel<P, J, false>;
             CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, P, smem, stream>>>(q, cb[c], cb[c + 1], T, F, X, npix, ldx, o, visits, na_flag, use_refill());
+            kern<<<grid, P, smem, stream>>>(q, cb[c], cb[c + 1], T, F, X, npix, ldx, o, visits, na_flag);
         }
         count_launch();
         CU_TRY(cudaGetLastError());
@@ -1510,7 +1503,6 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
     fp.nodes = im.nodes; fp.q = im.q; fp.leaf_sample = im.leaf_sample; fp.leaf_rid = nullptr;
     fp.T = f->ntrees; fp.F = f->nfeat;
     fp.acc = acc;
-    fp.refill = use_refill();
     fp.fb_list = fb; fp.fb_count = fb_count; fp.fb_capacity = (unsigned int)std::min<int64_t>(pl.rows, 0xffffffffLL);
     fp.counters = counters; fp.na_flag = na_flag;
     fp.tile2d = (env_int("RFSI_B200_TILE2D", 1) && loc_rows(L, a->npix)) ? 1 : 0;

@@ -175,73 +175,6 @@ __device__ __forceinline__ double traverse_q(const QForest& q, int t_begin, int 
     return sum;
 }
 
-// Same walk, but a slot moves on to its next tree as soon as every lane of the warp has
-// reached a leaf in the current one (one REDUX.AND per iteration over the J leaf flags),
-// instead of idling until the deepest of J trees is done: ~25 % fewer node loads.  Slot j
-// owns trees t_begin+j, +J, ... and keeps its own partial sum; the partial sums are added in
-// slot order at the end.  Deterministic, but not the sequential tree-order sum: results
-// differ from it by a few ulp (<= 1e-13 relative), inside the 1e-12 tolerance.  The lanes
-// of a warp advance together, so they keep sharing node loads.
-template <int P, int J, bool COUNT>
-__device__ __forceinline__ double traverse_q_refill(const QForest& q, int t_begin, int t_end, int T, double sum,
-                                                    const uint32_t* __restrict__ rs, const ForestOut& o,
-                                                    long long row, unsigned& nvisit, unsigned lanes)
-{
-    const char* rsb = reinterpret_cast<const char*>(rs);
-    uint32_t idx[J];
-    int tj[J];
-    double part[J];
-    unsigned alive = 0;  // warp-uniform: slot j still has a tree
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        part[j] = 0.0;
-        tj[j] = t_begin + j;
-        idx[j] = 0;
-        if (tj[j] < t_end) {
-            alive |= 1u << j;
-            const uint4 r = __ldg(reinterpret_cast<const uint4*>(q.roots + tj[j]));
-            idx[j] = q_step(r.z, 0u, r.x, *reinterpret_cast<const uint32_t*>(rsb + r.y * P));
-            if (COUNT) nvisit += (r.x != ~kQLeafRank) ? 1u : 0u;
-        }
-    }
-    while (alive) {
-        uint2 w[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) w[j] = __ldg(q.nodes + idx[j]);
-        unsigned leafbits = 0;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const uint32_t xr = *reinterpret_cast<const uint32_t*>(rsb + (w[j].y >> kQDeltaBits) * P);
-            idx[j] = q_step(idx[j], w[j].y & (kQMaxDelta - 1), w[j].x, xr);
-            leafbits |= (w[j].y == 0 ? 1u : 0u) << j;
-            if (COUNT) nvisit += (w[j].y != 0) ? 1u : 0u;
-        }
-        const unsigned done = __reduce_and_sync(lanes, leafbits) & alive;
-        if (done) {  // warp-uniform
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                if (done & (1u << j)) {
-                    part[j] += __ldg(q.leaf_val + idx[j]);
-                    if (o.samples) o.samples[row * T + tj[j]] = o.leaf_sample[idx[j]];
-                    if (o.terminal) o.terminal[(long long)tj[j] * o.ld_term + row] = o.leaf_rid[idx[j]];
-                    tj[j] += J;
-                    if (tj[j] < t_end) {
-                        const uint4 r = __ldg(reinterpret_cast<const uint4*>(q.roots + tj[j]));
-                        idx[j] = q_step(r.z, 0u, r.x, *reinterpret_cast<const uint32_t*>(rsb + r.y * P));
-                        if (COUNT) nvisit += (r.x != ~kQLeafRank) ? 1u : 0u;
-                    } else {
-                        alive &= ~(1u << j);
-                        idx[j] = 0;  // a harmless absorbing slot
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < J; ++j) sum += part[j];
-    return sum;
-}
-
 template <int P>
 __host__ __device__ constexpr size_t forest_q_smem_bytes(int F) {
     return (size_t)F * P * sizeof(uint32_t);
@@ -251,7 +184,7 @@ template <int P, int J, bool COUNT>
 __global__ void __launch_bounds__(P, (P * 64 * 4 <= 65536) ? 4 : 2)
 forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* __restrict__ X,
                  long long npix, long long ldx, ForestOut o, unsigned long long* __restrict__ visits,
-                 int* __restrict__ na_flag, int refill)
+                 int* __restrict__ na_flag)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* rs = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
@@ -266,15 +199,13 @@ forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* 
         }
     }
     unsigned nvisit = 0;
-    const unsigned lanes = __ballot_sync(0xffffffffu, in_range && !has_na);
     if (in_range) {
         if (has_na) {
             if (na_flag) *na_flag = 1;
             if (o.mean) o.mean[p] = na_real();
         } else {
             double sum = (t_begin > 0 && o.mean) ? o.mean[p] : 0.0;
-            if (refill) sum = traverse_q_refill<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit, lanes);
-            else sum = traverse_q<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
+            sum = traverse_q<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
             if (o.mean) o.mean[p] = (t_end == T) ? sum / (double)T : sum;
         }
     }

@@ -52,7 +52,6 @@ struct FusedParams {
     const double* leaf_sample;
     const int32_t* leaf_rid;
     int T, F;
-    int refill;                  // compact format: slots refill per warp (traverse_q_refill)
     int t_begin, t_end;          // this launch walks trees [t_begin, t_end) (one L2-sized chunk)
     double* acc;                 // [ndays*npix] running tree-order sums between chunk launches
     // outputs; row index = (d - day0)*npix + p relative to the *_base pointers
@@ -233,7 +232,6 @@ fused_kernel(const __grid_constant__ FusedParams a)
     }
 
     unsigned nvisit = 0;
-    const unsigned lanes = __ballot_sync(0xffffffffu, ok);
     if (ok) {
         ForestOut o;
         o.mean = nullptr;
@@ -244,11 +242,7 @@ fused_kernel(const __grid_constant__ FusedParams a)
         o.ld_term = 0;
         if (!Q) fs[a.F * P] = __longlong_as_double(0xFFF0000000000000LL);  // sentinel row: -inf
         double sum = a.t_begin > 0 ? a.acc[row] : 0.0;
-        if (Q && a.refill)
-            sum = traverse_q_refill<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
-                                                 reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row,
-                                                 nvisit, lanes);
-        else if (Q)
+        if (Q)
             sum = traverse_q<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
                                           reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
         else

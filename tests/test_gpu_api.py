@@ -8,7 +8,7 @@ import oracle
 import rfsi_b200 as rb
 from rfsi_b200 import synth
 from rfsi_b200.rfsi import pred_rfsi, rfsi
-from tests.util import same_mean, sum_mode  # noqa: F401  (runs every test in both summation modes)
+from tests.util import same_mean
 
 pytestmark = pytest.mark.gpu
 

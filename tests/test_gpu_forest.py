@@ -11,7 +11,7 @@ import oracle
 import rfsi_b200 as rb
 from rfsi_b200 import synth
 from rfsi_b200.forest import FlatForest
-from tests.util import same_mean, sum_mode  # noqa: F401  (runs every test in both summation modes)
+from tests.util import same_mean
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
