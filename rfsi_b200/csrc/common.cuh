@@ -42,6 +42,22 @@ constexpr int kQDeltaBits = 20;
 constexpr uint32_t kQMaxDelta = 1u << kQDeltaBits;
 constexpr int kQMaxFeat = 1 << (32 - kQDeltaBits - 2);  // feat*4 must fit the top 12 bits
 
+// Blocked ("b4") format, the default when it fits: the tree is cut into blocks of 4 levels,
+// one 128-byte line each: 32 words, word 0 spare, words 1..15 an implicit heap of up to 15
+// nodes (children of slot h at 2h and 2h+1), words 16..31 the 16 exits.
+//   node word  = ~((rank << 8) | feat)   (feat < 256, rank < 2^24 - 1)
+//   exit word  = index of the next block, or 0x80000000 | leaf node index
+// A node goes right iff rank(x) > rank, i.e. iff (rank(x) << 8) + ~((rank << 8) | feat) carries
+// (the feat byte can never make up the difference), so a level is one 32-bit node load, one
+// 32-bit shared load of the pixel's pre-shifted rank, and add.cc / addc h = 2h + carry.  A
+// leaf met before the fourth level is padded with pass-through nodes (rank 0xFFFFFF: never
+// exceeded) down to its exits.  Per 4 levels: 5 loads of 4 bytes from ONE line instead of 4
+// loads of 8 bytes from up to 4 lines.
+constexpr uint32_t kBLeafFlag = 0x80000000u;
+constexpr uint32_t kBPassWord = ~((0xFFFFFFu << 8) | 0u);   // complemented pass-through node
+constexpr int kBMaxFeat = 256;
+constexpr uint32_t kBMaxRank = 0xFFFFFEu;
+
 // rank_of() narrows its binary search with a per-feature table of kRankBuckets monotone
 // buckets between the feature's smallest and largest threshold (forest.cuh)
 constexpr int kRankBuckets = 4096;

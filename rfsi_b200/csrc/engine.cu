@@ -189,12 +189,16 @@ struct rfsi_forest {
     std::vector<int32_t> uoff;
     std::vector<double> rpar;         // [F][2] bucket function of rank_of()
     std::vector<int32_t> rtab;        // [F][kRankBuckets+1]
+    // blocked format (common.cuh)
+    bool blocked_ok = false;
+    std::vector<uint32_t> blocks;     // 32 words per block, block 0 = all pass-through
+    std::vector<uint32_t> broot;      // [T]
     struct Image {
         Node* nodes = nullptr;
         double* leaf_sample = nullptr;
         int32_t* leaf_rid = nullptr;
         bool compact = false;
-        QForest q{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        QForest q{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     };
     mutable std::mutex mu;
     mutable std::map<int, Image> images;
@@ -207,7 +211,10 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
     auto it = f->images.find(device);
     if (it != f->images.end()) { *out = it->second; return RFSI_OK; }
     rfsi_forest::Image im;
-    im.compact = f->compact_ok && env_int("RFSI_B200_COMPACT", 1) != 0;
+    // RFSI_B200_COMPACT: 0 = 16-byte fp64 nodes, 1 = 8-byte rank nodes, 2 (default) = 4-byte blocked
+    const int want = env_int("RFSI_B200_COMPACT", 2);
+    im.compact = f->compact_ok && want != 0;
+    const bool blocked = im.compact && f->blocked_ok && want >= 2;
     if (im.compact) {
         auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
             void* d = nullptr;
@@ -216,7 +223,13 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
             *dst = d;
             return RFSI_OK;
         };
-        RF_TRY(up(f->qnodes.data(), f->qnodes.size() * sizeof(uint64_t), reinterpret_cast<const void**>(&im.q.nodes)));
+        if (blocked) {
+            RF_TRY(up(f->blocks.data(), f->blocks.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.blocks)));
+            RF_TRY(up(f->broot.data(), f->broot.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.broot)));
+            im.q.rank_shift = 8;
+        } else {
+            RF_TRY(up(f->qnodes.data(), f->qnodes.size() * sizeof(uint64_t), reinterpret_cast<const void**>(&im.q.nodes)));
+        }
         RF_TRY(up(f->qroots.data(), f->qroots.size() * sizeof(QRoot), reinterpret_cast<const void**>(&im.q.roots)));
         RF_TRY(up(f->leaf_val.data(), f->leaf_val.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.leaf_val)));
         RF_TRY(up(f->uvals.data(), f->uvals.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.uvals)));
@@ -338,6 +351,55 @@ void build_compact(rfsi_forest* f) {
     }
     if (!ok) { f->qnodes.clear(); f->qroots.clear(); f->leaf_val.clear(); return; }
     f->compact_ok = true;
+
+    // ---- blocked image: 4 levels per 128-byte block (common.cuh) ----
+    f->blocked_ok = false;
+    if (F > kBMaxFeat) return;
+    for (int j = 0; j < F; ++j)
+        if (u[j].size() > (size_t)kBMaxRank) return;
+    std::vector<uint32_t>& B = f->blocks;
+    B.assign(32, kBPassWord);   // block 0: pass-through everywhere; its exits are never used
+    f->broot.assign((size_t)T, 0u);
+    struct Pending { uint32_t node, block; };
+    std::vector<Pending> todo;
+    bool fits = true;
+    // fill the heap of block `blk` below slot `pos` with the subtree rooted at wide node `nd`
+    auto place = [&](auto&& self, uint32_t blk, uint32_t nd, uint32_t pos) -> void {
+        const Node& n0 = f->nodes[nd];
+        const bool leaf = n0.feat >= F;
+        if (pos >= 16) {   // an exit
+            if (leaf) { B[(size_t)blk * 32 + pos] = kBLeafFlag | nd; return; }
+            const size_t nb = B.size() / 32;
+            if (nb >= 0x7fffffffu) { fits = false; return; }
+            B.resize(B.size() + 32, kBPassWord);
+            B[(size_t)blk * 32 + pos] = (uint32_t)nb;
+            todo.push_back({nd, (uint32_t)nb});
+            return;
+        }
+        if (leaf) {        // pad down to the exits
+            B[(size_t)blk * 32 + pos] = kBPassWord;
+            self(self, blk, nd, 2 * pos);
+            self(self, blk, nd, 2 * pos + 1);
+            return;
+        }
+        B[(size_t)blk * 32 + pos] = ~((rank_at(n0) << 8) | (uint32_t)n0.feat);
+        self(self, blk, (uint32_t)n0.child, 2 * pos);
+        self(self, blk, (uint32_t)n0.child + 1, 2 * pos + 1);
+    };
+    for (int t = 0; t < T && fits; ++t) {
+        if (f->nodes[t].feat >= F) { f->broot[t] = kBLeafFlag | (uint32_t)t; continue; }
+        const size_t nb = B.size() / 32;
+        B.resize(B.size() + 32, kBPassWord);
+        f->broot[t] = (uint32_t)nb;
+        todo.clear();
+        todo.push_back({(uint32_t)t, (uint32_t)nb});
+        for (size_t i = 0; i < todo.size() && fits; ++i) {   // blocks of a tree in BFS order
+            const Pending pd = todo[i];
+            place(place, pd.block, pd.node, 1);
+        }
+    }
+    if (!fits) { B.clear(); f->broot.clear(); return; }
+    f->blocked_ok = true;
 }
 
 }  // namespace
@@ -439,6 +501,7 @@ extern "C" void rfsi_forest_destroy(rfsi_forest_t* f) {
             cudaFree(const_cast<double*>(kv.second.q.leaf_val)); cudaFree(const_cast<double*>(kv.second.q.uvals));
             cudaFree(const_cast<int32_t*>(kv.second.q.uoff));
             cudaFree(const_cast<double*>(kv.second.q.rpar)); cudaFree(const_cast<int32_t*>(kv.second.q.rtab));
+            cudaFree(const_cast<uint32_t*>(kv.second.q.blocks)); cudaFree(const_cast<uint32_t*>(kv.second.q.broot));
         }
         cudaSetDevice(cur);
     }
@@ -461,12 +524,17 @@ extern "C" int64_t rfsi_forest_info(const rfsi_forest_t* f, int what) {
         case 3: return f->max_depth;
         case 4: return f->leaf_sample.empty() ? 0 : 1;
         case 5:
-            if (f->compact_ok && env_int("RFSI_B200_COMPACT", 1) != 0)
+            if (f->compact_ok && f->blocked_ok && env_int("RFSI_B200_COMPACT", 2) >= 2)
+                return (int64_t)(f->blocks.size() * 4 + f->leaf_val.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
+                                 f->leaf_sample.size() * sizeof(double));
+            if (f->compact_ok && env_int("RFSI_B200_COMPACT", 2) != 0)
                 return (int64_t)(f->qnodes.size() * 8 + f->leaf_val.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
                                  f->qroots.size() * sizeof(QRoot) + f->leaf_sample.size() * sizeof(double));
             return (int64_t)(f->nodes.size() * sizeof(Node) + f->leaf_sample.size() * sizeof(double));
         case 6: return f->n_internal;
-        case 7: return (f->compact_ok && env_int("RFSI_B200_COMPACT", 1) != 0) ? 1 : 0;
+        case 7: return !(f->compact_ok && env_int("RFSI_B200_COMPACT", 2) != 0) ? 0
+                       : ((f->blocked_ok && env_int("RFSI_B200_COMPACT", 2) >= 2) ? 2 : 1);
+        case 9: return (int64_t)f->blocks.size() / 32;
         case 8: return (int64_t)f->uvals.size();
         default: return -1;
     }
@@ -1402,13 +1470,16 @@ template <int P, int J, bool FALLBACK, bool Q>
 int launch_fused_pj(const FusedParams& fp, unsigned grid, int k, bool count, cudaStream_t st) {
     const size_t smem = fused_smem_bytes<P, Q>(fp.F, k, FALLBACK);
     ProfScope ps(FALLBACK ? PROF_FALLBACK : PROF_FUSED, st);
+    const int carve = env_int("RFSI_B200_CARVEOUT", -1);   // experiment knob: shared-memory carveout in percent
     if (count) {
         auto kern = fused_kernel<P, J, true, FALLBACK, Q>;
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (carve >= 0) CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         kern<<<grid, P, smem, st>>>(fp);
     } else {
         auto kern = fused_kernel<P, J, false, FALLBACK, Q>;
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (carve >= 0) CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         kern<<<grid, P, smem, st>>>(fp);
     }
     count_launch();

@@ -29,6 +29,9 @@ struct QForest {
     const int32_t* uoff;      // [F+1]
     const double* rpar;       // [F][2] {lo/2, scale} of the bucket function of feature f
     const int32_t* rtab;      // [F][kRankBuckets+1] number of thresholds in buckets < b
+    const uint32_t* blocks;   // blocked format (common.cuh): 32 words per block; nullptr = use `nodes`
+    const uint32_t* broot;    // [T] root block of each tree (or a leaf marker)
+    int rank_shift;           // ranks are stored in shared memory shifted left by this (8 when blocked)
 };
 
 // number of thresholds of feature f strictly below x (x is never NaN here).  The bucket
@@ -175,6 +178,62 @@ __device__ __forceinline__ double traverse_q(const QForest& q, int t_begin, int 
     return sum;
 }
 
+// Blocked-format walk (common.cuh).  rs holds the pixel's ranks << 8.  All J chains hop block by
+// block in lockstep: four unrolled levels, then the exit word.  A finished chain (leaf marker in
+// bb) idles on the all-pass-through block 0 until the slowest chain of the group is done.
+template <int P, int J, bool COUNT>
+__device__ __forceinline__ double traverse_b(const QForest& q, int t_begin, int t_end, int T, double sum,
+                                             const uint32_t* __restrict__ rs, const ForestOut& o, long long row,
+                                             unsigned& nvisit)
+{
+    const char* rsb = reinterpret_cast<const char*>(rs);
+    for (int t0 = t_begin; t0 < t_end; t0 += J) {
+        uint32_t bb[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) bb[j] = __ldg(q.broot + min(t0 + j, t_end - 1));
+        uint32_t all_done;
+        do {
+            uint32_t h[J];
+            const uint32_t* blk[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                blk[j] = q.blocks + (size_t)((bb[j] & kBLeafFlag) ? 0u : bb[j]) * 32u;
+                h[j] = 1u;
+            }
+#pragma unroll
+            for (int lev = 0; lev < 4; ++lev) {
+                uint32_t w[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) w[j] = __ldg(blk[j] + h[j]);
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (~w[j] & 0xFFu) * (P * 4));
+                    h[j] = q_step(h[j], h[j], w[j], xs);   // 2h + (xs > ~w)
+                    if (COUNT) nvisit += (w[j] != kBPassWord && !(bb[j] & kBLeafFlag)) ? 1u : 0u;
+                }
+            }
+            all_done = kBLeafFlag;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const uint32_t e = __ldg(blk[j] + h[j]);
+                bb[j] = (bb[j] & kBLeafFlag) ? bb[j] : e;
+                all_done &= bb[j];
+            }
+        } while (!all_done);
+#pragma unroll
+        for (int j = 0; j < J; ++j) bb[j] &= ~kBLeafFlag;   // leaf node indices
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            if (t0 + j < t_end) {
+                sum += __ldg(q.leaf_val + bb[j]);
+                if (o.terminal) o.terminal[(long long)(t0 + j) * o.ld_term + row] = o.leaf_rid[bb[j]];
+            }
+        }
+        if (o.samples) store_samples<J>(o, row * T + t0, t_end - t0, bb);
+    }
+    return sum;
+}
+
 template <int P>
 __host__ __device__ constexpr size_t forest_q_smem_bytes(int F) {
     return (size_t)F * P * sizeof(uint32_t);
@@ -195,7 +254,7 @@ forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* 
         for (int f = 0; f < F; ++f) {
             const double v = X[(long long)f * ldx + p];
             has_na |= (v != v);
-            rs[f * P] = rank_of(q, f, v);
+            rs[f * P] = rank_of(q, f, v) << q.rank_shift;
         }
     }
     unsigned nvisit = 0;
@@ -205,7 +264,8 @@ forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* 
             if (o.mean) o.mean[p] = na_real();
         } else {
             double sum = (t_begin > 0 && o.mean) ? o.mean[p] : 0.0;
-            sum = traverse_q<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
+            if (q.blocks) sum = traverse_b<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
+            else sum = traverse_q<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
             if (o.mean) o.mean[p] = (t_end == T) ? sum / (double)T : sum;
         }
     }

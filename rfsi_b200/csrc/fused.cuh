@@ -95,7 +95,7 @@ __device__ __forceinline__ int16_t centi_i16(double v) {
 // feature row r of this thread's pixel: fp64 value (wide format) or its rank (compact format)
 template <int P, bool Q>
 __device__ __forceinline__ void put_feature(const FusedParams& a, unsigned char* smem_raw, int r, double v) {
-    if (Q) (reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x)[r * P] = rank_of(a.q, r, v);
+    if (Q) (reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x)[r * P] = rank_of(a.q, r, v) << a.q.rank_shift;
     else (reinterpret_cast<double*>(smem_raw) + threadIdx.x)[r * P] = v;
 }
 
@@ -242,7 +242,10 @@ fused_kernel(const __grid_constant__ FusedParams a)
         o.ld_term = 0;
         if (!Q) fs[a.F * P] = __longlong_as_double(0xFFF0000000000000LL);  // sentinel row: -inf
         double sum = a.t_begin > 0 ? a.acc[row] : 0.0;
-        if (Q)
+        if (Q && a.q.blocks)
+            sum = traverse_b<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
+                                          reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
+        else if (Q)
             sum = traverse_q<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
                                           reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
         else

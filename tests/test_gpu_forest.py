@@ -142,14 +142,15 @@ def test_forest_properties_at_simulation_size():
 
 
 def test_wide_and_compact_node_formats_agree(monkeypatch):
-    """The 8-byte rank-quantised image and the 16-byte fp64 image make identical decisions."""
+    """The blocked 4-byte image (default), the 8-byte rank-quantised image and the 16-byte fp64
+    image make identical decisions."""
     flat, rng = _random_forest_case(11, 3000, 20, 64, 2)
     X = rng.normal(size=(20000, 20))
     X[::7, 3] = flat.split_val[flat.left != 0][:len(X[::7])][:X[::7].shape[0]]   # features exactly ON thresholds
     exp = oracle.forest_predict(flat.as_dict(), X, threads=8)
     probs = [0.25, 0.5, 0.75]
     expq = oracle.forest_quantiles(flat.as_dict(), X, probs, threads=8)
-    for compact in ("1", "0"):
+    for compact in ("2", "1", "0"):
         monkeypatch.setenv("RFSI_B200_COMPACT", compact)
         model = rb.RangerForest(flat)
         assert model.info()["nodes"] > 0
