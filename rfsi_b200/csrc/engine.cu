@@ -1501,7 +1501,8 @@ int launch_fused_p(const FusedParams& fp, unsigned grid, int k, bool count, cuda
 
 // One pixel chunk, all days, everything already on the device.
 int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPlan& pl, void* workspace,
-              unsigned long long* counters, int device, cudaStream_t st, bool reuse_candidates)
+              unsigned long long* counters, int device, cudaStream_t st, bool reuse_candidates,
+              bool count_visits)
 {
     rfsi_forest::Image im;
     RF_TRY(forest_image(f, device, &im));
@@ -1593,7 +1594,9 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
     } else {
         ntiles = (a->npix + Pm - 1) / Pm;
     }
-    const bool count = counters != nullptr;
+    // node-visit counting (counters[0..1]) costs issue slots in the hot loop: only on request.
+    // The too-few / fallback counters (counters[2..3]) are kept whenever `counters` is given.
+    const bool count = counters != nullptr && count_visits;
     const std::vector<int> cb = tree_chunks(f);
 
     for (int d0 = 0; d0 < a->ndays; d0 += pl.db) {
@@ -1649,7 +1652,7 @@ extern "C" int rfsi_dev_predict_fused(const rfsi_forest_t* f, const rfsi_fused_a
     const FusedPlan pl = plan_fused(f, a, kc_extra_default());
     int* na_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + pl.off_misc + 16);
     CU_TRY(cudaMemsetAsync(na_flag, 0, sizeof(int), (cudaStream_t)stream));
-    return dev_fused(f, a, pl, workspace, counters, device, (cudaStream_t)stream, false);
+    return dev_fused(f, a, pl, workspace, counters, device, (cudaStream_t)stream, false, true);
 }
 
 extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device)
@@ -1809,7 +1812,7 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
             b.out_mean_i16 = a->out_mean_i16 ? sl.mean16.as<int16_t>() : nullptr;
             b.out_iqr_i16 = a->out_iqr_i16 ? sl.iqr16.as<int16_t>() : nullptr;
             FusedPlan bpl = pl;  // same offsets (sized for a full chunk); only row counts differ
-            RF_TRY(dev_fused(f, &b, bpl, sl.ws.p, d_cnt.as<unsigned long long>(), device, s, reuse));
+            RF_TRY(dev_fused(f, &b, bpl, sl.ws.p, d_cnt.as<unsigned long long>(), device, s, reuse, false));
             sl.cand_chunk = p0;
             // results back: device [dloc*cur + p] -> host [(d0+dloc)*npix + p0 + p]
             if (a->out_mean)
