@@ -207,6 +207,9 @@ class ClockSampler:
 
 
 def main_ours(args):
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment; stdout
+    # must carry the one JSON line only
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import rfsi_b200 as rb
     from rfsi_b200 import _lib
