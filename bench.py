@@ -138,7 +138,7 @@ def main_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -207,9 +207,6 @@ class ClockSampler:
 
 
 def main_ours(args):
-    # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment; stdout
-    # must carry the one JSON line only
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import rfsi_b200 as rb
     from rfsi_b200 import _lib
@@ -499,13 +496,23 @@ def main_ours(args):
         }
         if qrf is not None:
             line["qrf"] = qrf
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def emit(line: dict):
+    """The one JSON line, written to the process's ORIGINAL stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
     a = parse()
+    # Libraries (NCCL's version banner, for one) write to fd 1 behind Python's back: park the real
+    # stdout, point fd 1 at stderr for the whole run, and emit the JSON line on the parked fd.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
