@@ -92,12 +92,15 @@ __device__ __forceinline__ void qrf_locate(const int* hist, int lane, int lane_s
     count = __shfl_sync(0xffffffffu, cnt, src);
 }
 
-// k-th smallest (0-based) of the valid samples, given the level-0 histogram.
+// k-th smallest (0-based) of the valid samples, given the level-0 histogram.  *next receives the
+// (k+1)-th smallest as well when it sits in the same final bucket (the usual case for the
+// lo/hi pair of one quantile), and *has_next says so.
 template <int R>
 __device__ __forceinline__ double qrf_select(const double (&v)[R], unsigned valid, const unsigned char (&b0)[R],
                                              const int* hist0, int sum0, int excl0, int* hist1, double* mem,
-                                             int lane, int k)
+                                             int lane, int k, double* next, bool* has_next)
 {
+    *has_next = false;
     int B, before, cnt;
     qrf_locate(hist0, lane, sum0, excl0, k, B, before, cnt);
     int kk = k - before;
@@ -115,7 +118,10 @@ __device__ __forceinline__ double qrf_select(const double (&v)[R], unsigned vali
             lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
             hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
-        if (lo == hi) return lo;   // all members equal
+        if (lo == hi) {            // all members equal
+            if (kk + 1 < cnt) { *next = lo; *has_next = true; }
+            return lo;
+        }
         unsigned char b1[R];
         int s1, e1;
         qrf_hist<R>(v, mm, lo, hi, hist1, lane, b1, s1, e1);
@@ -147,6 +153,11 @@ __device__ __forceinline__ double qrf_select(const double (&v)[R], unsigned vali
     }
     const unsigned hit = __ballot_sync(0xffffffffu, lane < cnt && rk == kk);
     const double out = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
+    if (kk + 1 < cnt) {
+        const unsigned hit2 = __ballot_sync(0xffffffffu, lane < cnt && rk == kk + 1);
+        *next = __shfl_sync(0xffffffffu, mine, __ffs(hit2) - 1);
+        *has_next = true;
+    }
     __syncwarp();
     return out;
 }
@@ -207,9 +218,13 @@ qrf_quantile_kernel(const double* __restrict__ samples, const unsigned char* __r
         } else {
             const double index = 1.0 + (double)(m - 1) * probs[j];
             const double lo = floor(index), hi = ceil(index);
-            const double xlo = qrf_select<R>(v, valid, b0, hist0, sum0, excl0, hist1, mem, lane, (int)lo - 1);
+            double nxt = 0.0, unused = 0.0;
+            bool has_nxt = false, unused_b = false;
+            const double xlo = qrf_select<R>(v, valid, b0, hist0, sum0, excl0, hist1, mem, lane, (int)lo - 1, &nxt, &has_nxt);
             const double xhi = (hi == lo) ? xlo
-                                          : qrf_select<R>(v, valid, b0, hist0, sum0, excl0, hist1, mem, lane, (int)hi - 1);
+                               : (has_nxt ? nxt
+                                          : qrf_select<R>(v, valid, b0, hist0, sum0, excl0, hist1, mem, lane, (int)hi - 1,
+                                                          &unused, &unused_b));
             if (index > lo && xhi != xlo) {
                 const double h = index - lo;
                 q = __dadd_rn(__dmul_rn(1.0 - h, xlo), __dmul_rn(h, xhi));
