@@ -216,7 +216,7 @@ qrf_quantile_kernel(const double* __restrict__ samples, const unsigned char* __r
         } else if (!(mn < mx)) {
             q = mn;   // every sample equal
         } else {
-            const double index = 1.0 + (double)(m - 1) * probs[j];
+            const double index = __dadd_rn(1.0, __dmul_rn((double)(m - 1), probs[j]));   // no FMA: R computes 1 + (n-1)*p in two roundings
             const double lo = floor(index), hi = ceil(index);
             double nxt = 0.0, unused = 0.0;
             bool has_nxt = false, unused_b = false;
