@@ -1,5 +1,7 @@
+"""near.obs kernel time vs station count (profile class 5) and wall time of the host call."""
 import sys, time, ctypes as C
-sys.path.insert(0, '/root/repo')
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import numpy as np
 import rfsi_b200 as rb
 from rfsi_b200 import synth, _lib
