@@ -831,16 +831,37 @@ int launch_forest_x(const rfsi_forest* f, const rfsi_forest::Image& im, const do
 
 constexpr int kMaxProbs = 128;
 
-int launch_qrf(const double* samples, const unsigned char* skip, int64_t nrows, int T, const double* probs_dev,
-               int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr, cudaStream_t stream)
+// row stride (entries) of the leaf-id scratch: whole groups of 8 trees are 32-byte aligned
+inline int64_t leaf_ids_ld(int T) { return ((int64_t)T + 7) & ~int64_t(7); }
+inline size_t leaf_ids_bytes(int64_t rows, int T) { return sizeof(uint32_t) * (size_t)rows * (size_t)leaf_ids_ld(T); }
+
+template <int R>
+int launch_qrf_r(const uint32_t* leaf_ids, const double* leaf_sample, const unsigned char* skip, int64_t nrows, int T,
+                 const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr, cudaStream_t stream)
+{
+    auto kern = qrf_quantile_kernel<R>;
+    const size_t smem = qrf_smem_bytes<R>();
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0, per_sm = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kQrfWarps, smem));
+    // persistent warps: one resident wave, each warp strides over the rows
+    const int64_t want = (nrows + kQrfWarps - 1) / kQrfWarps;
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * std::max(per_sm, 1));
+    kern<<<grid, 32 * kQrfWarps, smem, stream>>>(leaf_ids, leaf_ids_ld(T), leaf_sample, skip, nrows, T, probs_dev, nprobs,
+                                                 out_q, ld_q, out_iqr);
+    return RFSI_OK;
+}
+
+int launch_qrf(const uint32_t* leaf_ids, const double* leaf_sample, const unsigned char* skip, int64_t nrows, int T,
+               const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr, cudaStream_t stream)
 {
     if (nrows == 0) return RFSI_OK;
-    const unsigned grid = (unsigned)((nrows + 7) / 8);
     const int R = (T + 31) / 32;
     ProfScope ps(PROF_QRF, stream);
-#define RFSI_QRF_CASE(RR)                                                                            \
-    qrf_quantile_kernel<RR><<<grid, 256, 0, stream>>>(samples, skip, nrows, T, probs_dev, nprobs, out_q, \
-                                                      ld_q, out_iqr)
+#define RFSI_QRF_CASE(RR) \
+    RF_TRY(launch_qrf_r<RR>(leaf_ids, leaf_sample, skip, nrows, T, probs_dev, nprobs, out_q, ld_q, out_iqr, stream))
     if (R <= 1) RFSI_QRF_CASE(1);
     else if (R <= 2) RFSI_QRF_CASE(2);
     else if (R <= 4) RFSI_QRF_CASE(4);
@@ -1188,7 +1209,7 @@ extern "C" int rfsi_near_obs_days_f64(const double* loc_x, const double* loc_y, 
 // ------------------------------------------------------------------------------------
 extern "C" size_t rfsi_dev_forest_scratch_bytes(const rfsi_forest_t* f, int64_t npix, int32_t nprobs) {
     if (!f || npix <= 0 || nprobs <= 0) return 256;
-    return align_up(sizeof(double) * (size_t)npix * f->ntrees, 256) + align_up(sizeof(double) * kMaxProbs, 256);
+    return align_up(leaf_ids_bytes(npix, f->ntrees), 256) + align_up(sizeof(double) * kMaxProbs, 256);
 }
 
 extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
@@ -1202,20 +1223,20 @@ extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, 
     rfsi_forest::Image im;
     RF_TRY(forest_image(f, device, &im));
     cudaStream_t st = (cudaStream_t)stream;
-    ForestOut o{out_mean, nullptr, im.leaf_sample, out_terminal, nullptr, npix};
+    ForestOut o{out_mean, nullptr, leaf_ids_ld(f->ntrees), out_terminal, nullptr, npix};
     if (out_terminal) RF_TRY(forest_leaf_rid(f, device, &o.leaf_rid));
     double* probs_dev = nullptr;
     if (out_q) {
         if (!im.leaf_sample) return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
         RF_TRY(check_probs(probs_host, nprobs));
         if (!scratch) return fail(RFSI_E_ARG, "quantiles need a scratch buffer");
-        o.samples = reinterpret_cast<double*>(scratch);
+        o.leaf_ids = reinterpret_cast<uint32_t*>(scratch);
         probs_dev = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) +
-                                              align_up(sizeof(double) * (size_t)npix * f->ntrees, 256));
+                                              align_up(leaf_ids_bytes(npix, f->ntrees), 256));
         CU_TRY(cudaMemcpyAsync(probs_dev, probs_host, sizeof(double) * nprobs, cudaMemcpyHostToDevice, st));
     }
     RF_TRY(launch_forest_x(f, im, X, npix, ldx, o, visits, na_flag, st));
-    if (out_q) RF_TRY(launch_qrf(o.samples, nullptr, npix, f->ntrees, probs_dev, nprobs, out_q, npix, nullptr, st));
+    if (out_q) RF_TRY(launch_qrf(o.leaf_ids, im.leaf_sample, nullptr, npix, f->ntrees, probs_dev, nprobs, out_q, npix, nullptr, st));
     return RFSI_OK;
 }
 
@@ -1435,7 +1456,7 @@ FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_
     const int64_t npix = std::max<int64_t>(a->npix, 1);
     int db = std::min(a->ndays, 16);
     if (pl.want_q) {
-        const int64_t per_day = npix * f->ntrees * 8;
+        const int64_t per_day = npix * leaf_ids_ld(f->ntrees) * 4;
         db = (int)std::max<int64_t>(1, std::min<int64_t>(db, (int64_t(1) << 30) / per_day));
     }
     // keep the 1-D grid below 2^31 CTAs
@@ -1454,7 +1475,7 @@ FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_
     pl.off_misc = o; o += 256;  // fb_count, na_flag
     pl.off_probs = o; o += align_up(sizeof(double) * kMaxProbs, 256);
     if (pl.want_q) {
-        pl.off_samples = o; o += align_up(sizeof(double) * (size_t)pl.rows * f->ntrees, 256);
+        pl.off_samples = o; o += align_up(leaf_ids_bytes(pl.rows, f->ntrees), 256);
         pl.off_skip = o; o += align_up((size_t)pl.rows, 256);
     }
     pl.total = o;
@@ -1516,7 +1537,7 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
     unsigned int* fb_count = reinterpret_cast<unsigned int*>(ws + pl.off_misc);
     int* na_flag = reinterpret_cast<int*>(ws + pl.off_misc + 16);
     double* probs_dev = reinterpret_cast<double*>(ws + pl.off_probs);
-    double* samples = pl.want_q ? reinterpret_cast<double*>(ws + pl.off_samples) : nullptr;
+    uint32_t* leaf_ids = pl.want_q ? reinterpret_cast<uint32_t*>(ws + pl.off_samples) : nullptr;
     unsigned char* skip = pl.want_q ? reinterpret_cast<unsigned char*>(ws + pl.off_skip) : nullptr;
 
     // explicit coordinates: grid_ncol > 1 is the row length of a row-by-row ordering (a mapping hint only)
@@ -1572,7 +1593,7 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         else fp.cov_row[code] = (short)fi;  // a covariate feeds one model column
     }
     fp.pix_mask = a->pix_mask;
-    fp.nodes = im.nodes; fp.q = im.q; fp.leaf_sample = im.leaf_sample; fp.leaf_rid = nullptr;
+    fp.nodes = im.nodes; fp.q = im.q; fp.leaf_rid = nullptr;
     fp.T = f->ntrees; fp.F = f->nfeat;
     fp.acc = acc;
     fp.fb_list = fb; fp.fb_count = fb_count; fp.fb_capacity = (unsigned int)std::min<int64_t>(pl.rows, 0xffffffffLL);
@@ -1606,7 +1627,7 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         const int64_t obase = (int64_t)d0 * a->npix;
         fp.out_mean = a->out_mean ? a->out_mean + obase : nullptr;
         fp.out_mean_i16 = a->out_mean_i16 ? a->out_mean_i16 + obase : nullptr;
-        fp.samples = samples; fp.row_skip = skip;
+        fp.leaf_ids = leaf_ids; fp.ld_ids = leaf_ids_ld(f->ntrees); fp.row_skip = skip;
         CU_TRY(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int), st));
         const unsigned grid = (unsigned)(ntiles * nd);
         for (size_t c = 0; c + 1 < cb.size(); ++c) {  // one sweep of all tiles per L2-sized forest chunk
@@ -1628,7 +1649,7 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         if (pl.want_q) {
             double* oq = a->out_q ? a->out_q + obase : nullptr;
             // q[(j*ndays + d)*npix + p]: column stride between quantiles is ndays*npix
-            RF_TRY(launch_qrf(samples, skip, rows, f->ntrees, probs_dev, a->nprobs, oq, (int64_t)a->ndays * a->npix,
+            RF_TRY(launch_qrf(leaf_ids, im.leaf_sample, skip, rows, f->ntrees, probs_dev, a->nprobs, oq, (int64_t)a->ndays * a->npix,
                               a->out_iqr_i16 ? a->out_iqr_i16 + obase : nullptr, st));
         }
     }

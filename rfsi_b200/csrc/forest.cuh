@@ -52,28 +52,38 @@ __device__ __forceinline__ uint32_t rank_of(const QForest& q, int f, double x) {
 
 struct ForestOut {
     double* mean;             // [npix] (nullable)
-    double* samples;          // [npix][T] pixel-major leaf samples for the quantile pass (nullable)
-    const double* leaf_sample;  // per device-node sample (random.node.values), needed if samples
+    uint32_t* leaf_ids;       // [npix][ld_ids] pixel-major leaf (device-node) index per tree, for the quantile pass (nullable)
+    long long ld_ids;         // row stride of leaf_ids in entries: T rounded up to 8, so whole groups are 32-byte aligned
     int32_t* terminal;        // [T][ld_term] tree-local terminal node ids (nullable)
     const int32_t* leaf_rid;  // per device-node ranger node id, needed if terminal
     long long ld_term;
 };
 
-// Quantile path: the leaf samples of one group of J trees, written as 128-bit stores when
-// the group is whole and 16-byte aligned (each thread owns a contiguous row of T samples).
+// Quantile path: the leaves one group of J trees ended in, 4 bytes per tree (the sample
+// random.node.values[leaf, tree] is gathered by the quantile kernel, where the T gathers of a
+// row are independent loads of one warp instead of a dependent tail of this walk).  A whole
+// group of 8 is one 32-byte sector, written by one 256-bit store; the scratch is read once by
+// the next kernel and is larger than L2, so the stores are evict-first and do not push the
+// forest image out of L2.
 template <int J, class Idx>
-__device__ __forceinline__ void store_samples(const ForestOut& o, long long base, int remaining, const Idx (&idx)[J]) {
-    double sv[J];
+__device__ __forceinline__ void store_leaf_ids(const ForestOut& o, long long base, int remaining, const Idx (&idx)[J]) {
+    uint32_t* dst = o.leaf_ids + base;
+    if (J % 8 == 0 && remaining >= J && (base & 7) == 0) {
 #pragma unroll
-    for (int j = 0; j < J; ++j) sv[j] = (j < remaining) ? __ldg(o.leaf_sample + idx[j]) : 0.0;
-    if (J % 2 == 0 && remaining >= J && (base & 1) == 0) {
+        for (int j = 0; j < J; j += 8)
+            asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + j),
+                         "r"((uint32_t)idx[j]), "r"((uint32_t)idx[j + 1]), "r"((uint32_t)idx[j + 2]), "r"((uint32_t)idx[j + 3]),
+                         "r"((uint32_t)idx[j + 4]), "r"((uint32_t)idx[j + 5]), "r"((uint32_t)idx[j + 6]), "r"((uint32_t)idx[j + 7])
+                         : "memory");
+    } else if (J % 4 == 0 && remaining >= J && (base & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < J; j += 2)
-            *reinterpret_cast<double2*>(o.samples + base + j) = make_double2(sv[j], sv[j + 1]);
+        for (int j = 0; j < J; j += 4)
+            __stcs(reinterpret_cast<uint4*>(dst + j),
+                   make_uint4((uint32_t)idx[j], (uint32_t)idx[j + 1], (uint32_t)idx[j + 2], (uint32_t)idx[j + 3]));
     } else {
 #pragma unroll
         for (int j = 0; j < J; ++j)
-            if (j < remaining) o.samples[base + j] = sv[j];
+            if (j < remaining) dst[j] = (uint32_t)idx[j];
     }
 }
 
@@ -115,7 +125,7 @@ __device__ __forceinline__ double traverse_all(const Node* __restrict__ nodes, i
                 if (o.terminal) o.terminal[(long long)(t0 + j) * o.ld_term + row] = o.leaf_rid[idx[j]];
             }
         }
-        if (o.samples) store_samples<J>(o, row * T + t0, t_end - t0, idx);
+        if (o.leaf_ids) store_leaf_ids<J>(o, row * o.ld_ids + t0, t_end - t0, idx);
     }
     return sum;
 }
@@ -173,7 +183,7 @@ __device__ __forceinline__ double traverse_q(const QForest& q, int t_begin, int 
                 if (o.terminal) o.terminal[(long long)(t0 + j) * o.ld_term + row] = o.leaf_rid[idx[j]];
             }
         }
-        if (o.samples) store_samples<J>(o, row * T + t0, t_end - t0, idx);
+        if (o.leaf_ids) store_leaf_ids<J>(o, row * o.ld_ids + t0, t_end - t0, idx);
     }
     return sum;
 }
@@ -229,7 +239,7 @@ __device__ __forceinline__ double traverse_b(const QForest& q, int t_begin, int 
                 if (o.terminal) o.terminal[(long long)(t0 + j) * o.ld_term + row] = o.leaf_rid[bb[j]];
             }
         }
-        if (o.samples) store_samples<J>(o, row * T + t0, t_end - t0, bb);
+        if (o.leaf_ids) store_leaf_ids<J>(o, row * o.ld_ids + t0, t_end - t0, bb);
     }
     return sum;
 }

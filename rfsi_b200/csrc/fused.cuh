@@ -49,7 +49,6 @@ struct FusedParams {
     // forest
     const Node* nodes;           // wide format (nullptr when the compact image is in use)
     QForest q;                   // compact format
-    const double* leaf_sample;
     const int32_t* leaf_rid;
     int T, F;
     int t_begin, t_end;          // this launch walks trees [t_begin, t_end) (one L2-sized chunk)
@@ -57,7 +56,8 @@ struct FusedParams {
     // outputs; row index = (d - day0)*npix + p relative to the *_base pointers
     double* out_mean;
     int16_t* out_mean_i16;
-    double* samples;             // [ndays*npix][T]
+    uint32_t* leaf_ids;          // [ndays*npix][ld_ids] leaf index per tree (quantile pass; nullable)
+    long long ld_ids;
     unsigned char* row_skip;     // [ndays*npix]
     // fallback list
     int2* fb_list;
@@ -235,8 +235,8 @@ fused_kernel(const __grid_constant__ FusedParams a)
     if (ok) {
         ForestOut o;
         o.mean = nullptr;
-        o.samples = a.samples;
-        o.leaf_sample = a.leaf_sample;
+        o.leaf_ids = a.leaf_ids;
+        o.ld_ids = a.ld_ids;
         o.terminal = nullptr;
         o.leaf_rid = nullptr;
         o.ld_term = 0;

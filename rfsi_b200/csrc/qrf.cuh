@@ -7,41 +7,73 @@
 // iqr <- (q[,3]-q[,1])/2 (2_predictions.R:177; 5_prcp_prediction.R:292)
 // (SURVEY.md 8a rows a5/a6, Appendix A.3).
 //
-// B200 design: one warp per pixel-day, samples in registers (R = ceil(T/32) per lane).
-// Only 2 order statistics per quantile are needed, so instead of sorting (a 512-element
-// bitonic network is ~10^4 instructions per row) the warp SELECTS them exactly:
+// B200 design: one warp per pixel-day, R = ceil(T/32) samples per lane.  Only 2 order
+// statistics per quantile are needed, so instead of sorting (a 512-element bitonic network is
+// ~10^4 instructions per row) the warp SELECTS them exactly:
 //   1. min/max of the non-NA samples, then one histogram of 256 monotone buckets
 //      b(x) = min(255, int((x - min) * 256/(max - min))) in shared memory (built once per row;
 //      the maximum is pinned to bucket 255);
 //   2. per wanted rank k: a warp scan of the histogram finds the bucket holding the k-th
 //      smallest and how many samples precede it; the bucket's few members are compacted
-//      into shared memory and ranked against each other (ties by position);
+//      into shared memory and ranked against each other (ties by slot);
 //   3. a bucket with more than 32 members (heavy ties / skew) is re-bucketed between its
 //      own min and max until it is small or constant.
 // b() is monotone non-decreasing (fp subtract, multiply by a positive scale and truncation
 // all are), so bucket order == value order and the selected value IS the order statistic.
 // Interpolation uses exactly R's expression (1-h)*x[lo] + h*x[hi].
+//
+// Memory pipeline: the forest walk left 4-byte leaf indices per (row, tree).  Each CTA owns a
+// contiguous run of rows and its 8 warps walk it 8 adjacent rows at a time: adjacent pixels end
+// in the same leaves, so most of the T gathers leaf_sample[id] of a row hit lines its
+// neighbours just brought into L1 (a grid-strided assignment measured 4.6 % L1 hits and 7x the
+// DRAM traffic).  While a warp selects in row i, the gathers of row i+8 are in flight into
+// registers and the ids of row i+16 into shared memory (cp.async), so neither the DRAM read of
+// the id scratch nor the gathers sit on the critical path.
 #pragma once
 #include "common.cuh"
 
 namespace rfsi {
 
-constexpr int kQrfWarps = 8;   // rows per CTA
+constexpr int kQrfWarps = 8;        // rows in flight per CTA
+// resident CTAs per SM the register budget is cut for: two (16 warps, 2 x 66 KB of shared
+// memory at T = 512, which leaves ~96 KB of L1 for the gathers); one for 1024-tree rows
+#ifndef QRF_MIN_BLOCKS
+#define QRF_MIN_BLOCKS 2
+#endif
+template <int R> constexpr int qrf_min_blocks() { return R >= 32 ? 1 : QRF_MIN_BLOCKS; }
+
+// shared memory of one warp, in bytes: samples of the current row, two histograms, the
+// compaction buffer, the id buffer of the row after next
+template <int R>
+__host__ __device__ constexpr size_t qrf_warp_smem() {
+    return (size_t)R * 32 * 8 + 256 * 4 + 256 * 4 + 32 * 8 + (size_t)R * 32 * 4;
+}
+template <int R>
+__host__ __device__ constexpr size_t qrf_smem_bytes() { return kQrfWarps * qrf_warp_smem<R>(); }
+
+struct QrfWarp {
+    double* sv;      // [R*32] samples of the row, element r of lane l at r*32 + l
+    int* hist0;      // [256]
+    int* hist1;      // [256]
+    double* mem;     // [32]
+    uint32_t* ids;   // [R*32]
+};
 
 // Monotone bucket of x in [lo, hi].  Halved operands keep hi - lo finite for any finite
 // inputs; the maximum always lands in bucket 255 and the minimum in bucket 0, so a bucket
 // that is re-bucketed between its own min and max always loses members (termination).
 __device__ __forceinline__ int qrf_bucket(double x, double lo_half, double hi, double scale) {
-    if (x == hi) return 255;
     const double t = (x * 0.5 - lo_half) * scale;   // x >= lo, so t >= 0; NaN never reaches here
-    return (t >= 255.0) ? 255 : (int)t;
+    const int b = (t >= 255.0) ? 255 : (int)t;
+    return (x == hi) ? 255 : b;
 }
 
-// Histogram of the members (bit r of `members` set <=> v[r] takes part) between lo and hi;
-// returns the bucket of every member in b[], and this lane's 8-bin sum / exclusive prefix.
+// Histogram of the members (bit r of `members` set <=> sample r of this lane takes part)
+// between lo and hi; bp packs the bucket of element r into byte r&3 of word r>>2; returns this
+// lane's 8-bin sum and exclusive prefix.
 template <int R>
-__device__ __forceinline__ void qrf_hist(const double (&v)[R], unsigned members, double lo, double hi,
-                                         int* hist, int lane, unsigned char (&b)[R], int& lane_sum, int& lane_excl)
+__device__ __forceinline__ void qrf_hist(const double* sv, unsigned members, double lo, double hi, int* hist, int lane,
+                                         uint32_t (&bp)[(R + 3) / 4], int& lane_sum, int& lane_excl)
 {
     const double lo_half = lo * 0.5;
     double scale = 256.0 / (hi * 0.5 - lo_half);
@@ -50,12 +82,14 @@ __device__ __forceinline__ void qrf_hist(const double (&v)[R], unsigned members,
     reinterpret_cast<int4*>(hist)[lane * 2 + 1] = make_int4(0, 0, 0, 0);
     __syncwarp();
 #pragma unroll
+    for (int w = 0; w < (R + 3) / 4; ++w) bp[w] = 0;
+#pragma unroll
     for (int r = 0; r < R; ++r) {
-        b[r] = 0;
-        if (members & (1u << r)) {
-            b[r] = (unsigned char)qrf_bucket(v[r], lo_half, hi, scale);
-            atomicAdd(&hist[b[r]], 1);
-        }
+        const bool is = (members >> r) & 1u;
+        const double x = is ? sv[r * 32 + lane] : lo;
+        const int b = qrf_bucket(x, lo_half, hi, scale);
+        if (is) atomicAdd(&hist[b], 1);
+        bp[r >> 2] |= (uint32_t)b << (8 * (r & 3));
     }
     __syncwarp();
     const int4 h0 = reinterpret_cast<const int4*>(hist)[lane * 2];
@@ -71,48 +105,61 @@ __device__ __forceinline__ void qrf_hist(const double (&v)[R], unsigned members,
 }
 
 // The bucket that holds rank k (0-based among the histogram's members): returns the bucket,
-// the number of members before it and its size.
+// the number of members before it and its size.  Every lane scans its own 8 bins without
+// branching; the owning lane's answer travels in one packed shuffle (counts <= 1024).
 __device__ __forceinline__ void qrf_locate(const int* hist, int lane, int lane_sum, int lane_excl, int k,
                                            int& bucket, int& before, int& count)
 {
     const unsigned bal = __ballot_sync(0xffffffffu, lane_excl <= k && k < lane_excl + lane_sum);
     const int src = __ffs(bal) - 1;
-    int B = 0, cb = 0, cnt = 0;
-    if (lane == src) {
-        int c = lane_excl;
+    const int4 h0 = reinterpret_cast<const int4*>(hist)[lane * 2];
+    const int4 h1 = reinterpret_cast<const int4*>(hist)[lane * 2 + 1];
+    const int h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    uint32_t packed = 0;
+    int c = lane_excl;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int h = hist[lane * 8 + i];
-            if (k >= c && k < c + h) { B = lane * 8 + i; cb = c; cnt = h; }
-            c += h;
-        }
+    for (int i = 0; i < 8; ++i) {
+        const bool in = (k >= c) && (k < c + h[i]);
+        packed = in ? ((uint32_t)(lane * 8 + i) | ((uint32_t)c << 8) | ((uint32_t)h[i] << 19)) : packed;
+        c += h[i];
     }
-    bucket = __shfl_sync(0xffffffffu, B, src);
-    before = __shfl_sync(0xffffffffu, cb, src);
-    count = __shfl_sync(0xffffffffu, cnt, src);
+    packed = __shfl_sync(0xffffffffu, packed, src);
+    bucket = (int)(packed & 0xFFu);
+    before = (int)((packed >> 8) & 0x7FFu);
+    count = (int)(packed >> 19);
+}
+
+// bit r set <=> byte r of the packed buckets equals B
+template <int R>
+__device__ __forceinline__ unsigned qrf_match(const uint32_t (&bp)[(R + 3) / 4], int B) {
+    const uint32_t Bw = (uint32_t)B * 0x01010101u;
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < (R + 3) / 4; ++w) {
+        const uint32_t eq = __vcmpeq4(bp[w], Bw) & 0x01010101u;   // 1 in the low bit of every equal byte
+        m |= ((eq * 0x01020408u) >> 24 & 0xFu) << (4 * w);        // gather the four bits (no carries meet)
+    }
+    return m;
 }
 
 // k-th smallest (0-based) of the valid samples, given the level-0 histogram.  *next receives the
 // (k+1)-th smallest as well when it sits in the same final bucket (the usual case for the
 // lo/hi pair of one quantile), and *has_next says so.
 template <int R>
-__device__ __forceinline__ double qrf_select(const double (&v)[R], unsigned valid, const unsigned char (&b0)[R],
-                                             const int* hist0, int sum0, int excl0, int* hist1, double* mem,
-                                             int lane, int k, double* next, bool* has_next)
+__device__ __forceinline__ double qrf_select(const QrfWarp& s, unsigned valid, const uint32_t (&b0)[(R + 3) / 4],
+                                             int sum0, int excl0, int lane, int k, double* next, bool* has_next)
 {
     *has_next = false;
     int B, before, cnt;
-    qrf_locate(hist0, lane, sum0, excl0, k, B, before, cnt);
+    qrf_locate(s.hist0, lane, sum0, excl0, k, B, before, cnt);
     int kk = k - before;
-    unsigned mm = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) mm |= ((valid >> r) & 1u & (b0[r] == B ? 1u : 0u)) << r;
+    unsigned mm = qrf_match<R>(b0, B) & valid;
 
     while (cnt > 32) {   // heavy bucket: re-bucket between its own min and max
         double lo = __longlong_as_double(0x7FF0000000000000LL), hi = __longlong_as_double(0xFFF0000000000000LL);
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (mm & (1u << r)) { lo = fmin(lo, v[r]); hi = fmax(hi, v[r]); }
+            if (mm & (1u << r)) { const double x = s.sv[r * 32 + lane]; lo = fmin(lo, x); hi = fmax(hi, x); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -122,33 +169,34 @@ __device__ __forceinline__ double qrf_select(const double (&v)[R], unsigned vali
             if (kk + 1 < cnt) { *next = lo; *has_next = true; }
             return lo;
         }
-        unsigned char b1[R];
+        uint32_t b1[(R + 3) / 4];
         int s1, e1;
-        qrf_hist<R>(v, mm, lo, hi, hist1, lane, b1, s1, e1);
-        qrf_locate(hist1, lane, s1, e1, kk, B, before, cnt);
+        qrf_hist<R>(s.sv, mm, lo, hi, s.hist1, lane, b1, s1, e1);
+        qrf_locate(s.hist1, lane, s1, e1, kk, B, before, cnt);
         kk -= before;
-        unsigned m2 = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) m2 |= ((mm >> r) & 1u & (b1[r] == B ? 1u : 0u)) << r;
-        mm = m2;
+        mm &= qrf_match<R>(b1, B);
         __syncwarp();
     }
 
-    // compact the bucket's members (<= 32) and rank them against each other
+    // compact the bucket's members (<= 32) and rank them against each other (ties by slot).
+    // Few of the R ballots have a member at all; the uniform test skips the rest.
     int pos = 0;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const bool is = (mm >> r) & 1u;
         const unsigned bal = __ballot_sync(0xffffffffu, is);
-        if (is) mem[pos + __popc(bal & lt)] = v[r];
-        pos += __popc(bal);
+        if (bal) {
+            if (is) s.mem[pos + __popc(bal & lt)] = s.sv[r * 32 + lane];
+            pos += __popc(bal);
+        }
     }
     __syncwarp();
-    const double mine = (lane < cnt) ? mem[lane] : 0.0;
+    const double mine = (lane < cnt) ? s.mem[lane] : 0.0;
     int rk = 0;
+#pragma unroll 4
     for (int j = 0; j < cnt; ++j) {
-        const double other = mem[j];
+        const double other = s.mem[j];
         rk += (other < mine || (other == mine && j < lane)) ? 1 : 0;
     }
     const unsigned hit = __ballot_sync(0xffffffffu, lane < cnt && rk == kk);
@@ -162,89 +210,137 @@ __device__ __forceinline__ double qrf_select(const double (&v)[R], unsigned vali
     return out;
 }
 
-// samples: [nrows][T] pixel-major; skip (nullable): rows whose outputs are NA.
+__device__ __forceinline__ void qrf_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+
+// leaf_ids: [nrows][ld_ids] pixel-major leaf index per tree (written by the forest walk);
+// leaf_sample: the forest's per-leaf sample table; skip (nullable): rows whose outputs are NA
+// (their ids were never written).
 // out_q[j*ld_q + row] for j < nprobs (nullable); out_iqr_i16[row] (nullable) =
 // round-half-even((q[nprobs-1]-q[0])/2*100), NA -> -32767.
 template <int R>
-__global__ void __launch_bounds__(32 * kQrfWarps)
-qrf_quantile_kernel(const double* __restrict__ samples, const unsigned char* __restrict__ skip,
-                    long long nrows, int T, const double* __restrict__ probs, int nprobs,
+__global__ void __launch_bounds__(32 * kQrfWarps, qrf_min_blocks<R>())
+qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, const double* __restrict__ leaf_sample,
+                    const unsigned char* __restrict__ skip, long long nrows, int T,
+                    const double* __restrict__ probs, int nprobs,
                     double* __restrict__ out_q, long long ld_q, int16_t* __restrict__ out_iqr_i16)
 {
-    __shared__ __align__(16) int s_hist0[kQrfWarps][256];
-    __shared__ __align__(16) int s_hist1[kQrfWarps][256];
-    __shared__ double s_mem[kQrfWarps][32];
+    extern __shared__ __align__(16) unsigned char qrf_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long row = (long long)blockIdx.x * kQrfWarps + wib;
-    if (row >= nrows) return;   // whole warp
-    int* hist0 = s_hist0[wib];
-    int* hist1 = s_hist1[wib];
-    double* mem = s_mem[wib];
+    QrfWarp s;
+    {
+        unsigned char* base = qrf_smem + (size_t)wib * qrf_warp_smem<R>();
+        s.sv = reinterpret_cast<double*>(base);               base += (size_t)R * 32 * 8;
+        s.hist0 = reinterpret_cast<int*>(base);               base += 256 * 4;
+        s.hist1 = reinterpret_cast<int*>(base);               base += 256 * 4;
+        s.mem = reinterpret_cast<double*>(base);              base += 32 * 8;
+        s.ids = reinterpret_cast<uint32_t*>(base);
+    }
+    // this CTA's contiguous run of rows; its warps take them kQrfWarps at a time
+    const long long per_cta = ((nrows + gridDim.x - 1) / gridDim.x + kQrfWarps - 1) / kQrfWarps * kQrfWarps;
+    const long long row_end = min(nrows, (long long)(blockIdx.x + 1) * per_cta);
+    const long long stride = kQrfWarps;
+    long long row = (long long)blockIdx.x * per_cta + wib;
+    if (row >= row_end) return;   // whole warp
+    const int nchunk = (int)(ld_ids >> 2);   // 16-byte pieces of one id row
+    const double nan = na_real();
 
-    double v[R];
-    unsigned valid = 0;
-    const bool skipped = skip && skip[row];
-    const double* src = samples + row * T;
-    double mn = __longlong_as_double(0x7FF0000000000000LL), mx = __longlong_as_double(0xFFF0000000000000LL);
+    auto fetch_ids = [&](long long rw) {      // ids of row rw -> s.ids (asynchronous)
+        if (rw < row_end) {
+            const uint32_t* src = leaf_ids + rw * ld_ids;
+            for (int c = lane; c < nchunk; c += 32) qrf_cp_async16(s.ids + 4 * c, src + 4 * c);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto ids_ready = [&]() {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+    };
+    double vn[R];                              // samples of the row about to be processed
+    auto gather = [&](long long rw, bool skipped) {   // s.ids -> vn (loads stay in flight)
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int t = r * 32 + lane;   // coalesced
-        double x = 0.0;
-        if (!skipped && t < T) {
-            x = src[t];
+        for (int r = 0; r < R; ++r) {
+            const int t = r * 32 + lane;
+            vn[r] = (rw < row_end && !skipped && t < T) ? __ldg(leaf_sample + s.ids[t]) : nan;
+        }
+        __syncwarp();                          // every lane has read s.ids: it may be refilled
+    };
+
+    // prologue: ids(row) -> gathers(row) in flight, ids(row + stride) in flight
+    bool skip_next = (skip && row + stride < row_end) ? skip[row + stride] != 0 : false;
+    fetch_ids(row);
+    ids_ready();
+    gather(row, skip && skip[row]);
+    fetch_ids(row + stride);
+
+    for (; row < row_end; row += stride) {
+        // ---- take this row's samples out of the registers ------------------------------
+        unsigned valid = 0;
+        double mn = __longlong_as_double(0x7FF0000000000000LL), mx = __longlong_as_double(0xFFF0000000000000LL);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double x = vn[r];
+            s.sv[r * 32 + lane] = x;
             if (x == x) { valid |= 1u << r; mn = fmin(mn, x); mx = fmax(mx, x); }   // na.rm = TRUE
         }
-        v[r] = x;
-    }
-    int m = __popc(valid);
+        // ---- next row's gathers, the row after's ids ---------------------------------------
+        ids_ready();                           // also publishes s.sv to the warp
+        gather(row + stride, skip_next);
+        fetch_ids(row + 2 * stride);
+        skip_next = (skip && row + 2 * stride < row_end) ? skip[row + 2 * stride] != 0 : false;
+
+        int m = __popc(valid);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m += __shfl_xor_sync(0xffffffffu, m, o);
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
+        for (int o = 16; o > 0; o >>= 1) {
+            m += __shfl_xor_sync(0xffffffffu, m, o);
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
 
-    unsigned char b0[R];
-    int sum0 = 0, excl0 = 0;
-    if (m > 0 && mn < mx) qrf_hist<R>(v, valid, mn, mx, hist0, lane, b0, sum0, excl0);
+        uint32_t b0[(R + 3) / 4];
+        int sum0 = 0, excl0 = 0;
+        if (m > 0 && mn < mx) qrf_hist<R>(s.sv, valid, mn, mx, s.hist0, lane, b0, sum0, excl0);
 
-    double qfirst = 0.0, qlast = 0.0;
-    for (int j = 0; j < nprobs; ++j) {
-        double q;
-        if (m == 0) {
-            q = na_real();
-        } else if (!(mn < mx)) {
-            q = mn;   // every sample equal
-        } else {
-            const double index = __dadd_rn(1.0, __dmul_rn((double)(m - 1), probs[j]));   // no FMA: R computes 1 + (n-1)*p in two roundings
-            const double lo = floor(index), hi = ceil(index);
-            double nxt = 0.0, unused = 0.0;
-            bool has_nxt = false, unused_b = false;
-            const double xlo = qrf_select<R>(v, valid, b0, hist0, sum0, excl0, hist1, mem, lane, (int)lo - 1, &nxt, &has_nxt);
-            const double xhi = (hi == lo) ? xlo
-                               : (has_nxt ? nxt
-                                          : qrf_select<R>(v, valid, b0, hist0, sum0, excl0, hist1, mem, lane, (int)hi - 1,
-                                                          &unused, &unused_b));
-            if (index > lo && xhi != xlo) {
-                const double h = index - lo;
-                q = __dadd_rn(__dmul_rn(1.0 - h, xlo), __dmul_rn(h, xhi));
+        double qfirst = 0.0, qlast = 0.0;
+        for (int j = 0; j < nprobs; ++j) {
+            double q;
+            if (m == 0) {
+                q = nan;
+            } else if (!(mn < mx)) {
+                q = mn;   // every sample equal
             } else {
-                q = xlo;
+                const double index = __dadd_rn(1.0, __dmul_rn((double)(m - 1), probs[j]));   // no FMA: R computes 1 + (n-1)*p in two roundings
+                const double lo = floor(index), hi = ceil(index);
+                double nxt = 0.0, unused = 0.0;
+                bool has_nxt = false, unused_b = false;
+                const double xlo = qrf_select<R>(s, valid, b0, sum0, excl0, lane, (int)lo - 1, &nxt, &has_nxt);
+                const double xhi = (hi == lo) ? xlo
+                                   : (has_nxt ? nxt
+                                              : qrf_select<R>(s, valid, b0, sum0, excl0, lane, (int)hi - 1, &unused, &unused_b));
+                if (index > lo && xhi != xlo) {
+                    const double h = index - lo;
+                    q = __dadd_rn(__dmul_rn(1.0 - h, xlo), __dmul_rn(h, xhi));
+                } else {
+                    q = xlo;
+                }
             }
+            if (lane == 0 && out_q) out_q[(long long)j * ld_q + row] = q;
+            if (j == 0) qfirst = q;
+            qlast = q;
         }
-        if (lane == 0 && out_q) out_q[(long long)j * ld_q + row] = q;
-        if (j == 0) qfirst = q;
-        qlast = q;
-    }
-    if (lane == 0 && out_iqr_i16) {
-        const double c = __dmul_rn(__dmul_rn(__dsub_rn(qlast, qfirst), 0.5), 100.0);
-        int16_t r16 = -32767;
-        if (c == c) {
-            double rr = rint(c);
-            rr = fmin(fmax(rr, -32767.0), 32767.0);
-            r16 = (int16_t)rr;
+        if (lane == 0 && out_iqr_i16) {
+            const double c = __dmul_rn(__dmul_rn(__dsub_rn(qlast, qfirst), 0.5), 100.0);
+            int16_t r16 = -32767;
+            if (c == c) {
+                double rr = rint(c);
+                rr = fmin(fmax(rr, -32767.0), 32767.0);
+                r16 = (int16_t)rr;
+            }
+            out_iqr_i16[row] = r16;
         }
-        out_iqr_i16[row] = r16;
+        __syncwarp();   // the row's shared memory is free again
     }
 }
 
