@@ -59,6 +59,30 @@ struct QrfWarp {
     uint32_t* ids;   // [R*32]
 };
 
+// Warp-wide min and max of non-NaN doubles without 64-bit shuffles: the IEEE bit pattern maps
+// to an unsigned key of the same order, whose high word is reduced first (one REDUX) and the
+// low word among the lanes that hold the winning high word second.
+__device__ __forceinline__ unsigned long long qrf_key(double x) {
+    const long long b = __double_as_longlong(x);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000LL));
+}
+__device__ __forceinline__ double qrf_unkey(unsigned long long k) {
+    const long long b = (long long)k;
+    return __longlong_as_double(b ^ ((~b >> 63) | (long long)0x8000000000000000LL));
+}
+__device__ __forceinline__ double qrf_warp_min(double x) {
+    const unsigned long long k = qrf_key(x);
+    const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(k >> 32));
+    const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(k >> 32) == hi ? (unsigned)k : 0xffffffffu);
+    return qrf_unkey(((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ double qrf_warp_max(double x) {
+    const unsigned long long k = qrf_key(x);
+    const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(k >> 32));
+    const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(k >> 32) == hi ? (unsigned)k : 0u);
+    return qrf_unkey(((unsigned long long)hi << 32) | lo);
+}
+
 // Monotone bucket of x in [lo, hi].  Halved operands keep hi - lo finite for any finite
 // inputs; the maximum always lands in bucket 255 and the minimum in bucket 0, so a bucket
 // that is re-bucketed between its own min and max always loses members (termination).
@@ -159,12 +183,9 @@ __device__ __forceinline__ double qrf_select(const QrfWarp& s, unsigned valid, c
         double lo = __longlong_as_double(0x7FF0000000000000LL), hi = __longlong_as_double(0xFFF0000000000000LL);
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (mm & (1u << r)) { const double x = s.sv[r * 32 + lane]; lo = fmin(lo, x); hi = fmax(hi, x); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        }
+            if (mm & (1u << r)) { const double x = s.sv[r * 32 + lane]; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+        lo = qrf_warp_min(lo);
+        hi = qrf_warp_max(hi);
         if (lo == hi) {            // all members equal
             if (kk + 1 < cnt) { *next = lo; *has_next = true; }
             return lo;
@@ -179,17 +200,16 @@ __device__ __forceinline__ double qrf_select(const QrfWarp& s, unsigned valid, c
     }
 
     // compact the bucket's members (<= 32) and rank them against each other (ties by slot).
-    // Few of the R ballots have a member at all; the uniform test skips the rest.
     int pos = 0;
     const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
+    unsigned any = __reduce_or_sync(0xffffffffu, mm);   // the few r at which some lane has a member
+    while (any) {
+        const int r = __ffs(any) - 1;
+        any &= any - 1;
         const bool is = (mm >> r) & 1u;
         const unsigned bal = __ballot_sync(0xffffffffu, is);
-        if (bal) {
-            if (is) s.mem[pos + __popc(bal & lt)] = s.sv[r * 32 + lane];
-            pos += __popc(bal);
-        }
+        if (is) s.mem[pos + __popc(bal & lt)] = s.sv[r * 32 + lane];
+        pos += __popc(bal);
     }
     __syncwarp();
     const double mine = (lane < cnt) ? s.mem[lane] : 0.0;
@@ -283,7 +303,7 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
         for (int r = 0; r < R; ++r) {
             const double x = vn[r];
             s.sv[r * 32 + lane] = x;
-            if (x == x) { valid |= 1u << r; mn = fmin(mn, x); mx = fmax(mx, x); }   // na.rm = TRUE
+            if (x == x) { valid |= 1u << r; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }   // na.rm = TRUE
         }
         // ---- next row's gathers, the row after's ids ---------------------------------------
         ids_ready();                           // also publishes s.sv to the warp
@@ -291,13 +311,9 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
         fetch_ids(row + 2 * stride);
         skip_next = (skip && row + 2 * stride < row_end) ? skip[row + 2 * stride] != 0 : false;
 
-        int m = __popc(valid);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m += __shfl_xor_sync(0xffffffffu, m, o);
-            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        }
+        const int m = (int)__reduce_add_sync(0xffffffffu, (unsigned)__popc(valid));
+        mn = qrf_warp_min(mn);   // +inf / -inf when the row has no sample
+        mx = qrf_warp_max(mx);
 
         uint32_t b0[(R + 3) / 4];
         int sum0 = 0, excl0 = 0;
