@@ -193,11 +193,16 @@ struct rfsi_forest {
     bool blocked_ok = false;
     std::vector<uint32_t> blocks;     // 32 words per block, block 0 = all pass-through
     std::vector<uint32_t> broot;      // [T]
+    // leaf tables of the blocked image: leaves renumbered left to right within each tree, so the
+    // leaves under any subtree are contiguous (neighbouring pixels end in neighbouring leaves)
+    std::vector<double> leaf_val_c, leaf_sample_c;
+    std::vector<int32_t> leaf_rid_c;
     struct Image {
         Node* nodes = nullptr;
         double* leaf_sample = nullptr;
         int32_t* leaf_rid = nullptr;
         bool compact = false;
+        bool blocked = false;
         QForest q{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     };
     mutable std::mutex mu;
@@ -215,6 +220,7 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
     const int want = env_int("RFSI_B200_COMPACT", 2);
     im.compact = f->compact_ok && want != 0;
     const bool blocked = im.compact && f->blocked_ok && want >= 2;
+    im.blocked = blocked;
     if (im.compact) {
         auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
             void* d = nullptr;
@@ -231,7 +237,8 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
             RF_TRY(up(f->qnodes.data(), f->qnodes.size() * sizeof(uint64_t), reinterpret_cast<const void**>(&im.q.nodes)));
         }
         RF_TRY(up(f->qroots.data(), f->qroots.size() * sizeof(QRoot), reinterpret_cast<const void**>(&im.q.roots)));
-        RF_TRY(up(f->leaf_val.data(), f->leaf_val.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.leaf_val)));
+        const std::vector<double>& lv = blocked ? f->leaf_val_c : f->leaf_val;
+        RF_TRY(up(lv.data(), lv.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.leaf_val)));
         RF_TRY(up(f->uvals.data(), f->uvals.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.uvals)));
         RF_TRY(up(f->uoff.data(), f->uoff.size() * sizeof(int32_t), reinterpret_cast<const void**>(&im.q.uoff)));
         RF_TRY(up(f->rpar.data(), f->rpar.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.rpar)));
@@ -241,9 +248,9 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
         CU_TRY(cudaMemcpy(im.nodes, f->nodes.data(), f->nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
     }
     if (!f->leaf_sample.empty()) {
-        CU_TRY(cudaMalloc(&im.leaf_sample, f->leaf_sample.size() * sizeof(double)));
-        CU_TRY(cudaMemcpy(im.leaf_sample, f->leaf_sample.data(), f->leaf_sample.size() * sizeof(double),
-                          cudaMemcpyHostToDevice));
+        const std::vector<double>& ls = blocked ? f->leaf_sample_c : f->leaf_sample;
+        CU_TRY(cudaMalloc(&im.leaf_sample, ls.size() * sizeof(double)));
+        CU_TRY(cudaMemcpy(im.leaf_sample, ls.data(), ls.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     f->images[device] = im;
     *out = im;
@@ -255,8 +262,9 @@ int forest_leaf_rid(const rfsi_forest* f, int device, const int32_t** out) {
     std::lock_guard<std::mutex> lk(f->mu);
     rfsi_forest::Image& im = f->images[device];
     if (!im.leaf_rid) {
-        CU_TRY(cudaMalloc(&im.leaf_rid, f->leaf_rid.size() * sizeof(int32_t)));
-        CU_TRY(cudaMemcpy(im.leaf_rid, f->leaf_rid.data(), f->leaf_rid.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        const std::vector<int32_t>& lr = im.blocked ? f->leaf_rid_c : f->leaf_rid;
+        CU_TRY(cudaMalloc(&im.leaf_rid, lr.size() * sizeof(int32_t)));
+        CU_TRY(cudaMemcpy(im.leaf_rid, lr.data(), lr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     *out = im.leaf_rid;
     return RFSI_OK;
@@ -357,6 +365,32 @@ void build_compact(rfsi_forest* f) {
     if (F > kBMaxFeat) return;
     for (int j = 0; j < F; ++j)
         if (u[j].size() > (size_t)kBMaxRank) return;
+    // leaf numbers: in-order (left to right) within each tree, trees one after the other
+    std::vector<uint32_t> leaf_no(n, 0u);
+    {
+        const bool has_s = !f->leaf_sample.empty();
+        f->leaf_val_c.clear(); f->leaf_sample_c.clear(); f->leaf_rid_c.clear();
+        f->leaf_val_c.reserve(n / 2 + T); f->leaf_rid_c.reserve(n / 2 + T);
+        if (has_s) f->leaf_sample_c.reserve(n / 2 + T);
+        std::vector<uint32_t> stack;
+        for (int t = 0; t < T; ++t) {
+            stack.assign(1, (uint32_t)t);
+            while (!stack.empty()) {
+                const uint32_t nd = stack.back();
+                stack.pop_back();
+                const Node& n0 = f->nodes[nd];
+                if (n0.feat >= F) {
+                    leaf_no[nd] = (uint32_t)f->leaf_val_c.size();
+                    f->leaf_val_c.push_back(n0.val);
+                    f->leaf_rid_c.push_back(f->leaf_rid[nd]);
+                    if (has_s) f->leaf_sample_c.push_back(f->leaf_sample[nd]);
+                } else {
+                    stack.push_back((uint32_t)n0.child + 1);   // right, popped after the whole left subtree
+                    stack.push_back((uint32_t)n0.child);
+                }
+            }
+        }
+    }
     std::vector<uint32_t>& B = f->blocks;
     B.assign(32, kBPassWord);   // block 0: pass-through everywhere; its exits are never used
     f->broot.assign((size_t)T, 0u);
@@ -368,7 +402,7 @@ void build_compact(rfsi_forest* f) {
         const Node& n0 = f->nodes[nd];
         const bool leaf = n0.feat >= F;
         if (pos >= 16) {   // an exit
-            if (leaf) { B[(size_t)blk * 32 + pos] = kBLeafFlag | nd; return; }
+            if (leaf) { B[(size_t)blk * 32 + pos] = kBLeafFlag | leaf_no[nd]; return; }
             const size_t nb = B.size() / 32;
             if (nb >= 0x7fffffffu) { fits = false; return; }
             B.resize(B.size() + 32, kBPassWord);
@@ -387,7 +421,7 @@ void build_compact(rfsi_forest* f) {
         self(self, blk, (uint32_t)n0.child + 1, 2 * pos + 1);
     };
     for (int t = 0; t < T && fits; ++t) {
-        if (f->nodes[t].feat >= F) { f->broot[t] = kBLeafFlag | (uint32_t)t; continue; }
+        if (f->nodes[t].feat >= F) { f->broot[t] = kBLeafFlag | leaf_no[t]; continue; }
         const size_t nb = B.size() / 32;
         B.resize(B.size() + 32, kBPassWord);
         f->broot[t] = (uint32_t)nb;
@@ -525,8 +559,8 @@ extern "C" int64_t rfsi_forest_info(const rfsi_forest_t* f, int what) {
         case 4: return f->leaf_sample.empty() ? 0 : 1;
         case 5:
             if (f->compact_ok && f->blocked_ok && env_int("RFSI_B200_COMPACT", 2) >= 2)
-                return (int64_t)(f->blocks.size() * 4 + f->leaf_val.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
-                                 f->leaf_sample.size() * sizeof(double));
+                return (int64_t)(f->blocks.size() * 4 + f->leaf_val_c.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
+                                 f->leaf_sample_c.size() * sizeof(double));
             if (f->compact_ok && env_int("RFSI_B200_COMPACT", 2) != 0)
                 return (int64_t)(f->qnodes.size() * 8 + f->leaf_val.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
                                  f->qroots.size() * sizeof(QRoot) + f->leaf_sample.size() * sizeof(double));
