@@ -132,7 +132,8 @@ int rfsi_forest_predict(const rfsi_forest_t* f, const double* X, int64_t npix, i
 
 /* predict(<ranger quantreg=TRUE>, df, type="quantiles", quantiles=probs):
  * temp_croatia/2_predictions.R:174-176, prcp_catalonia/5_prcp_prediction.R:289-291.
- * out is npix x nprobs column-major. */
+ * out is npix x nprobs column-major.  Forests of up to 1024 trees (the reference grows 250);
+ * more -> RFSI_E_ARG before any work is launched. */
 int rfsi_forest_quantiles(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
                           const double* probs, int32_t nprobs, double* out, int device);
 

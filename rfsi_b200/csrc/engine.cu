@@ -1262,6 +1262,7 @@ extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, 
     double* probs_dev = nullptr;
     if (out_q) {
         if (!im.leaf_sample) return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
+        if (f->ntrees > 1024) return fail(RFSI_E_ARG, "quantile forests with more than 1024 trees are not supported (T=%d)", f->ntrees);
         RF_TRY(check_probs(probs_host, nprobs));
         if (!scratch) return fail(RFSI_E_ARG, "quantiles need a scratch buffer");
         o.leaf_ids = reinterpret_cast<uint32_t*>(scratch);
@@ -1475,6 +1476,8 @@ int validate_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
         RF_TRY(check_probs(a->probs, a->nprobs));
         if (f->leaf_sample.empty())
             return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
+        if (f->ntrees > 1024)
+            return fail(RFSI_E_ARG, "quantile forests with more than 1024 trees are not supported (T=%d)", f->ntrees);
     }
     if (fused_smem_bytes<kFallbackP, false>(f->nfeat, a->n_obs + 1, true) > 227 * 1024 &&
         !(f->compact_ok && fused_smem_bytes<kFallbackP, true>(f->nfeat, a->n_obs + 1, true) <= 227 * 1024))

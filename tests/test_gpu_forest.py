@@ -104,6 +104,52 @@ def test_quantiles_with_na_samples_and_duplicates():
     np.testing.assert_array_equal(got, oracle.forest_quantiles(flat.as_dict(), X, probs, threads=8))
 
 
+@pytest.mark.parametrize("T,npix", [(100, 700), (300, 500), (512, 300), (600, 300), (1024, 130)])
+def test_quantiles_every_samples_per_lane_variant(T, npix):
+    """The quantile kernel is instantiated per ceil(T/32) in {1,2,4,8,16,32}: cover 4, 16 and 32
+    (1024 trees is the documented maximum), with row counts that leave warps and CTAs idle."""
+    flat, rng = _random_forest_case(9000 + T, 200, 4, T, 4)
+    model = rb.RangerForest(flat)
+    X = rng.normal(size=(npix, 4))
+    probs = [0.0, 0.05, 0.25, 0.5, 0.75, 0.99, 1.0]
+    got = rb.predict(model, X, type="quantiles", quantiles=probs).predictions
+    np.testing.assert_array_equal(got, oracle.forest_quantiles(flat.as_dict(), X, probs, threads=8))
+    same_mean(rb.predict(model, X).predictions, oracle.forest_predict(flat.as_dict(), X, threads=8))
+
+
+def test_quantiles_more_than_1024_trees_is_an_error():
+    flat, rng = _random_forest_case(1, 60, 2, 1025, 10)
+    model = rb.RangerForest(flat)
+    with pytest.raises(rb.RfsiError) as e:
+        rb.predict(model, rng.normal(size=(10, 2)), type="quantiles", quantiles=[0.5])
+    assert e.value.code == -3 and "1024" in str(e.value)
+    assert rb.predict(model, rng.normal(size=(10, 2))).predictions.shape == (10,)   # the mean still works
+
+
+@pytest.mark.parametrize("mode", ["coarse", "two_values", "one_outlier", "all_equal"])
+def test_quantiles_heavy_ties_rebucketing(mode):
+    """More than 32 equal / near-equal samples in one histogram bucket: the re-bucketing loop
+    and its all-equal exit (qrf.cuh) against the oracle's sort."""
+    flat, rng = _random_forest_case(4242, 400, 5, 300, 3)
+    rnv = flat.random_node_values.copy()
+    ok = ~np.isnan(rnv)
+    if mode == "coarse":
+        rnv[ok] = np.round(rnv[ok], 0)                       # a handful of distinct values
+    elif mode == "two_values":
+        rnv[ok] = np.where(rnv[ok] > 0, 1.0, 1.0 + 2.0 ** -40)   # one bucket at level 0, split at level 1
+    elif mode == "one_outlier":
+        rnv[ok] = 3.5 + 1e-9 * rng.integers(0, 3, size=int(ok.sum()))   # three values 1e-9 apart ...
+        rnv[flat.rnv_offsets[0]:flat.rnv_offsets[1]] = 1.0e6             # ... and tree 0 far away
+    else:
+        rnv[ok] = -7.25
+    flat.random_node_values = rnv
+    model = rb.RangerForest(flat)
+    X = rng.normal(size=(1500, 5))
+    probs = [0.0, 0.1, 0.25, 0.5, 0.75, 0.9, 1.0]
+    got = rb.predict(model, X, type="quantiles", quantiles=probs).predictions
+    np.testing.assert_array_equal(got, oracle.forest_quantiles(flat.as_dict(), X, probs, threads=8))
+
+
 def test_deep_skinny_tree_and_chunked_rows():
     """A degenerate chain tree (depth 300) and > 1 row chunk through the host API."""
     depth = 300
