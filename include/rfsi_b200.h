@@ -163,12 +163,15 @@ int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, int64_t npi
  * (prcp_catalonia/5_prcp_prediction.R:253-276: tmax/tmin on the DEM grid in tenths of a
  * degree, IMERG on a 0.1-degree global grid).  North-up raster: layer l, row r (0 = top),
  * column c at data[(l*nrow + r)*ncol + c]; cell (r, c) spans x_ul + c*dx .. x_ul + (c+1)*dx
- * and y_ul - (r+1)*dy .. y_ul - r*dy.  value = raw*scale + offset; raw == nodata or a point
- * outside the raster gives NA. */
+ * and y_ul - (r+1)*dy .. y_ul - r*dy.  value = raw*scale + offset -- or, with
+ * RFSI_RASTER_DIVIDE or-ed into dtype, raw/scale + offset: the scripts' `extract(tmin, gg) / 10`
+ * (5_prcp_prediction.R:254,256) is a division, and x/10 != x*0.1 in the last bit; raw == nodata
+ * or a point outside the raster gives NA. */
 enum { RFSI_F64 = 0, RFSI_F32 = 1, RFSI_I32 = 2, RFSI_I16 = 3, RFSI_U16 = 4, RFSI_U8 = 5 };
+#define RFSI_RASTER_DIVIDE 0x100
 typedef struct rfsi_raster {
     const void* data;
-    int32_t dtype;   /* RFSI_F64 ... RFSI_U8 */
+    int32_t dtype;   /* RFSI_F64 ... RFSI_U8 [| RFSI_RASTER_DIVIDE] */
     int32_t nlayers; /* 1 = static; otherwise one layer per day */
     int64_t ncol, nrow;
     double x_ul, y_ul, dx, dy; /* outer corner of the top-left cell; cell size (both > 0) */
@@ -182,6 +185,15 @@ typedef struct rfsi_raster {
 int rfsi_raster_extract(const rfsi_raster_t* r, int32_t layer, const double* loc_x, const double* loc_y,
                         int64_t npix, double grid_x0, double grid_y0, double grid_dx, double grid_dy,
                         int64_t grid_ncol, int64_t pix_begin, double* out, int device);
+
+/* A covariate repair applied after sampling and before cbind, in the order given:
+ *   cov[target] <- ifelse(cov[target] > cov[other], cov[other] - delta, cov[target])
+ * i.e. `df$tmin <- ifelse(df$tmin > df$tmax, df$tmax-1, df$tmin)` (5_prcp_prediction.R:258) is
+ * {target = tmin, other = tmax, delta = 1}; NA where either side is NA (R's ifelse). */
+typedef struct rfsi_cov_fix {
+    int32_t target, other; /* covariate column indices, both static or both per-day */
+    double delta;
+} rfsi_cov_fix_t;
 
 typedef struct rfsi_fused_args {
     size_t struct_size; /* = sizeof(rfsi_fused_args_t) */
@@ -229,6 +241,16 @@ typedef struct rfsi_fused_args {
      * covariate c is sampled on the device from that raster at the prediction locations
      * (cov[c] is then ignored) -- host-buffer entry point only */
     const rfsi_raster_t* cov_raster;
+    /* optional (nullable) list of ncov_fix covariate repairs -- host-buffer entry point only
+     * (the device form takes the caller's covariate columns as read-only) */
+    const rfsi_cov_fix_t* cov_fix;
+    int32_t ncov_fix;
+    /* optional (nullable, npix each): the coordinates at which cov_raster is sampled when they
+     * are not the near.obs coordinates -- the scripts keep the grid twice, `gg` in the rasters'
+     * lon/lat for extract() and `gg2 <- spTransform(gg, utm31)` in metres for near.obs
+     * (5_prcp_prediction.R:42-46,254-283) -- host-buffer entry point only */
+    const double* cov_loc_x;
+    const double* cov_loc_y;
 } rfsi_fused_args_t;
 
 int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device);

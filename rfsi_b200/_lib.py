@@ -40,7 +40,12 @@ class Raster(C.Structure):
     ]
 
 
+RASTER_DIVIDE = 0x100
 RASTER_DTYPES = {"float64": 0, "float32": 1, "int32": 2, "int16": 3, "uint16": 4, "uint8": 5}
+
+
+class CovFix(C.Structure):
+    _fields_ = [("target", C.c_int32), ("other", C.c_int32), ("delta", C.c_double)]
 
 
 class FusedArgs(C.Structure):
@@ -74,6 +79,10 @@ class FusedArgs(C.Structure):
         ("out_iqr_i16", C.c_void_p),
         ("pix_mask", C.c_void_p),
         ("cov_raster", C.POINTER(Raster)),
+        ("cov_fix", C.POINTER(CovFix)),
+        ("ncov_fix", C.c_int32),
+        ("cov_loc_x", C.c_void_p),
+        ("cov_loc_y", C.c_void_p),
     ]
 
 

@@ -24,7 +24,7 @@ import numpy as np
 from . import _lib
 from dataclasses import dataclass
 
-from ._lib import FEAT_DIST, FEAT_OBS, RASTER_DTYPES, FusedArgs, Raster as _CRaster, RfsiError
+from ._lib import FEAT_DIST, FEAT_OBS, RASTER_DIVIDE, RASTER_DTYPES, CovFix, FusedArgs, Raster as _CRaster, RfsiError
 from .forest import FlatForest, RangerForest, flatten_ranger, from_sklearn
 
 try:  # pandas plays the role of R's data.frame
@@ -185,7 +185,8 @@ def predict(model: RangerForest, data, type: str = "response", quantiles: Sequen
 class Raster:
     """A north-up covariate raster: data (nrow, ncol) or (nlayers, nrow, ncol) of float64 /
     float32 / int32 / int16 / uint16 / uint8; (x_ul, y_ul) the outer corner of the top-left
-    cell; value = raw*scale + offset; raw == nodata -> NA.  Sampled on the device like
+    cell; value = raw*scale + offset (divide=True: raw/scale + offset, R's `extract(r, p) / 10`);
+    raw == nodata -> NA.  Sampled on the device like
     raster::extract(r, points) (prcp_catalonia/5_prcp_prediction.R:253-276)."""
     data: np.ndarray
     x_ul: float
@@ -195,6 +196,7 @@ class Raster:
     nodata: float = float("nan")
     scale: float = 1.0
     offset: float = 0.0
+    divide: bool = False
 
     def _c(self):
         d = np.ascontiguousarray(self.data)
@@ -202,7 +204,7 @@ class Raster:
             d = d[None]
         if d.dtype.name not in RASTER_DTYPES:
             raise ValueError(f"raster dtype {d.dtype} unsupported (use one of {list(RASTER_DTYPES)})")
-        r = _CRaster(d.ctypes.data, RASTER_DTYPES[d.dtype.name], d.shape[0], d.shape[2], d.shape[1],
+        r = _CRaster(d.ctypes.data, RASTER_DTYPES[d.dtype.name] | (RASTER_DIVIDE if self.divide else 0), d.shape[0], d.shape[2], d.shape[1],
                      float(self.x_ul), float(self.y_ul), float(self.dx), float(self.dy), float(self.nodata),
                      float(self.scale), float(self.offset))
         return r, d
@@ -249,13 +251,18 @@ def feature_map(feature_names: Sequence[str], cov_names: Sequence[str], n_obs: i
 def predict_fused(model: RangerForest, *, obs_xy, obs_z, n_obs: int, locations=None, grid=None,
                   pix_begin: int = 0, npix: Optional[int] = None, covariates: Optional[dict] = None,
                   quantiles: Optional[Sequence[float]] = None, want_mean: bool = True, rm_dupl: bool = True,
-                  centi_int16: bool = False, pix_mask=None, device: int = 0) -> dict:
+                  centi_int16: bool = False, pix_mask=None, cov_fix: Sequence = (), cov_locations=None, device: int = 0) -> dict:
     """near.obs + cbind + predict for every (pixel, day) in one call (rfsi_predict_fused).
 
     obs_z: (ndays, nobs) observed values, NaN = no observation that day (the scripts'
     per-day `st[!is.na(st$TEMP),]` filter, 2_predictions.R:122-125).
     locations: (npix, 2) coordinates, or grid=(x0, y0, dx, dy, ncol) + npix (+ pix_begin)
-    for raster cells in row-major order.  covariates: {name: (npix,) or (ndays, npix)}.
+    for raster cells in row-major order.  covariates: {name: (npix,) or (ndays, npix) or Raster}.
+    cov_fix: [(target, other, delta), ...] covariate repairs applied on the device after sampling,
+    `df$target <- ifelse(df$target > df$other, df$other - delta, df$target)`
+    (5_prcp_prediction.R:258: ("tmin", "tmax", 1)).  cov_locations: (npix, 2) coordinates at which
+    Raster covariates are sampled when they differ from the near.obs coordinates (lon/lat `gg` vs
+    projected `gg2`, 5_prcp_prediction.R:42-46).
     Returns {"mean": (ndays, npix), "quantiles": (Q, ndays, npix), "mean_i16", "iqr_i16"}.
     """
     lib = _lib.load()
@@ -312,6 +319,21 @@ def predict_fused(model: RangerForest, *, obs_xy, obs_z, n_obs: int, locations=N
     a.cov_day_stride = C.cast(cov_strides, C.POINTER(C.c_int64))
     if any_raster:
         a.cov_raster = C.cast(rasters, C.POINTER(_CRaster))
+    if cov_locations is not None:
+        cl = np.asarray(cov_locations, dtype=np.float64)
+        if cl.shape != (npix, 2):
+            raise ValueError("cov_locations must be (npix, 2)")
+        clx, cly = _f64(cl[:, 0]), _f64(cl[:, 1])
+        keep += [clx, cly]
+        a.cov_loc_x, a.cov_loc_y = _ptr(clx), _ptr(cly)
+    fixes = (CovFix * max(len(cov_fix), 1))()
+    for i, (t, o, delta) in enumerate(cov_fix):
+        if t not in cov_names or o not in cov_names:
+            raise ValueError(f"cov_fix: {t!r} / {o!r} are not covariates of this call")
+        fixes[i] = CovFix(cov_names.index(t), cov_names.index(o), float(delta))
+    if len(cov_fix):
+        a.cov_fix = C.cast(fixes, C.POINTER(CovFix))
+        a.ncov_fix = len(cov_fix)
     fmap = feature_map(model.feature_names, cov_names, int(n_obs))
     a.feat_map = fmap.ctypes.data_as(C.POINTER(C.c_int32))
     out = {}

@@ -1366,7 +1366,7 @@ extern "C" int rfsi_forest_terminal_nodes(const rfsi_forest_t* f, const double* 
 namespace {
 
 size_t raster_cell_bytes(int dtype) {
-    switch (dtype) { case RFSI_F64: return 8; case RFSI_F32: case RFSI_I32: return 4;
+    switch (dtype & ~RFSI_RASTER_DIVIDE) { case RFSI_F64: return 8; case RFSI_F32: case RFSI_I32: return 4;
                      case RFSI_I16: case RFSI_U16: return 2; case RFSI_U8: return 1; default: return 0; }
 }
 
@@ -1375,6 +1375,8 @@ int check_raster(const rfsi_raster_t* r, const char* who) {
     if (raster_cell_bytes(r->dtype) == 0) return fail(RFSI_E_ARG, "%s: unknown raster dtype %d", who, r->dtype);
     if (r->ncol < 1 || r->nrow < 1 || r->nlayers < 1 || !(r->dx > 0) || !(r->dy > 0))
         return fail(RFSI_E_ARG, "%s: raster needs ncol, nrow, nlayers >= 1 and dx, dy > 0", who);
+    if ((r->dtype & RFSI_RASTER_DIVIDE) && r->scale == 0.0)
+        return fail(RFSI_E_ARG, "%s: RFSI_RASTER_DIVIDE with scale 0", who);
     return RFSI_OK;
 }
 
@@ -1472,6 +1474,13 @@ int validate_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
                     return fail(RFSI_E_ARG, "fused: covariate raster %d has %d layers for %d days", c,
                                 a->cov_raster[c].nlayers, a->ndays);
             }
+    if ((a->cov_loc_x == nullptr) != (a->cov_loc_y == nullptr)) return fail(RFSI_E_ARG, "fused: cov_loc_x/cov_loc_y go together");
+    if (a->ncov_fix < 0 || (a->ncov_fix > 0 && !a->cov_fix)) return fail(RFSI_E_ARG, "fused: bad cov_fix list");
+    for (int k = 0; k < a->ncov_fix; ++k) {
+        const rfsi_cov_fix_t& x = a->cov_fix[k];
+        if (x.target < 0 || x.target >= a->ncov || x.other < 0 || x.other >= a->ncov || x.target == x.other)
+            return fail(RFSI_E_ARG, "fused: cov_fix[%d] names covariates %d, %d of %d", k, x.target, x.other, a->ncov);
+    }
     if ((a->out_q || a->out_iqr_i16)) {
         RF_TRY(check_probs(a->probs, a->nprobs));
         if (f->leaf_sample.empty())
@@ -1705,6 +1714,8 @@ extern "C" int rfsi_dev_predict_fused(const rfsi_forest_t* f, const rfsi_fused_a
 {
     RF_TRY(validate_fused(f, a));
     if (a->cov_raster) return fail(RFSI_E_ARG, "fused (device form): sample rasters first; cov_raster is host-entry only");
+    if (a->ncov_fix) return fail(RFSI_E_ARG, "fused (device form): covariate columns are read-only; cov_fix is host-entry only");
+    if (a->cov_loc_x) return fail(RFSI_E_ARG, "fused (device form): cov_loc_x/cov_loc_y are host-entry only");
     if (!workspace) return fail(RFSI_E_ARG, "fused: workspace is NULL");
     RF_TRY(use_device(device));
     const FusedPlan pl = plan_fused(f, a, kc_extra_default());
@@ -1780,13 +1791,17 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
         return is_rast[c] ? a->cov_raster[c].nlayers != 1 : a->cov_day_stride[c] != 0;
     };
 
+    for (int k = 0; k < a->ncov_fix; ++k)
+        if (cov_dynamic(a->cov_fix[k].target) != cov_dynamic(a->cov_fix[k].other))
+            return fail(RFSI_E_ARG, "fused: cov_fix[%d] pairs a static covariate with a per-day one", k);
+
     // per-slot device buffers: a work item is (pixel chunk, day batch)
     rfsi_fused_args_t proto = *a;
     proto.npix = chunk;
     FusedPlan pl = plan_fused(f, &proto, kc_extra);
     const int db = pl.db;
     struct Slot {
-        DevBuf ws, lx, ly, mask, mean, q, mean16, iqr16;
+        DevBuf ws, lx, ly, clx, cly, mask, mean, q, mean16, iqr16;
         DevBuf cov[kMaxCov];
         int64_t cand_chunk = -1;
         Stream st;  // last member: destroyed (and synchronised) before the buffers above
@@ -1796,6 +1811,7 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
         RF_TRY(slot[s].st.create());
         RF_TRY(slot[s].ws.alloc(pl.total));
         if (a->loc_x) { RF_TRY(slot[s].lx.alloc(sizeof(double) * chunk)); RF_TRY(slot[s].ly.alloc(sizeof(double) * chunk)); }
+        if (a->cov_loc_x) { RF_TRY(slot[s].clx.alloc(sizeof(double) * chunk)); RF_TRY(slot[s].cly.alloc(sizeof(double) * chunk)); }
         if (a->pix_mask) RF_TRY(slot[s].mask.alloc((size_t)chunk));
         if (a->out_mean) RF_TRY(slot[s].mean.alloc(sizeof(double) * chunk * db));
         if (a->out_q) RF_TRY(slot[s].q.alloc(sizeof(double) * chunk * db * a->nprobs));
@@ -1835,12 +1851,17 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
                 if (!reuse) CU_TRY(cudaMemcpyAsync(sl.mask.p, a->pix_mask + p0, (size_t)cur, cudaMemcpyHostToDevice, s));
                 b.pix_mask = sl.mask.as<unsigned char>();
             }
+            if (a->cov_loc_x && !reuse) {
+                CU_TRY(cudaMemcpyAsync(sl.clx.p, a->cov_loc_x + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+                CU_TRY(cudaMemcpyAsync(sl.cly.p, a->cov_loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+            }
             const double* covp[kMaxCov];
             int64_t covs[kMaxCov];
             for (int c = 0; c < a->ncov; ++c) {
                 if (is_rast[c]) {  // sample the raster at this chunk's locations, this batch's days
                     LocSpec Lc{b.loc_x, b.loc_y, a->grid_x0, a->grid_y0, a->grid_dx, a->grid_dy,
                                a->loc_x ? 1 : a->grid_ncol, a->loc_x ? 0 : b.pix_begin};
+                    if (a->cov_loc_x) { Lc.x = sl.clx.as<double>(); Lc.y = sl.cly.as<double>(); }
                     const RasterDev rd = raster_dev(a->cov_raster[c], d_rast[c].p);
                     if (!cov_dynamic(c)) {
                         if (!reuse) RF_TRY(launch_raster_extract(rd, 0, 1, Lc, cur, sl.cov[c].as<double>(), cur, s));
@@ -1864,7 +1885,19 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
                 }
                 covp[c] = sl.cov[c].as<double>();
             }
+            for (int k = 0; k < a->ncov_fix; ++k) {  // repairs, on the staged columns (static ones once per chunk)
+                const rfsi_cov_fix_t& x = a->cov_fix[k];
+                const bool dyn = cov_dynamic(x.target);
+                if (!dyn && reuse) continue;
+                const long long n = (long long)cur * (dyn ? nd : 1);
+                cov_fix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sl.cov[x.target].as<double>(),
+                                                                            sl.cov[x.other].as<double>(), x.delta, n);
+                count_launch();
+                CU_TRY(cudaGetLastError());
+            }
             b.cov = covp; b.cov_day_stride = covs; b.cov_raster = nullptr;
+            b.cov_fix = nullptr; b.ncov_fix = 0;
+            b.cov_loc_x = b.cov_loc_y = nullptr;
             b.out_mean = a->out_mean ? sl.mean.as<double>() : nullptr;
             b.out_q = a->out_q ? sl.q.as<double>() : nullptr;
             b.out_mean_i16 = a->out_mean_i16 ? sl.mean16.as<int16_t>() : nullptr;

@@ -17,7 +17,7 @@ struct RasterDev {
 };
 
 __device__ __forceinline__ double raster_raw(const RasterDev& r, long long i) {
-    switch (r.dtype) {
+    switch (r.dtype & 0xff) {
         case 0: return reinterpret_cast<const double*>(r.data)[i];
         case 1: return (double)reinterpret_cast<const float*>(r.data)[i];
         case 2: return (double)reinterpret_cast<const int32_t*>(r.data)[i];
@@ -38,7 +38,9 @@ __device__ __forceinline__ double raster_value(const RasterDev& r, int layer, do
     if (w >= r.nrow) w = r.nrow - 1;
     const double raw = raster_raw(r, ((long long)layer * r.nrow + w) * r.ncol + c);
     if (raw != raw || raw == r.nodata) return na_real();
-    return __dadd_rn(__dmul_rn(raw, r.scale), r.offset);   // two roundings, like the CPU (no FMA contraction)
+    // two roundings, like the CPU (no FMA contraction); RFSI_RASTER_DIVIDE: R's `extract(r, pts) / 10`
+    const double v = (r.dtype & 0x100) ? __ddiv_rn(raw, r.scale) : __dmul_rn(raw, r.scale);
+    return __dadd_rn(v, r.offset);
 }
 
 // out[(l - layer0)*ld + p] for layers [layer0, layer0 + nl) (a static raster: nl = 1, layer0 = 0)
@@ -50,6 +52,16 @@ __global__ void raster_extract_kernel(RasterDev r, int layer0, int nl, LocSpec L
     double x, y;
     get_loc(L, p, x, y);
     for (int l = 0; l < nl; ++l) out[(long long)l * ld + p] = raster_value(r, layer0 + l, x, y);
+}
+
+// df$t <- ifelse(df$t > df$o, df$o - delta, df$t) over n cells (5_prcp_prediction.R:258)
+__global__ void cov_fix_kernel(double* __restrict__ t, const double* __restrict__ o, double delta, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = t[i], b = o[i];
+    if (a != a || b != b) t[i] = na_real();          // ifelse(NA, ...) is NA
+    else if (a > b) t[i] = __dsub_rn(b, delta);
 }
 
 }  // namespace rfsi
