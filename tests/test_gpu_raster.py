@@ -12,7 +12,7 @@ from tests.util import same_mean
 pytestmark = pytest.mark.gpu
 
 
-def np_extract(data, x_ul, y_ul, dx, dy, nodata, scale, offset, xy, layer=0):
+def np_extract(data, x_ul, y_ul, dx, dy, nodata, scale, offset, xy, layer=0, divide=False):
     d = data if data.ndim == 3 else data[None]
     nrow, ncol = d.shape[1:]
     x, y = xy[:, 0], xy[:, 1]
@@ -22,7 +22,7 @@ def np_extract(data, x_ul, y_ul, dx, dy, nodata, scale, offset, xy, layer=0):
     out = np.full(len(x), np.nan)
     raw = d[layer][np.clip(r, 0, nrow - 1), np.clip(c, 0, ncol - 1)].astype(np.float64)
     ok = inside & ~(raw == nodata) & ~np.isnan(raw)
-    out[ok] = raw[ok] * scale + offset
+    out[ok] = (raw[ok] / scale if divide else raw[ok] * scale) + offset
     return out
 
 
@@ -85,3 +85,71 @@ def test_fused_with_raster_covariates_matches_host_sampled_covariates():
     c = rb.predict_fused(model, obs_xy=case.obs_xy, obs_z=case.obs_z, n_obs=case.n_obs, locations=loc[sel],
                          covariates={"imerg": R["imerg"], "tmax": host_cov["tmax"][:, sel], "tmin": host_cov["tmin"][:, sel]})
     np.testing.assert_array_equal(c["mean"], a["mean"][:, sel])
+
+
+def test_divide_is_a_division_not_a_multiplication_by_the_reciprocal():
+    """extract(tmin, gg) / 10 (5_prcp_prediction.R:254): x/10 and x*0.1 differ in the last bit for
+    about a third of the integers; the engine must give R's value."""
+    data = np.arange(-400, 400, dtype=np.int16).reshape(20, 40)
+    xy = np.column_stack([np.tile(np.arange(40) + 0.5, 20), np.repeat(20 - (np.arange(20) + 0.5), 40)])
+    r = rb.Raster(data, 0.0, 20.0, 1.0, 1.0, nodata=-32767, scale=10.0, divide=True)
+    got = rb.raster_extract(r, locations=xy)
+    np.testing.assert_array_equal(got, data.ravel().astype(np.float64) / 10)
+    mul = rb.raster_extract(rb.Raster(data, 0.0, 20.0, 1.0, 1.0, nodata=-32767, scale=0.1), locations=xy)
+    assert (mul != got).sum() > 100                       # the two are not interchangeable
+    with pytest.raises(rb.RfsiError):
+        rb.raster_extract(rb.Raster(data, 0.0, 20.0, 1.0, 1.0, scale=0.0, divide=True), locations=xy)
+
+
+def test_fused_covariate_repair_and_separate_sampling_coordinates():
+    """5_prcp_prediction.R:253-283: rasters sampled at `gg` (their own CRS), near.obs at `gg2`
+    (projected), tmin repaired where it exceeds tmax -- all inside the one fused call."""
+    case = synth.make_case("c4", ndays=3)
+    ncol, nrow = case.ncol, case.nrow
+    rng = np.random.default_rng(5)
+    loc = case.locations()
+    # the rasters live in another coordinate system: an affine image of the prediction coordinates
+    cov_loc = np.column_stack([0.16 + loc[:, 0] * 0.008, 40.5 + loc[:, 1] * 0.008])
+    geo = dict(x_ul=0.16, y_ul=40.5 + nrow * 0.008, dx=0.008, dy=0.008)
+    tmax = rng.integers(-50, 350, size=(3, nrow, ncol)).astype(np.int16)
+    tmin = (tmax - rng.integers(-30, 120, size=tmax.shape)).astype(np.int16)     # above tmax in ~20 % of the cells
+    imerg = rng.integers(0, 500, size=(3, 30, 40)).astype(np.uint16)
+    R = {"tmax": rb.Raster(tmax, nodata=-32767, scale=10.0, divide=True, **geo),
+         "tmin": rb.Raster(tmin, nodata=-32767, scale=10.0, divide=True, **geo),
+         "imerg": rb.Raster(imerg, 0.0, 40.5 + nrow * 0.008 + 0.1, 0.1, 0.1)}
+    host = {k: np.stack([np_extract(r.data, r.x_ul, r.y_ul, r.dx, r.dy, r.nodata, r.scale, r.offset, cov_loc, d, r.divide)
+                         for d in range(3)]) for k, r in R.items()}
+    assert not any(np.isnan(v).any() for v in host.values())
+    bad = host["tmin"] > host["tmax"]
+    assert 0.05 < bad.mean() < 0.5
+    fixed = dict(host)
+    fixed["tmin"] = np.where(bad, host["tmax"] - 1, host["tmin"])           # ifelse(tmin > tmax, tmax-1, tmin)
+
+    def station_cov(k):                             # the training table samples the same rasters at the stations
+        def f(xy, d):
+            at = np.column_stack([0.16 + xy[:, 0] * 0.008, 40.5 + xy[:, 1] * 0.008])
+            v = {n: np_extract(R[n].data, R[n].x_ul, R[n].y_ul, R[n].dx, R[n].dy, R[n].nodata, R[n].scale, R[n].offset,
+                               at, d, R[n].divide) for n in R}
+            v["tmin"] = np.where(v["tmin"] > v["tmax"], v["tmax"] - 1, v["tmin"])
+            return v[k]
+        return f
+    case.cov_daily = {k: station_cov(k) for k in R}
+    X, y = synth.training_table(case, lambda l, o, z, n: oracle.near_obs(l, o, z, n)[:2])
+    flat = grow.grow_forest(X, y, case.feature_names, num_trees=40, quantreg=True)
+    model = rb.RangerForest(flat)
+    kw = dict(obs_xy=case.obs_xy, obs_z=case.obs_z, n_obs=case.n_obs, quantiles=[0.25, 0.5, 0.75])
+    a = rb.predict_fused(model, locations=loc, cov_locations=cov_loc, covariates=R, cov_fix=[("tmin", "tmax", 1.0)], **kw)
+    b = rb.predict_fused(model, locations=loc, covariates=fixed, **kw)
+    np.testing.assert_array_equal(a["mean"], b["mean"])
+    np.testing.assert_array_equal(a["quantiles"], b["quantiles"])
+    unfixed = rb.predict_fused(model, locations=loc, cov_locations=cov_loc, covariates=R, **kw)
+    assert (unfixed["mean"] != a["mean"]).any()            # the repair matters for this forest
+    # repairs also apply to host-array covariates, static pairs included; mixed dynamics are refused
+    c = rb.predict_fused(model, locations=loc, covariates=host, cov_fix=[("tmin", "tmax", 1.0)], **kw)
+    np.testing.assert_array_equal(c["mean"], a["mean"])
+    with pytest.raises(rb.RfsiError):
+        rb.predict_fused(model, locations=loc, covariates={**host, "tmax": host["tmax"][0]}, cov_fix=[("tmin", "tmax", 1.0)], **kw)
+    sel = np.sort(rng.choice(case.npix, 1200, replace=False))
+    ref = oracle.predict_fused(flat.as_dict(), case.feature_names, loc_xy=loc[sel], obs_xy=case.obs_xy, obs_z=case.obs_z,
+                               n_obs=case.n_obs, covariates={k: v[:, sel] for k, v in fixed.items()})
+    same_mean(a["mean"][:, sel], ref["mean"])
