@@ -386,8 +386,11 @@ def main_ours(args):
     fused_ms, fused_n = prof["fused"]
     units_per_launch = P * D * args.steps / max(1, fused_n)
     achieved = b_rf * units_per_launch / (fused_ms / max(1, fused_n) * 1e-3) / 1e9 if fused_ms > 0 else None
+    image = {0: "wide 16-byte fp64 nodes", 1: "compact 8-byte rank nodes", 2: "blocked 4-byte rank nodes, 4 levels per 128-byte line"}
+    image_code = int(info.get("image", 2))
     roofline = {
-        "bound": "hbm", "kernel": "fused_kernel<256,8,false,false,compact> (per-day candidate compaction + forest traversal)",
+        "bound": "hbm", "kernel": f"fused_kernel<256,J> on the {image[image_code]} "
+                                  "(per-day candidate compaction + forest traversal)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
         "traffic": (traffic * units_per_launch) if traffic else None,
         "traffic_source": "profiles/traffic.json (ncu --set full dram__bytes_read+write, bench shape), bytes per launch",
@@ -398,7 +401,7 @@ def main_ours(args):
         "geometry_pass_ms_per_step": prof["knn_geometry"][0] / max(1, args.steps),
         "forest_bytes": info["device_bytes"],
         "note": "achieved counts every node visit as a 16-B gather (SURVEY.md 8d: algorithmic bytes); a warp's 32 "
-                "adjacent pixels share tree paths and the compact image moves 8 B per node, so L1/L2 serve most "
+                "adjacent pixels share tree paths and the rank-quantised images move 4 or 8 B per node, so L1/L2 serve most "
                 "visits: frac > 1 of the HBM roof, DRAM traffic ~14x below the algorithmic figure; the kernel is "
                 "L1-data-path bound (profiles/r01_e_*)",
     }

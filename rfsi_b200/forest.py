@@ -212,7 +212,8 @@ class RangerForest:
 
     def info(self) -> dict:
         lib = _lib.load()
-        keys = ["ntrees", "nfeat", "nodes", "max_depth", "has_samples", "device_bytes", "internal_nodes"]
+        keys = ["ntrees", "nfeat", "nodes", "max_depth", "has_samples", "device_bytes", "internal_nodes", "image",
+                "unique_thresholds", "blocks"]          # image: 0 wide, 1 compact, 2 blocked
         return {k: int(lib.rfsi_forest_info(self.handle, i)) for i, k in enumerate(keys)}
 
     def upload(self, device: int = 0):
