@@ -184,12 +184,95 @@ SEXP C_rfsi_pred_fused(SEXP h, SEXP loc_xy, SEXP obs_xy, SEXP obs_z, SEXP n_obs,
     return out;
 }
 
+/* the map-making loop of prcp_catalonia/5_prcp_prediction.R:244-309 in one call:
+ * cov is a list whose elements are numeric (as in C_rfsi_pred_fused) or raster descriptors
+ *   list(values = getValues(r) (double or integer, cells row by row from the top-left, layers
+ *        one after the other), dim = c(ncol, nrow, nlayers), geo = c(xmin, ymax, xres, yres),
+ *        divisor = 10 or NULL)
+ * sampled on the device at cov_loc (npix x 2, the grid in the rasters' CRS: `gg`) while
+ * near.obs runs at loc_xy (`gg2`); fix_idx (k x 2, 1-based covariate indices target / other)
+ * and fix_delta (k) are the repairs `ifelse(target > other, other - delta, target)`.
+ * -> list(pred = round(mean*100), iqr = round((q_last - q_first)/2*100)) as integer npix x ndays
+ * matrices, NA where the scripts write NAflag. */
+SEXP C_rfsi_pred_maps(SEXP h, SEXP loc_xy, SEXP cov_loc, SEXP obs_xy, SEXP obs_z, SEXP n_obs, SEXP cov, SEXP feat_map,
+                      SEXP probs, SEXP fix_idx, SEXP fix_delta, SEXP device)
+{
+    rfsi_forest_t* f = forest_of(h);
+    const R_xlen_t npix = Rf_nrows(loc_xy), nobs = Rf_nrows(obs_xy);
+    const int ndays = Rf_ncols(obs_z), ncov = (int)XLENGTH(cov);
+    rfsi_fused_args_t a;
+    memset(&a, 0, sizeof a);
+    a.struct_size = sizeof a;
+    a.loc_x = REAL(loc_xy); a.loc_y = REAL(loc_xy) + npix; a.npix = (int64_t)npix; a.grid_ncol = 1;
+    if (cov_loc != R_NilValue) {
+        if (Rf_nrows(cov_loc) != npix) Rf_error("pred.maps: cov.locations must have one row per location");
+        a.cov_loc_x = REAL(cov_loc); a.cov_loc_y = REAL(cov_loc) + npix;
+    }
+    a.obs_x = REAL(obs_xy); a.obs_y = REAL(obs_xy) + nobs; a.nobs = (int32_t)nobs;
+    a.obs_z = REAL(obs_z); a.ndays = ndays; a.n_obs = Rf_asInteger(n_obs); a.rm_dupl = 1;
+    const size_t nc = (size_t)(ncov ? ncov : 1);
+    const double** cols = (const double**)R_alloc(nc, sizeof(double*));
+    int64_t* strides = (int64_t*)R_alloc(nc, sizeof(int64_t));
+    rfsi_raster_t* rast = (rfsi_raster_t*)R_alloc(nc, sizeof(rfsi_raster_t));
+    memset(rast, 0, nc * sizeof(rfsi_raster_t));
+    for (int c = 0; c < ncov; ++c) {
+        SEXP v = VECTOR_ELT(cov, c);
+        cols[c] = NULL; strides[c] = 0;
+        if (TYPEOF(v) == VECSXP) {          /* raster descriptor */
+            SEXP val = VECTOR_ELT(v, 0), dim = VECTOR_ELT(v, 1), geo = VECTOR_ELT(v, 2), dv = VECTOR_ELT(v, 3);
+            rfsi_raster_t* r = &rast[c];
+            if (TYPEOF(val) == INTSXP) { r->data = INTEGER(val); r->dtype = RFSI_I32; r->nodata = (double)NA_INTEGER; }
+            else { r->data = REAL(val); r->dtype = RFSI_F64; r->nodata = R_NaN; }   /* NA_real_ is a NaN: masked anyway */
+            r->ncol = INTEGER(dim)[0]; r->nrow = INTEGER(dim)[1]; r->nlayers = INTEGER(dim)[2];
+            r->x_ul = REAL(geo)[0]; r->y_ul = REAL(geo)[1]; r->dx = REAL(geo)[2]; r->dy = REAL(geo)[3];
+            r->scale = 1.0; r->offset = 0.0;
+            if (dv != R_NilValue) { r->scale = REAL(dv)[0]; r->dtype |= RFSI_RASTER_DIVIDE; }
+        } else {
+            cols[c] = REAL(v);
+            strides[c] = (XLENGTH(v) == npix) ? 0 : (int64_t)npix;
+        }
+    }
+    a.ncov = ncov; a.cov = cols; a.cov_day_stride = strides; a.cov_raster = rast; a.feat_map = INTEGER(feat_map);
+    const int nfix = fix_idx == R_NilValue ? 0 : Rf_nrows(fix_idx);
+    rfsi_cov_fix_t* fix = (rfsi_cov_fix_t*)R_alloc((size_t)(nfix ? nfix : 1), sizeof(rfsi_cov_fix_t));
+    for (int k = 0; k < nfix; ++k) {
+        fix[k].target = INTEGER(fix_idx)[k] - 1; fix[k].other = INTEGER(fix_idx)[k + nfix] - 1;
+        fix[k].delta = REAL(fix_delta)[k];
+    }
+    a.cov_fix = nfix ? fix : NULL; a.ncov_fix = nfix;
+    const size_t cells = (size_t)npix * (size_t)ndays;
+    int16_t* m16 = (int16_t*)R_alloc(cells ? cells : 1, sizeof(int16_t));
+    int16_t* q16 = NULL;
+    a.out_mean_i16 = m16;
+    double* mean = (double*)R_alloc(cells ? cells : 1, sizeof(double));   /* the Int16 epilogue rides on the mean */
+    a.out_mean = mean;
+    if (probs != R_NilValue) {
+        a.probs = REAL(probs); a.nprobs = (int32_t)XLENGTH(probs);
+        q16 = (int16_t*)R_alloc(cells ? cells : 1, sizeof(int16_t));
+        a.out_iqr_i16 = q16;
+    }
+    check_rc(rfsi_predict_fused(f, &a, Rf_asInteger(device)));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP pm = PROTECT(Rf_allocMatrix(INTSXP, (int)npix, ndays));
+    for (size_t i = 0; i < cells; ++i) INTEGER(pm)[i] = m16[i] == -32767 ? NA_INTEGER : (int)m16[i];
+    SET_VECTOR_ELT(out, 0, pm);
+    if (q16) {
+        SEXP qm = PROTECT(Rf_allocMatrix(INTSXP, (int)npix, ndays));
+        for (size_t i = 0; i < cells; ++i) INTEGER(qm)[i] = q16[i] == -32767 ? NA_INTEGER : (int)q16[i];
+        SET_VECTOR_ELT(out, 1, qm);
+        UNPROTECT(1);
+    }
+    UNPROTECT(2);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_rfsi_near_obs", (DL_FUNC)&C_rfsi_near_obs, 6},
     {"C_rfsi_near_obs_days", (DL_FUNC)&C_rfsi_near_obs_days, 5},
     {"C_rfsi_forest_new", (DL_FUNC)&C_rfsi_forest_new, 7},
     {"C_rfsi_predict", (DL_FUNC)&C_rfsi_predict, 4},
     {"C_rfsi_pred_fused", (DL_FUNC)&C_rfsi_pred_fused, 9},
+    {"C_rfsi_pred_maps", (DL_FUNC)&C_rfsi_pred_maps, 12},
     {NULL, NULL, 0}};
 
 void R_init_rfsib200(DllInfo* dll) {

@@ -20,6 +20,9 @@ SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP); SEXP VECTOR_ELT(SEXP, R_xlen_t); void
 SEXP Rf_mkChar(const char*); SEXP Rf_setAttrib(SEXP, SEXP, SEXP); SEXP Rf_install(const char*);
 void Rf_error(const char*, ...); void Rf_warning(const char*, ...);
 char* R_alloc(size_t, int);
+int TYPEOF(SEXP);
+extern int R_NaInt; extern double R_NaN;
+#define NA_INTEGER R_NaInt
 SEXP R_MakeExternalPtr(void*, SEXP, SEXP); void* R_ExternalPtrAddr(SEXP); void R_ClearExternalPtr(SEXP);
 typedef void (*R_CFinalizer_t)(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
