@@ -254,6 +254,14 @@ typedef struct rfsi_fused_args {
 } rfsi_fused_args_t;
 
 int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device);
+/* The same call spread over several GPUs of one box: the pixels are cut into ndevices contiguous
+ * bands (whole raster rows where the locations are raster cells), one host thread per band drives
+ * its device, forest and station tables are replicated, and every band's results are copied
+ * straight into its slice of the caller's arrays -- no collective, no reduction (the work
+ * shards trivially; this is what lets ONE R process use all GPUs of the box, where the scripts
+ * use foreach %dopar% over days, 5_prcp_prediction.R:243-244).  devices may repeat.  Returns the
+ * first error of any band, else the first warning. */
+int rfsi_predict_fused_multi(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const int* devices, int ndevices);
 /* same with every pointer in `a` (except probs, feat_map, cov, cov_day_stride, which
  * stay host arrays; cov[c] are device pointers) already on `device`.  workspace:
  * rfsi_dev_fused_workspace_bytes() bytes of device memory.  counters (nullable):

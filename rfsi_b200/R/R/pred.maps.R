@@ -9,6 +9,8 @@
 #                one layer per day -- sampled on the GPU like extract(r, gg)
 #   divisor    : named numeric, e.g. c(tmin = 10, tmax = 10) for `extract(tmin, gg) / 10`
 #   cov.fix    : list(c("tmin", "tmax", 1)) for `df$tmin <- ifelse(df$tmin > df$tmax, df$tmax-1, df$tmin)`
+#   device     : one GPU index, or several (0:7): the pixels are cut into one band per GPU inside
+#                the library (rfsi_predict_fused_multi) -- one R process drives the whole box
 # Returns list(pred, iqr): integer npix x ndays matrices, round(x*100), NA where the scripts
 # write NAflag = -32767; hand them to writeRaster(..., datatype='INT2S') as before.
 pred.maps <- function(model, gg, gg2 = gg, obs.xy, obs.z, n.obs, covariates, divisor = NULL, cov.fix = NULL,

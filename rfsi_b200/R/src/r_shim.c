@@ -251,7 +251,9 @@ SEXP C_rfsi_pred_maps(SEXP h, SEXP loc_xy, SEXP cov_loc, SEXP obs_xy, SEXP obs_z
         q16 = (int16_t*)R_alloc(cells ? cells : 1, sizeof(int16_t));
         a.out_iqr_i16 = q16;
     }
-    check_rc(rfsi_predict_fused(f, &a, Rf_asInteger(device)));
+    /* device: one GPU, or an integer vector of GPUs (one band of pixels each) */
+    if (XLENGTH(device) > 1) check_rc(rfsi_predict_fused_multi(f, &a, INTEGER(device), (int)XLENGTH(device)));
+    else check_rc(rfsi_predict_fused(f, &a, Rf_asInteger(device)));
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
     SEXP pm = PROTECT(Rf_allocMatrix(INTSXP, (int)npix, ndays));
     for (size_t i = 0; i < cells; ++i) INTEGER(pm)[i] = m16[i] == -32767 ? NA_INTEGER : (int)m16[i];

@@ -114,6 +114,7 @@ _SIGNATURES = [
     ("rfsi_dev_forest_predict", C.c_int,
      [_P, _P, C.c_int64, C.c_int64, _P, _P, C.c_int32, _P, _P, _P, _P, _P, C.c_int, _P]),
     ("rfsi_predict_fused", C.c_int, [_P, C.POINTER(FusedArgs), C.c_int]),
+    ("rfsi_predict_fused_multi", C.c_int, [_P, C.POINTER(FusedArgs), C.POINTER(C.c_int), C.c_int]),
     ("rfsi_dev_fused_workspace_bytes", C.c_size_t, [_P, C.POINTER(FusedArgs)]),
     ("rfsi_dev_predict_fused", C.c_int, [_P, C.POINTER(FusedArgs), _P, _P, C.c_int, _P]),
     ("rfsi_launch_count", C.c_uint64, []),

@@ -251,7 +251,8 @@ def feature_map(feature_names: Sequence[str], cov_names: Sequence[str], n_obs: i
 def predict_fused(model: RangerForest, *, obs_xy, obs_z, n_obs: int, locations=None, grid=None,
                   pix_begin: int = 0, npix: Optional[int] = None, covariates: Optional[dict] = None,
                   quantiles: Optional[Sequence[float]] = None, want_mean: bool = True, rm_dupl: bool = True,
-                  centi_int16: bool = False, pix_mask=None, cov_fix: Sequence = (), cov_locations=None, device: int = 0) -> dict:
+                  centi_int16: bool = False, pix_mask=None, cov_fix: Sequence = (), cov_locations=None, device: int = 0,
+                  devices: Optional[Sequence[int]] = None) -> dict:
     """near.obs + cbind + predict for every (pixel, day) in one call (rfsi_predict_fused).
 
     obs_z: (ndays, nobs) observed values, NaN = no observation that day (the scripts'
@@ -262,7 +263,8 @@ def predict_fused(model: RangerForest, *, obs_xy, obs_z, n_obs: int, locations=N
     `df$target <- ifelse(df$target > df$other, df$other - delta, df$target)`
     (5_prcp_prediction.R:258: ("tmin", "tmax", 1)).  cov_locations: (npix, 2) coordinates at which
     Raster covariates are sampled when they differ from the near.obs coordinates (lon/lat `gg` vs
-    projected `gg2`, 5_prcp_prediction.R:42-46).
+    projected `gg2`, 5_prcp_prediction.R:42-46).  devices: several GPUs of the box, one band of
+    pixels each (rfsi_predict_fused_multi); default the single `device`.
     Returns {"mean": (ndays, npix), "quantiles": (Q, ndays, npix), "mean_i16", "iqr_i16"}.
     """
     lib = _lib.load()
@@ -357,7 +359,11 @@ def predict_fused(model: RangerForest, *, obs_xy, obs_z, n_obs: int, locations=N
     if pix_mask is not None:
         mask = np.ascontiguousarray(pix_mask, dtype=np.uint8)
         a.pix_mask = _ptr(mask)
-    rc = lib.rfsi_predict_fused(model.handle, C.byref(a), device)
+    if devices is not None:
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = lib.rfsi_predict_fused_multi(model.handle, C.byref(a), devs, len(devices))
+    else:
+        rc = lib.rfsi_predict_fused(model.handle, C.byref(a), device)
     if _lib.check(rc) == _lib.RFSI_W_TOO_FEW_OBS:
         warnings.warn(_lib.last_error())
     del keep, probs, mask

@@ -1724,14 +1724,38 @@ extern "C" int rfsi_dev_predict_fused(const rfsi_forest_t* f, const rfsi_fused_a
     return dev_fused(f, a, pl, workspace, counters, device, (cudaStream_t)stream, false, true);
 }
 
-extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device)
-{
+namespace {
+
+int validate_fused_host(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
     RF_TRY(validate_fused(f, a));
     for (int32_t s = 0; s < a->nobs; ++s)
         if (a->obs_x[s] != a->obs_x[s] || a->obs_y[s] != a->obs_y[s])
             return fail(RFSI_E_NA_INPUT, "fused: station %d has an NA coordinate", s + 1);
+    return RFSI_OK;
+}
+
+// Explicit coordinates that are really raster cells stored row by row: the row length (the
+// caller's grid_ncol hint, else detected from the first two rows), or 0/1 when they are not.
+int64_t explicit_row_len(const rfsi_fused_args_t* a) {
+    int64_t row_len = a->loc_x ? a->grid_ncol : 0;
+    if (a->loc_x && row_len <= 1) {
+        int64_t i = 1;
+        while (i < a->npix && a->loc_y[i] == a->loc_y[0]) ++i;
+        if (i >= 16 && i < a->npix && a->npix % i == 0 && a->npix / i >= 4 && a->loc_y[i - 1] == a->loc_y[0] &&
+            a->loc_y[2 * i - 1] == a->loc_y[i] && a->loc_x[i] == a->loc_x[0])
+            row_len = i;
+    }
+    return row_len;
+}
+
+// The host-buffer pipeline for the pixels [pb, pe) of the call (the whole call: 0, npix; one
+// band of it per device in rfsi_predict_fused_multi).  Outputs, covariates and masks are
+// indexed by the call's global pixel index, so bands write disjoint slices of the same arrays.
+int host_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device, int64_t pb, int64_t pe)
+{
     RF_TRY(use_device(device));
-    if (a->npix == 0) return RFSI_OK;
+    if (pe <= pb) return RFSI_OK;
+    const int64_t band = pe - pb;
     Trace tr;
     const int S = a->nobs, D = a->ndays;
     // candidates beyond n.obs+1: as many as the worst day has missing stations (capped)
@@ -1746,23 +1770,16 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
     // explicit coordinates that are really raster cells stored row by row (the usual R input:
     // coordinates(SpatialPixels) / a grid data.frame): find the row length so threads can be
     // mapped to compact 2-D tiles.  Only a mapping hint -- results do not depend on it.
-    int64_t row_len = a->loc_x ? a->grid_ncol : 0;
-    if (a->loc_x && row_len <= 1) {
-        int64_t i = 1;
-        while (i < a->npix && a->loc_y[i] == a->loc_y[0]) ++i;
-        if (i >= 16 && i < a->npix && a->npix % i == 0 && a->npix / i >= 4 && a->loc_y[i - 1] == a->loc_y[0] &&
-            a->loc_y[2 * i - 1] == a->loc_y[i] && a->loc_x[i] == a->loc_x[0])
-            row_len = i;
-    }
+    const int64_t row_len = explicit_row_len(a);
 
     // pixel chunking: bound per-chunk device memory
     const bool want_q = a->out_q || a->out_iqr_i16;
     int64_t chunk = 1 << 20;
     if (want_q) chunk = std::max<int64_t>(4096, std::min<int64_t>(chunk, (int64_t(1) << 30) / (8 * (int64_t)f->ntrees)));
-    chunk = std::min(chunk, a->npix);
-    if (!a->loc_x && a->pix_begin % a->grid_ncol == 0 && chunk < a->npix && chunk >= a->grid_ncol)
+    chunk = std::min(chunk, band);
+    if (!a->loc_x && (a->pix_begin + pb) % a->grid_ncol == 0 && chunk < band && chunk >= a->grid_ncol)
         chunk = chunk / a->grid_ncol * a->grid_ncol;  // whole raster rows per chunk keeps 2-D tiles
-    if (a->loc_x && row_len > 1 && chunk < a->npix && chunk >= row_len) chunk = chunk / row_len * row_len;
+    if (a->loc_x && row_len > 1 && pb % row_len == 0 && chunk < band && chunk >= row_len) chunk = chunk / row_len * row_len;
 
     DevBuf d_ox, d_oy, d_oz, d_cnt;
     RF_TRY(d_ox.alloc(sizeof(double) * std::max(S, 1)));
@@ -1806,7 +1823,7 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
         int64_t cand_chunk = -1;
         Stream st;  // last member: destroyed (and synchronised) before the buffers above
     } slot[2];
-    const int nslots = (a->npix <= chunk && D <= db) ? 1 : 2;
+    const int nslots = (band <= chunk && D <= db) ? 1 : 2;
     for (int s = 0; s < nslots; ++s) {
         RF_TRY(slot[s].st.create());
         RF_TRY(slot[s].ws.alloc(pl.total));
@@ -1825,8 +1842,8 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
     RF_TRY(pool_ready());
     tr.mark("setup (alloc + stations)");
     int si = 0;
-    for (int64_t p0 = 0; p0 < a->npix; p0 += chunk) {
-        const int64_t cur = std::min(chunk, a->npix - p0);
+    for (int64_t p0 = pb; p0 < pe; p0 += chunk) {
+        const int64_t cur = std::min(chunk, pe - p0);
         for (int d0 = 0; d0 < D; d0 += db, si = (si + 1) % nslots) {
             const int nd = std::min(db, D - d0);
             Slot& sl = slot[si];
@@ -1943,4 +1960,48 @@ extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_
         return RFSI_W_TOO_FEW_OBS;
     }
     return RFSI_OK;
+}
+
+}  // namespace
+
+extern "C" int rfsi_predict_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device)
+{
+    RF_TRY(validate_fused_host(f, a));
+    RF_TRY(use_device(device));
+    return host_fused(f, a, device, 0, a->npix);
+}
+
+// north_star (c): the raster cut into one band of pixels per GPU, no collective on the compute
+// path.  One host thread per band drives its device through host_fused() and its D2H copies land
+// straight in the caller's arrays ("device-side gather to host" = ndevices independent streams).
+extern "C" int rfsi_predict_fused_multi(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const int* devices,
+                                        int ndevices)
+{
+    RF_TRY(validate_fused_host(f, a));
+    if (!devices || ndevices < 1 || ndevices > 64) return fail(RFSI_E_ARG, "fused_multi: needs 1..64 devices");
+    for (int g = 0; g < ndevices; ++g) RF_TRY(use_device(devices[g]));
+    if (ndevices == 1 || a->npix == 0) return host_fused(f, a, devices[0], 0, a->npix);
+    // bands of whole raster rows where the locations are raster cells (keeps the 2-D pixel tiles)
+    int64_t unit = 1;
+    if (!a->loc_x && a->pix_begin % a->grid_ncol == 0) unit = a->grid_ncol;
+    else if (a->loc_x && explicit_row_len(a) > 1) unit = explicit_row_len(a);
+    const int64_t units = (a->npix + unit - 1) / unit;
+    std::vector<int64_t> cut((size_t)ndevices + 1);
+    for (int g = 0; g <= ndevices; ++g) cut[(size_t)g] = std::min<int64_t>(a->npix, units * g / ndevices * unit);
+    cut[(size_t)ndevices] = a->npix;
+    std::vector<int> rc((size_t)ndevices, RFSI_OK);
+    std::vector<std::string> msg((size_t)ndevices);
+    std::vector<std::thread> th;
+    for (int g = 0; g < ndevices; ++g)
+        th.emplace_back([&, g] {
+            rc[(size_t)g] = host_fused(f, a, devices[g], cut[(size_t)g], cut[(size_t)g + 1]);
+            if (rc[(size_t)g] != RFSI_OK) msg[(size_t)g] = g_err;   // g_err is thread-local
+        });
+    for (auto& t : th) t.join();
+    int worst = RFSI_OK, who = -1;   // the first error, else the first warning
+    for (int g = 0; g < ndevices; ++g)
+        if (rc[(size_t)g] < 0 && worst >= 0) { worst = rc[(size_t)g]; who = g; }
+        else if (rc[(size_t)g] > 0 && worst == RFSI_OK) { worst = rc[(size_t)g]; who = g; }
+    if (who >= 0) g_err = msg[(size_t)who];
+    return worst;
 }

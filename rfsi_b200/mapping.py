@@ -110,12 +110,13 @@ class MapResult:
 def predict_maps(model: RangerForest, grid: PredictionGrid, obs_xy, obs_z, day_names: Sequence[str], n_obs: int,
                  covariates: Dict[str, Union[CovariateFiles, np.ndarray]], cov_fix: Sequence = (),
                  quantiles: Optional[Sequence[float]] = (0.25, 0.5, 0.75), out_dir=None, min_stations: int = 2,
-                 compression: str = "lzw", device: int = 0) -> MapResult:
+                 compression: str = "lzw", device: int = 0, devices: Optional[Sequence[int]] = None) -> MapResult:
     """The loop of 5_prcp_prediction.R:244-313 for all days at once.
 
     obs_xy (nobs, 2) in the near.obs CRS, obs_z (ndays, nobs) with NaN = no observation.
     covariates: name -> CovariateFiles (sampled on the device at the grid's raster coordinates)
     or an array (npix,) / (ndays, npix).  With out_dir, writes <day>.tif and <day>_iqr.tif.
+    devices: several GPUs of the box, one band of pixels each (the scripts' foreach %dopar%).
     """
     obs_z = np.atleast_2d(np.asarray(obs_z, dtype=np.float64))
     ndays = obs_z.shape[0]
@@ -134,7 +135,7 @@ def predict_maps(model: RangerForest, grid: PredictionGrid, obs_xy, obs_z, day_n
             cov[name] = v[use] if v.ndim == 2 else v
     res = api.predict_fused(model, obs_xy=obs_xy, obs_z=obs_z[use], n_obs=n_obs, locations=grid.xy,
                             cov_locations=None if grid.xy is grid.xy_raster else grid.xy_raster, covariates=cov,
-                            cov_fix=cov_fix, quantiles=quantiles, centi_int16=True, device=device)
+                            cov_fix=cov_fix, quantiles=quantiles, centi_int16=True, device=device, devices=devices)
     out = MapResult([day_names[i] for i in use], res["mean_i16"], res.get("iqr_i16"))
     if out_dir is not None:
         out_dir = Path(out_dir)

@@ -2,7 +2,9 @@
 """Scale run: half of the 10^4 x 10^4 C5 raster (5 x 10^7 pixels) x 4 days through the HOST API in one
 call -- covariates as per-day rasters sampled on the device, products as Int16 (what the mapping
 scripts write) -- with a sample checked against the CPU oracle.
-python tools/scale_run.py [rows] [days]"""
+python tools/scale_run.py [rows] [days] [ndevices] [trees]
+With ndevices > 1 the same call is repeated with devices=0..ndevices-1 (rfsi_predict_fused_multi:
+one band of rows per GPU inside ONE process) and must return the same bits."""
 import sys, time
 from pathlib import Path
 import numpy as np
@@ -14,6 +16,8 @@ from rfsi_b200 import grow, synth
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+NDEV = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+TREES = int(sys.argv[4]) if len(sys.argv) > 4 else 500
 case = synth.make_case("c5", ndays=20)
 rng = np.random.default_rng(0)
 # covariates: coarse daily rasters (1000 x 1000 cells of 10 x 10 pixels), Int16 tenths
@@ -30,7 +34,7 @@ def gpu_no(l, o, z, n):
     a = rb.near_obs(l, np.column_stack([o, z]), zcol=2, n_obs=n).to_numpy()
     return a[:, :n], a[:, n:]
 X, y = synth.training_table(case, gpu_no)
-t0 = time.time(); flat = grow.grow_forest(X, y, case.feature_names, num_trees=500); print(f"grew 500 trees in {time.time()-t0:.1f}s", file=sys.stderr)
+t0 = time.time(); flat = grow.grow_forest(X, y, case.feature_names, num_trees=TREES); print(f"grew {TREES} trees in {time.time()-t0:.1f}s", file=sys.stderr)
 model = rb.RangerForest(flat); model.upload(0)
 npix = rows * case.ncol
 kw = dict(obs_xy=case.obs_xy, obs_z=case.obs_z[:D], n_obs=case.n_obs, grid=case.grid, npix=npix, covariates=R)
@@ -47,3 +51,13 @@ ref = oracle.predict_fused(flat.as_dict(), case.feature_names, loc_xy=loc, obs_x
 assert np.array_equal(out["mean"][:, sel], ref["mean"]), "sample differs from the oracle"
 assert np.array_equal(out["mean_i16"][:, sel].ravel(), oracle.centi_int16(ref["mean"].ravel()))
 print("  sample of 2000 pixels x all days: bit-equal to the CPU oracle (fp64 mean and Int16 product)")
+if NDEV > 1:
+    devs = list(range(min(NDEV, rb.device_count()))) if rb.device_count() > 1 else [0] * NDEV
+    for d in set(devs):
+        model.upload(d)
+    rb.predict_fused(model, **{**kw, "npix": 20 * case.ncol * len(devs)}, centi_int16=True, devices=devs)   # warm-up: contexts, pools
+    t0 = time.perf_counter()
+    multi = rb.predict_fused(model, centi_int16=True, devices=devs, **kw)
+    dtm = time.perf_counter() - t0
+    assert all(np.array_equal(out[k], multi[k]) for k in out), "banded result differs from the single-device call"
+    print(f"devices={devs} in ONE process: {dtm:.2f} s = {npix*D/dtm/1e6:.1f} M pixel-days/s ({dt/dtm:.2f}x the single-device call), bit-equal")
