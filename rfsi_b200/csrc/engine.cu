@@ -199,7 +199,9 @@ struct rfsi_forest {
     std::vector<int32_t> leaf_rid_c;
     struct Image {
         Node* nodes = nullptr;
-        double* leaf_sample = nullptr;
+        double* leaf_sample = nullptr;     // per-leaf samples (fp64 form of the quantile kernel), or
+        uint32_t* leaf_rank = nullptr;     // their ranks in sample_dict (default form, NA = 0xFFFFFFFF)
+        double* sample_dict = nullptr;     // sorted distinct sample values
         int32_t* leaf_rid = nullptr;
         bool compact = false;
         bool blocked = false;
@@ -210,6 +212,45 @@ struct rfsi_forest {
 };
 
 namespace {
+
+// bytes per leaf of the quantile sample table: dictionary ranks (default) or the fp64 samples
+inline size_t sample_entry_bytes() { return env_int("RFSI_B200_QRF_RANKS", 1) != 0 ? sizeof(uint32_t) : sizeof(double); }
+
+// order-preserving integer key of a double's bit pattern (a total order: -0.0 < +0.0)
+inline uint64_t sample_key(double x) {
+    int64_t b;
+    memcpy(&b, &x, 8);
+    return (uint64_t)(b ^ ((b >> 63) | (int64_t)0x8000000000000000LL));
+}
+
+// dict = the distinct non-NA samples in ascending order; rank[i] = position of ls[i] in dict
+// (0xFFFFFFFF for NA: ranger leaves cells of random.node.values unset)
+void sample_ranks(const std::vector<double>& ls, std::vector<double>& dict, std::vector<uint32_t>& rank) {
+    std::vector<uint64_t> keys;
+    keys.reserve(ls.size());
+    for (double x : ls) if (x == x) keys.push_back(sample_key(x));
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    dict.resize(keys.size());
+    for (size_t i = 0; i < keys.size(); ++i) {
+        const int64_t b = (int64_t)keys[i];
+        const int64_t bits = b ^ ((~b >> 63) | (int64_t)0x8000000000000000LL);
+        memcpy(&dict[i], &bits, 8);
+    }
+    rank.resize(ls.size());
+    const size_t n = ls.size();
+    const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&, t] {
+            for (size_t i = n * t / nt; i < n * (t + 1) / nt; ++i) {
+                const double x = ls[i];
+                rank[i] = (x == x) ? (uint32_t)(std::lower_bound(keys.begin(), keys.end(), sample_key(x)) - keys.begin())
+                                   : 0xFFFFFFFFu;
+            }
+        });
+    for (auto& x : th) x.join();
+}
 
 int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
     std::lock_guard<std::mutex> lk(f->mu);
@@ -249,8 +290,21 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
     }
     if (!f->leaf_sample.empty()) {
         const std::vector<double>& ls = blocked ? f->leaf_sample_c : f->leaf_sample;
-        CU_TRY(cudaMalloc(&im.leaf_sample, ls.size() * sizeof(double)));
-        CU_TRY(cudaMemcpy(im.leaf_sample, ls.data(), ls.size() * sizeof(double), cudaMemcpyHostToDevice));
+        if (env_int("RFSI_B200_QRF_RANKS", 1) != 0 && ls.size() < 0xFFFFFFFFull) {
+            // 4-byte form: the distinct sample values (at most one per training row) sorted in
+            // the total order of their bit patterns (-0.0 < +0.0 stay distinct entries, so the
+            // values that come back are the very doubles ranger stored), and each leaf's rank
+            std::vector<double> dict;
+            std::vector<uint32_t> rank;
+            sample_ranks(ls, dict, rank);
+            CU_TRY(cudaMalloc(&im.leaf_rank, std::max<size_t>(rank.size(), 1) * sizeof(uint32_t)));
+            CU_TRY(cudaMemcpy(im.leaf_rank, rank.data(), rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CU_TRY(cudaMalloc(&im.sample_dict, std::max<size_t>(dict.size(), 1) * sizeof(double)));
+            CU_TRY(cudaMemcpy(im.sample_dict, dict.data(), dict.size() * sizeof(double), cudaMemcpyHostToDevice));
+        } else {
+            CU_TRY(cudaMalloc(&im.leaf_sample, ls.size() * sizeof(double)));
+            CU_TRY(cudaMemcpy(im.leaf_sample, ls.data(), ls.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
     }
     f->images[device] = im;
     *out = im;
@@ -530,6 +584,8 @@ extern "C" void rfsi_forest_destroy(rfsi_forest_t* f) {
         if (cudaSetDevice(kv.first) == cudaSuccess) {
             if (kv.second.nodes) cudaFree(kv.second.nodes);
             if (kv.second.leaf_sample) cudaFree(kv.second.leaf_sample);
+            if (kv.second.leaf_rank) cudaFree(kv.second.leaf_rank);
+            if (kv.second.sample_dict) cudaFree(kv.second.sample_dict);
             if (kv.second.leaf_rid) cudaFree(kv.second.leaf_rid);
             cudaFree(const_cast<uint2*>(kv.second.q.nodes)); cudaFree(const_cast<QRoot*>(kv.second.q.roots));
             cudaFree(const_cast<double*>(kv.second.q.leaf_val)); cudaFree(const_cast<double*>(kv.second.q.uvals));
@@ -560,11 +616,11 @@ extern "C" int64_t rfsi_forest_info(const rfsi_forest_t* f, int what) {
         case 5:
             if (f->compact_ok && f->blocked_ok && env_int("RFSI_B200_COMPACT", 2) >= 2)
                 return (int64_t)(f->blocks.size() * 4 + f->leaf_val_c.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
-                                 f->leaf_sample_c.size() * sizeof(double));
+                                 f->leaf_sample_c.size() * sample_entry_bytes());
             if (f->compact_ok && env_int("RFSI_B200_COMPACT", 2) != 0)
                 return (int64_t)(f->qnodes.size() * 8 + f->leaf_val.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
-                                 f->qroots.size() * sizeof(QRoot) + f->leaf_sample.size() * sizeof(double));
-            return (int64_t)(f->nodes.size() * sizeof(Node) + f->leaf_sample.size() * sizeof(double));
+                                 f->qroots.size() * sizeof(QRoot) + f->leaf_sample.size() * sample_entry_bytes());
+            return (int64_t)(f->nodes.size() * sizeof(Node) + f->leaf_sample.size() * sample_entry_bytes());
         case 6: return f->n_internal;
         case 7: return !(f->compact_ok && env_int("RFSI_B200_COMPACT", 2) != 0) ? 0
                        : ((f->blocked_ok && env_int("RFSI_B200_COMPACT", 2) >= 2) ? 2 : 1);
@@ -869,12 +925,13 @@ constexpr int kMaxProbs = 128;
 inline int64_t leaf_ids_ld(int T) { return ((int64_t)T + 7) & ~int64_t(7); }
 inline size_t leaf_ids_bytes(int64_t rows, int T) { return sizeof(uint32_t) * (size_t)rows * (size_t)leaf_ids_ld(T); }
 
-template <int R>
-int launch_qrf_r(const uint32_t* leaf_ids, const double* leaf_sample, const unsigned char* skip, int64_t nrows, int T,
-                 const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr, cudaStream_t stream)
+template <int R, class K>
+int launch_qrf_r(const uint32_t* leaf_ids, const K* leaf_key, const double* dict, const unsigned char* skip, int64_t nrows,
+                 int T, const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr,
+                 cudaStream_t stream)
 {
-    auto kern = qrf_quantile_kernel<R>;
-    const size_t smem = qrf_smem_bytes<R>();
+    auto kern = qrf_quantile_kernel<R, K>;
+    const size_t smem = qrf_smem_bytes<R, K>();
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, per_sm = 0;
     CU_TRY(cudaGetDevice(&dev));
@@ -883,19 +940,33 @@ int launch_qrf_r(const uint32_t* leaf_ids, const double* leaf_sample, const unsi
     // persistent warps: one resident wave, each warp strides over the rows
     const int64_t want = (nrows + kQrfWarps - 1) / kQrfWarps;
     const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * std::max(per_sm, 1));
-    kern<<<grid, 32 * kQrfWarps, smem, stream>>>(leaf_ids, leaf_ids_ld(T), leaf_sample, skip, nrows, T, probs_dev, nprobs,
+    kern<<<grid, 32 * kQrfWarps, smem, stream>>>(leaf_ids, leaf_ids_ld(T), leaf_key, dict, skip, nrows, T, probs_dev, nprobs,
                                                  out_q, ld_q, out_iqr);
     return RFSI_OK;
 }
 
-int launch_qrf(const uint32_t* leaf_ids, const double* leaf_sample, const unsigned char* skip, int64_t nrows, int T,
+// the leaf table of an image in whichever form it was uploaded (ranks by default)
+struct LeafSamples {
+    const double* sample = nullptr;
+    const uint32_t* rank = nullptr;
+    const double* dict = nullptr;
+    explicit operator bool() const { return sample || rank; }
+};
+inline LeafSamples leaf_samples(const rfsi_forest::Image& im) { return LeafSamples{im.leaf_sample, im.leaf_rank, im.sample_dict}; }
+
+int launch_qrf(const uint32_t* leaf_ids, const LeafSamples& ls, const unsigned char* skip, int64_t nrows, int T,
                const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr, cudaStream_t stream)
 {
     if (nrows == 0) return RFSI_OK;
     const int R = (T + 31) / 32;
     ProfScope ps(PROF_QRF, stream);
-#define RFSI_QRF_CASE(RR) \
-    RF_TRY(launch_qrf_r<RR>(leaf_ids, leaf_sample, skip, nrows, T, probs_dev, nprobs, out_q, ld_q, out_iqr, stream))
+#define RFSI_QRF_CASE(RR)                                                                                              \
+    do {                                                                                                               \
+        if (ls.rank) RF_TRY((launch_qrf_r<RR, uint32_t>(leaf_ids, ls.rank, ls.dict, skip, nrows, T, probs_dev, nprobs,  \
+                                                         out_q, ld_q, out_iqr, stream)));                              \
+        else RF_TRY((launch_qrf_r<RR, double>(leaf_ids, ls.sample, nullptr, skip, nrows, T, probs_dev, nprobs, out_q,   \
+                                              ld_q, out_iqr, stream)));                                                \
+    } while (0)
     if (R <= 1) RFSI_QRF_CASE(1);
     else if (R <= 2) RFSI_QRF_CASE(2);
     else if (R <= 4) RFSI_QRF_CASE(4);
@@ -1261,7 +1332,7 @@ extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, 
     if (out_terminal) RF_TRY(forest_leaf_rid(f, device, &o.leaf_rid));
     double* probs_dev = nullptr;
     if (out_q) {
-        if (!im.leaf_sample) return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
+        if (!leaf_samples(im)) return fail(RFSI_E_ARG, "quantiles need a forest imported with random.node.values (quantreg=TRUE)");
         if (f->ntrees > 1024) return fail(RFSI_E_ARG, "quantile forests with more than 1024 trees are not supported (T=%d)", f->ntrees);
         RF_TRY(check_probs(probs_host, nprobs));
         if (!scratch) return fail(RFSI_E_ARG, "quantiles need a scratch buffer");
@@ -1271,7 +1342,7 @@ extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, 
         CU_TRY(cudaMemcpyAsync(probs_dev, probs_host, sizeof(double) * nprobs, cudaMemcpyHostToDevice, st));
     }
     RF_TRY(launch_forest_x(f, im, X, npix, ldx, o, visits, na_flag, st));
-    if (out_q) RF_TRY(launch_qrf(o.leaf_ids, im.leaf_sample, nullptr, npix, f->ntrees, probs_dev, nprobs, out_q, npix, nullptr, st));
+    if (out_q) RF_TRY(launch_qrf(o.leaf_ids, leaf_samples(im), nullptr, npix, f->ntrees, probs_dev, nprobs, out_q, npix, nullptr, st));
     return RFSI_OK;
 }
 
@@ -1695,7 +1766,7 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         if (pl.want_q) {
             double* oq = a->out_q ? a->out_q + obase : nullptr;
             // q[(j*ndays + d)*npix + p]: column stride between quantiles is ndays*npix
-            RF_TRY(launch_qrf(leaf_ids, im.leaf_sample, skip, rows, f->ntrees, probs_dev, a->nprobs, oq, (int64_t)a->ndays * a->npix,
+            RF_TRY(launch_qrf(leaf_ids, leaf_samples(im), skip, rows, f->ntrees, probs_dev, a->nprobs, oq, (int64_t)a->ndays * a->npix,
                               a->out_iqr_i16 ? a->out_iqr_i16 + obase : nullptr, st));
         }
     }

@@ -42,20 +42,28 @@ constexpr int kQrfWarps = 8;        // rows in flight per CTA
 #endif
 template <int R> constexpr int qrf_min_blocks() { return R >= 32 ? 1 : QRF_MIN_BLOCKS; }
 
+// The kernel exists for two key types K.  double: the leaf table holds the samples themselves
+// (8 B per leaf).  uint32_t: the table holds each sample's RANK in the forest-wide sorted
+// dictionary of distinct sample values (4 B per leaf; the dictionary -- at most one entry per
+// training row -- stays in L2); ranks order exactly like the values, so the selection runs on
+// integers and only the two order statistics of a quantile are looked up as fp64.  Half the
+// bytes per gather and twice the leaves per 32-byte sector for neighbouring pixels to share.
+
 // shared memory of one warp, in bytes: samples of the current row, two histograms, the
 // compaction buffer, the id buffer of the row after next
-template <int R>
+template <int R, class K>
 __host__ __device__ constexpr size_t qrf_warp_smem() {
-    return (size_t)R * 32 * 8 + 256 * 4 + 256 * 4 + 32 * 8 + (size_t)R * 32 * 4;
+    return (size_t)R * 32 * sizeof(K) + 256 * 4 + 256 * 4 + 32 * sizeof(K) + (size_t)R * 32 * 4;
 }
-template <int R>
-__host__ __device__ constexpr size_t qrf_smem_bytes() { return kQrfWarps * qrf_warp_smem<R>(); }
+template <int R, class K>
+__host__ __device__ constexpr size_t qrf_smem_bytes() { return kQrfWarps * qrf_warp_smem<R, K>(); }
 
+template <class K>
 struct QrfWarp {
-    double* sv;      // [R*32] samples of the row, element r of lane l at r*32 + l
+    K* sv;           // [R*32] samples of the row, element r of lane l at r*32 + l
     int* hist0;      // [256]
     int* hist1;      // [256]
-    double* mem;     // [32]
+    K* mem;          // [32]
     uint32_t* ids;   // [R*32]
 };
 
@@ -83,25 +91,62 @@ __device__ __forceinline__ double qrf_warp_max(double x) {
     return qrf_unkey(((unsigned long long)hi << 32) | lo);
 }
 
-// Monotone bucket of x in [lo, hi].  Halved operands keep hi - lo finite for any finite
-// inputs; the maximum always lands in bucket 255 and the minimum in bucket 0, so a bucket
-// that is re-bucketed between its own min and max always loses members (termination).
-__device__ __forceinline__ int qrf_bucket(double x, double lo_half, double hi, double scale) {
-    const double t = (x * 0.5 - lo_half) * scale;   // x >= lo, so t >= 0; NaN never reaches here
-    const int b = (t >= 255.0) ? 255 : (int)t;
-    return (x == hi) ? 255 : b;
-}
+// Key traits.  bucket() is monotone non-decreasing in x on [lo, hi]; the maximum always lands in
+// bucket 255 and the minimum in bucket 0, so a bucket that is re-bucketed between its own min and
+// max always loses members (termination).
+template <class K> struct QrfKey;
+
+template <> struct QrfKey<double> {
+    struct Scale { double lo_half, scale; };
+    static __device__ __forceinline__ double na() { return na_real(); }
+    static __device__ __forceinline__ bool ok(double x) { return x == x; }                      // na.rm = TRUE
+    static __device__ __forceinline__ double top() { return __longlong_as_double(0x7FF0000000000000LL); }
+    static __device__ __forceinline__ double bottom() { return __longlong_as_double(0xFFF0000000000000LL); }
+    static __device__ __forceinline__ double warp_min(double x) { return qrf_warp_min(x); }
+    static __device__ __forceinline__ double warp_max(double x) { return qrf_warp_max(x); }
+    // halved operands keep hi - lo finite for any finite inputs
+    static __device__ __forceinline__ Scale make_scale(double lo, double hi) {
+        Scale s{lo * 0.5, 0.0};
+        s.scale = 256.0 / (hi * 0.5 - s.lo_half);
+        if (!(s.scale < 1.0e300)) s.scale = 1.0e300;   // hi - lo tiny: keep the product finite and monotone
+        return s;
+    }
+    static __device__ __forceinline__ int bucket(double x, double hi, const Scale& s) {
+        const double t = (x * 0.5 - s.lo_half) * s.scale;   // x >= lo, so t >= 0; NaN never reaches here
+        const int b = (t >= 255.0) ? 255 : (int)t;
+        return (x == hi) ? 255 : b;
+    }
+    static __device__ __forceinline__ double value(double k, const double*) { return k; }
+};
+
+template <> struct QrfKey<uint32_t> {
+    struct Scale { uint32_t lo; float scale; };
+    static __device__ __forceinline__ uint32_t na() { return 0xFFFFFFFFu; }
+    static __device__ __forceinline__ bool ok(uint32_t x) { return x != 0xFFFFFFFFu; }
+    static __device__ __forceinline__ uint32_t top() { return 0xFFFFFFFFu; }
+    static __device__ __forceinline__ uint32_t bottom() { return 0u; }
+    static __device__ __forceinline__ uint32_t warp_min(uint32_t x) { return __reduce_min_sync(0xffffffffu, x); }
+    static __device__ __forceinline__ uint32_t warp_max(uint32_t x) { return __reduce_max_sync(0xffffffffu, x); }
+    static __device__ __forceinline__ Scale make_scale(uint32_t lo, uint32_t hi) {
+        return Scale{lo, 256.0f / (float)(hi - lo)};     // only called with lo < hi
+    }
+    // integer -> float conversion, multiplication by a positive constant and truncation are all monotone
+    static __device__ __forceinline__ int bucket(uint32_t x, uint32_t hi, const Scale& s) {
+        const float t = (float)(x - s.lo) * s.scale;
+        const int b = (t >= 255.0f) ? 255 : (int)t;
+        return (x == hi) ? 255 : b;
+    }
+    static __device__ __forceinline__ double value(uint32_t k, const double* dict) { return __ldg(dict + k); }
+};
 
 // Histogram of the members (bit r of `members` set <=> sample r of this lane takes part)
 // between lo and hi; bp packs the bucket of element r into byte r&3 of word r>>2; returns this
 // lane's 8-bin sum and exclusive prefix.
-template <int R>
-__device__ __forceinline__ void qrf_hist(const double* sv, unsigned members, double lo, double hi, int* hist, int lane,
+template <int R, class K>
+__device__ __forceinline__ void qrf_hist(const K* sv, unsigned members, K lo, K hi, int* hist, int lane,
                                          uint32_t (&bp)[(R + 3) / 4], int& lane_sum, int& lane_excl)
 {
-    const double lo_half = lo * 0.5;
-    double scale = 256.0 / (hi * 0.5 - lo_half);
-    if (!(scale < 1.0e300)) scale = 1.0e300;          // hi - lo tiny: keep the product finite and monotone
+    const typename QrfKey<K>::Scale sc = QrfKey<K>::make_scale(lo, hi);
     reinterpret_cast<int4*>(hist)[lane * 2] = make_int4(0, 0, 0, 0);
     reinterpret_cast<int4*>(hist)[lane * 2 + 1] = make_int4(0, 0, 0, 0);
     __syncwarp();
@@ -110,8 +155,8 @@ __device__ __forceinline__ void qrf_hist(const double* sv, unsigned members, dou
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const bool is = (members >> r) & 1u;
-        const double x = is ? sv[r * 32 + lane] : lo;
-        const int b = qrf_bucket(x, lo_half, hi, scale);
+        const K x = is ? sv[r * 32 + lane] : lo;
+        const int b = QrfKey<K>::bucket(x, hi, sc);
         if (is) atomicAdd(&hist[b], 1);
         bp[r >> 2] |= (uint32_t)b << (8 * (r & 3));
     }
@@ -169,9 +214,9 @@ __device__ __forceinline__ unsigned qrf_match(const uint32_t (&bp)[(R + 3) / 4],
 // k-th smallest (0-based) of the valid samples, given the level-0 histogram.  *next receives the
 // (k+1)-th smallest as well when it sits in the same final bucket (the usual case for the
 // lo/hi pair of one quantile), and *has_next says so.
-template <int R>
-__device__ __forceinline__ double qrf_select(const QrfWarp& s, unsigned valid, const uint32_t (&b0)[(R + 3) / 4],
-                                             int sum0, int excl0, int lane, int k, double* next, bool* has_next)
+template <int R, class K>
+__device__ __forceinline__ K qrf_select(const QrfWarp<K>& s, unsigned valid, const uint32_t (&b0)[(R + 3) / 4],
+                                        int sum0, int excl0, int lane, int k, K* next, bool* has_next)
 {
     *has_next = false;
     int B, before, cnt;
@@ -180,19 +225,19 @@ __device__ __forceinline__ double qrf_select(const QrfWarp& s, unsigned valid, c
     unsigned mm = qrf_match<R>(b0, B) & valid;
 
     while (cnt > 32) {   // heavy bucket: re-bucket between its own min and max
-        double lo = __longlong_as_double(0x7FF0000000000000LL), hi = __longlong_as_double(0xFFF0000000000000LL);
+        K lo = QrfKey<K>::top(), hi = QrfKey<K>::bottom();
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (mm & (1u << r)) { const double x = s.sv[r * 32 + lane]; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
-        lo = qrf_warp_min(lo);
-        hi = qrf_warp_max(hi);
+            if (mm & (1u << r)) { const K x = s.sv[r * 32 + lane]; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+        lo = QrfKey<K>::warp_min(lo);
+        hi = QrfKey<K>::warp_max(hi);
         if (lo == hi) {            // all members equal
             if (kk + 1 < cnt) { *next = lo; *has_next = true; }
             return lo;
         }
         uint32_t b1[(R + 3) / 4];
         int s1, e1;
-        qrf_hist<R>(s.sv, mm, lo, hi, s.hist1, lane, b1, s1, e1);
+        qrf_hist<R, K>(s.sv, mm, lo, hi, s.hist1, lane, b1, s1, e1);
         qrf_locate(s.hist1, lane, s1, e1, kk, B, before, cnt);
         kk -= before;
         mm &= qrf_match<R>(b1, B);
@@ -212,15 +257,15 @@ __device__ __forceinline__ double qrf_select(const QrfWarp& s, unsigned valid, c
         pos += __popc(bal);
     }
     __syncwarp();
-    const double mine = (lane < cnt) ? s.mem[lane] : 0.0;
+    const K mine = (lane < cnt) ? s.mem[lane] : K(0);
     int rk = 0;
 #pragma unroll 4
     for (int j = 0; j < cnt; ++j) {
-        const double other = s.mem[j];
+        const K other = s.mem[j];
         rk += (other < mine || (other == mine && j < lane)) ? 1 : 0;
     }
     const unsigned hit = __ballot_sync(0xffffffffu, lane < cnt && rk == kk);
-    const double out = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
+    const K out = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
     if (kk + 1 < cnt) {
         const unsigned hit2 = __ballot_sync(0xffffffffu, lane < cnt && rk == kk + 1);
         *next = __shfl_sync(0xffffffffu, mine, __ffs(hit2) - 1);
@@ -236,26 +281,28 @@ __device__ __forceinline__ void qrf_cp_async16(void* smem_dst, const void* gsrc)
 }
 
 // leaf_ids: [nrows][ld_ids] pixel-major leaf index per tree (written by the forest walk);
-// leaf_sample: the forest's per-leaf sample table; skip (nullable): rows whose outputs are NA
-// (their ids were never written).
+// leaf_key: the forest's per-leaf table (samples, or their dictionary ranks with NA = 0xFFFFFFFF);
+// dict: the sorted distinct sample values (rank form only); skip (nullable): rows whose outputs
+// are NA (their ids were never written).
 // out_q[j*ld_q + row] for j < nprobs (nullable); out_iqr_i16[row] (nullable) =
 // round-half-even((q[nprobs-1]-q[0])/2*100), NA -> -32767.
-template <int R>
+template <int R, class K>
 __global__ void __launch_bounds__(32 * kQrfWarps, qrf_min_blocks<R>())
-qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, const double* __restrict__ leaf_sample,
-                    const unsigned char* __restrict__ skip, long long nrows, int T,
+qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, const K* __restrict__ leaf_key,
+                    const double* __restrict__ dict, const unsigned char* __restrict__ skip, long long nrows, int T,
                     const double* __restrict__ probs, int nprobs,
                     double* __restrict__ out_q, long long ld_q, int16_t* __restrict__ out_iqr_i16)
 {
     extern __shared__ __align__(16) unsigned char qrf_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    QrfWarp s;
+    using KT = QrfKey<K>;
+    QrfWarp<K> s;
     {
-        unsigned char* base = qrf_smem + (size_t)wib * qrf_warp_smem<R>();
-        s.sv = reinterpret_cast<double*>(base);               base += (size_t)R * 32 * 8;
+        unsigned char* base = qrf_smem + (size_t)wib * qrf_warp_smem<R, K>();
+        s.sv = reinterpret_cast<K*>(base);                    base += (size_t)R * 32 * sizeof(K);
         s.hist0 = reinterpret_cast<int*>(base);               base += 256 * 4;
         s.hist1 = reinterpret_cast<int*>(base);               base += 256 * 4;
-        s.mem = reinterpret_cast<double*>(base);              base += 32 * 8;
+        s.mem = reinterpret_cast<K*>(base);                   base += 32 * sizeof(K);
         s.ids = reinterpret_cast<uint32_t*>(base);
     }
     // this CTA's contiguous run of rows; its warps take them kQrfWarps at a time
@@ -278,12 +325,12 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
     };
-    double vn[R];                              // samples of the row about to be processed
+    K vn[R];                                   // samples of the row about to be processed
     auto gather = [&](long long rw, bool skipped) {   // s.ids -> vn (loads stay in flight)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int t = r * 32 + lane;
-            vn[r] = (rw < row_end && !skipped && t < T) ? __ldg(leaf_sample + s.ids[t]) : nan;
+            vn[r] = (rw < row_end && !skipped && t < T) ? __ldg(leaf_key + s.ids[t]) : KT::na();
         }
         __syncwarp();                          // every lane has read s.ids: it may be refilled
     };
@@ -298,12 +345,12 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
     for (; row < row_end; row += stride) {
         // ---- take this row's samples out of the registers ------------------------------
         unsigned valid = 0;
-        double mn = __longlong_as_double(0x7FF0000000000000LL), mx = __longlong_as_double(0xFFF0000000000000LL);
+        K mn = KT::top(), mx = KT::bottom();
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const double x = vn[r];
+            const K x = vn[r];
             s.sv[r * 32 + lane] = x;
-            if (x == x) { valid |= 1u << r; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }   // na.rm = TRUE
+            if (KT::ok(x)) { valid |= 1u << r; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }   // na.rm = TRUE
         }
         // ---- next row's gathers, the row after's ids ---------------------------------------
         ids_ready();                           // also publishes s.sv to the warp
@@ -312,12 +359,12 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
         skip_next = (skip && row + 2 * stride < row_end) ? skip[row + 2 * stride] != 0 : false;
 
         const int m = (int)__reduce_add_sync(0xffffffffu, (unsigned)__popc(valid));
-        mn = qrf_warp_min(mn);   // +inf / -inf when the row has no sample
-        mx = qrf_warp_max(mx);
+        mn = KT::warp_min(mn);   // top / bottom when the row has no sample
+        mx = KT::warp_max(mx);
 
         uint32_t b0[(R + 3) / 4];
         int sum0 = 0, excl0 = 0;
-        if (m > 0 && mn < mx) qrf_hist<R>(s.sv, valid, mn, mx, s.hist0, lane, b0, sum0, excl0);
+        if (m > 0 && mn < mx) qrf_hist<R, K>(s.sv, valid, mn, mx, s.hist0, lane, b0, sum0, excl0);
 
         double qfirst = 0.0, qlast = 0.0;
         for (int j = 0; j < nprobs; ++j) {
@@ -325,16 +372,18 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
             if (m == 0) {
                 q = nan;
             } else if (!(mn < mx)) {
-                q = mn;   // every sample equal
+                q = KT::value(mn, dict);   // every sample equal
             } else {
                 const double index = __dadd_rn(1.0, __dmul_rn((double)(m - 1), probs[j]));   // no FMA: R computes 1 + (n-1)*p in two roundings
                 const double lo = floor(index), hi = ceil(index);
-                double nxt = 0.0, unused = 0.0;
+                K nxt = K(0), unused = K(0);
                 bool has_nxt = false, unused_b = false;
-                const double xlo = qrf_select<R>(s, valid, b0, sum0, excl0, lane, (int)lo - 1, &nxt, &has_nxt);
-                const double xhi = (hi == lo) ? xlo
-                                   : (has_nxt ? nxt
-                                              : qrf_select<R>(s, valid, b0, sum0, excl0, lane, (int)hi - 1, &unused, &unused_b));
+                const K klo = qrf_select<R, K>(s, valid, b0, sum0, excl0, lane, (int)lo - 1, &nxt, &has_nxt);
+                const K khi = (hi == lo) ? klo
+                              : (has_nxt ? nxt
+                                         : qrf_select<R, K>(s, valid, b0, sum0, excl0, lane, (int)hi - 1, &unused, &unused_b));
+                const double xlo = KT::value(klo, dict);
+                const double xhi = (khi == klo) ? xlo : KT::value(khi, dict);
                 if (index > lo && xhi != xlo) {
                     const double h = index - lo;
                     q = __dadd_rn(__dmul_rn(1.0 - h, xlo), __dmul_rn(h, xhi));
