@@ -945,6 +945,26 @@ int launch_qrf_r(const uint32_t* leaf_ids, const K* leaf_key, const double* dict
     return RFSI_OK;
 }
 
+// strip form of the quantile kernel (qrf.cuh): rank keys, up to 512 trees
+template <int R>
+int launch_qrf_strip(const uint32_t* leaf_ids, const uint32_t* leaf_rank, const double* dict, const unsigned char* skip,
+                     int64_t nrows, int T, const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr,
+                     cudaStream_t stream)
+{
+    auto kern = qrf_quantile_strip_kernel<R>;
+    const size_t smem = qrf_strip_smem<R>();
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0, per_sm = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kStripRows, smem));
+    const int64_t groups = (nrows + kStripRows - 1) / kStripRows;   // persistent CTAs, a contiguous run of tiles each
+    const unsigned grid = (unsigned)std::min<int64_t>(groups, (int64_t)sms * std::max(per_sm, 1));
+    kern<<<grid, 32 * kStripRows, smem, stream>>>(leaf_ids, leaf_ids_ld(T), leaf_rank, dict, skip, nrows, T, probs_dev, nprobs,
+                                                  out_q, ld_q, out_iqr);
+    return RFSI_OK;
+}
+
 // the leaf table of an image in whichever form it was uploaded (ranks by default)
 struct LeafSamples {
     const double* sample = nullptr;
@@ -960,9 +980,13 @@ int launch_qrf(const uint32_t* leaf_ids, const LeafSamples& ls, const unsigned c
     if (nrows == 0) return RFSI_OK;
     const int R = (T + 31) / 32;
     ProfScope ps(PROF_QRF, stream);
+    static const int strip = env_int("RFSI_B200_QRF_STRIP", 1);
 #define RFSI_QRF_CASE(RR)                                                                                              \
     do {                                                                                                               \
-        if (ls.rank) RF_TRY((launch_qrf_r<RR, uint32_t>(leaf_ids, ls.rank, ls.dict, skip, nrows, T, probs_dev, nprobs,  \
+        if (ls.rank && strip && RR <= 16)                                                                              \
+            RF_TRY((launch_qrf_strip<(RR <= 16 ? RR : 16)>(leaf_ids, ls.rank, ls.dict, skip, nrows, T, probs_dev, nprobs, \
+                                                           out_q, ld_q, out_iqr, stream)));                            \
+        else if (ls.rank) RF_TRY((launch_qrf_r<RR, uint32_t>(leaf_ids, ls.rank, ls.dict, skip, nrows, T, probs_dev, nprobs,  \
                                                          out_q, ld_q, out_iqr, stream)));                              \
         else RF_TRY((launch_qrf_r<RR, double>(leaf_ids, ls.sample, nullptr, skip, nrows, T, probs_dev, nprobs, out_q,   \
                                               ld_q, out_iqr, stream)));                                                \
