@@ -127,6 +127,9 @@ struct rfsi_tiff {
 
 namespace {
 
+// [at, at + n) lies inside a file of `size` bytes (no wrap-around: BigTIFF offsets are 64-bit)
+inline bool in_file(uint64_t at, uint64_t n, uint64_t size) { return at <= size && n <= size - at; }
+
 template <class T>
 T rd(const rfsi_tiff& t, uint64_t at) {
     T v;
@@ -148,9 +151,9 @@ int parse_ifd(rfsi_tiff& t) {
         t.big = true; ifd = rd<uint64_t>(t, 8);
     } else return fail(RFSI_IO_E_FORMAT, "%s: magic %u is neither TIFF (42) nor BigTIFF (43)", t.path.c_str(), magic);
     const uint64_t esz = t.big ? 20 : 12, csz = t.big ? 8 : 2, inl = t.big ? 8 : 4;
-    if (ifd + csz > t.size) return fail(RFSI_IO_E_FORMAT, "%s: image directory beyond end of file", t.path.c_str());
+    if (!in_file(ifd, csz, t.size)) return fail(RFSI_IO_E_FORMAT, "%s: image directory beyond end of file", t.path.c_str());
     const uint64_t n = t.big ? rd<uint64_t>(t, ifd) : rd<uint16_t>(t, ifd);
-    if (n > 4096 || ifd + csz + n * esz > t.size)
+    if (n > 4096 || !in_file(ifd + csz, n * esz, t.size))
         return fail(RFSI_IO_E_FORMAT, "%s: image directory with %llu entries does not fit the file", t.path.c_str(),
                     (unsigned long long)n);
     for (uint64_t e = 0; e < n; ++e) {
@@ -158,10 +161,11 @@ int parse_ifd(rfsi_tiff& t) {
         const int id = rd<uint16_t>(t, at), type = rd<uint16_t>(t, at + 2);
         const uint64_t count = t.big ? rd<uint64_t>(t, at + 4) : rd<uint32_t>(t, at + 4);
         if (type < 1 || type > 18 || kTypeSize[type] == 0) continue;  // unknown field type: skip the entry
+        if (count > (uint64_t(1) << 32)) return fail(RFSI_IO_E_FORMAT, "%s: tag %d has an absurd count", t.path.c_str(), id);
         const uint64_t bytes = count * (uint64_t)kTypeSize[type];
         uint64_t where = at + (t.big ? 12 : 8);
         if (bytes > inl) where = t.big ? rd<uint64_t>(t, where) : rd<uint32_t>(t, where);
-        if (count > (uint64_t(1) << 32) || where + bytes > t.size)
+        if (!in_file(where, bytes, t.size))
             return fail(RFSI_IO_E_FORMAT, "%s: tag %d points outside the file", t.path.c_str(), id);
         Tag tg;
         tg.type = type; tg.count = count;
@@ -179,6 +183,8 @@ int derive(rfsi_tiff& t) {
     const char* p = t.path.c_str();
     t.W = (int64_t)t.int1(T_WIDTH, 0); t.H = (int64_t)t.int1(T_HEIGHT, 0);
     if (t.W < 1 || t.H < 1) return fail(RFSI_IO_E_FORMAT, "%s: missing ImageWidth / ImageLength", p);
+    if (t.W > (int64_t(1) << 31) || t.H > (int64_t(1) << 31) || (double)t.W * (double)t.H > 1.0e12)
+        return fail(RFSI_IO_E_UNSUPPORTED, "%s: %lld x %lld cells is beyond what this reader takes", p, (long long)t.W, (long long)t.H);
     t.spp = (int)t.int1(T_SPP, 1);
     if (t.spp < 1 || t.spp > 65535) return fail(RFSI_IO_E_FORMAT, "%s: SamplesPerPixel %d", p, t.spp);
     std::vector<uint64_t> v;
@@ -217,6 +223,7 @@ int derive(rfsi_tiff& t) {
     if (t.tiled) {
         t.tw = (int64_t)t.int1(T_TILE_W, 0); t.th = (int64_t)t.int1(T_TILE_H, 0);
         if (t.tw < 1 || t.th < 1) return fail(RFSI_IO_E_FORMAT, "%s: tiled file without TileWidth / TileLength", p);
+        if (t.tw > (1 << 20) || t.th > (1 << 20)) return fail(RFSI_IO_E_FORMAT, "%s: tile of %lld x %lld cells", p, (long long)t.tw, (long long)t.th);
         if (!t.ints(T_TILE_OFFSETS, t.off) || !t.ints(T_TILE_BYTES, t.cnt))
             return fail(RFSI_IO_E_FORMAT, "%s: tiled file without TileOffsets / TileByteCounts", p);
         expect = (uint64_t)((t.W + t.tw - 1) / t.tw) * (uint64_t)((t.H + t.th - 1) / t.th);
@@ -236,7 +243,11 @@ int derive(rfsi_tiff& t) {
         return fail(RFSI_IO_E_FORMAT, "%s: %zu chunk offsets / %zu byte counts, expected %llu", p, t.off.size(),
                     t.cnt.size(), (unsigned long long)expect);
     for (size_t i = 0; i < t.off.size(); ++i)
-        if (t.off[i] + t.cnt[i] > t.size) return fail(RFSI_IO_E_FORMAT, "%s: chunk %zu lies outside the file", p, i);
+        if (!in_file(t.off[i], t.cnt[i], t.size)) return fail(RFSI_IO_E_FORMAT, "%s: chunk %zu lies outside the file", p, i);
+    {   // one decoded chunk must be a sane allocation (rows x cols x samples x bytes)
+        const double chunk = (double)(t.tiled ? t.th : t.rps) * (double)(t.tiled ? t.tw : t.W) * (t.planar == 1 ? t.spp : 1) * (t.bits / 8.0);
+        if (chunk > 4.0e9) return fail(RFSI_IO_E_UNSUPPORTED, "%s: a single strip / tile of %.3g bytes", p, chunk);
+    }
 
     rfsi_tiff_info_t& I = t.info;
     I.ncol = t.W; I.nrow = t.H; I.nlayers = t.spp; I.dtype = dt; I.compression = t.comp; I.predictor = t.pred;
@@ -465,7 +476,12 @@ int run_threads(int threads, size_t njobs, const std::function<int(size_t, int)>
         for (;;) {
             const size_t j = next.fetch_add(1);
             if (j >= njobs || status.load() != RFSI_IO_OK) return;
-            const int rc = job(j, tid);
+            int rc;
+            try {
+                rc = job(j, tid);
+            } catch (const std::exception& e) {   // e.g. bad_alloc: never let it leave a worker thread
+                rc = fail(RFSI_IO_E_FORMAT, "job %zu: %s", j, e.what());
+            }
             if (rc != RFSI_IO_OK) { errs[(size_t)tid] = g_err; status.store(rc); return; }
         }
     };
@@ -495,10 +511,17 @@ extern "C" int rfsi_tiff_open(const char* path, rfsi_tiff_t** out) {
     void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     ::close(fd);
     if (m == MAP_FAILED) return fail(RFSI_IO_E_OPEN, "cannot map %s: %s", path, strerror(errno));
-    rfsi_tiff* t = new rfsi_tiff;
-    t->path = path; t->base = static_cast<const uint8_t*>(m); t->size = (size_t)sb.st_size;
-    int rc = parse_ifd(*t);
-    if (rc == RFSI_IO_OK) rc = derive(*t);
+    rfsi_tiff* t = new (std::nothrow) rfsi_tiff;
+    if (!t) { munmap(m, (size_t)sb.st_size); return fail(RFSI_IO_E_OPEN, "%s: out of memory", path); }
+    t->base = static_cast<const uint8_t*>(m); t->size = (size_t)sb.st_size;
+    int rc;
+    try {
+        t->path = path;
+        rc = parse_ifd(*t);
+        if (rc == RFSI_IO_OK) rc = derive(*t);
+    } catch (const std::exception& e) {   // no C++ exception may cross the C ABI
+        rc = fail(RFSI_IO_E_FORMAT, "%s: %s while parsing", path, e.what());
+    }
     if (rc != RFSI_IO_OK) { delete t; return rc; }
     *out = t;
     return RFSI_IO_OK;
@@ -521,7 +544,29 @@ extern "C" int64_t rfsi_tiff_tag(const rfsi_tiff_t* t, int32_t tag, int32_t* fie
     return (int64_t)g->count;
 }
 
+namespace {
+int tiff_read_impl(const rfsi_tiff_t* tp, void* out, size_t out_bytes, int threads);
+int tiff_write_impl(const char* path, const rfsi_tiff_write_args_t* a);
+}  // namespace
+
+// no C++ exception may cross the C ABI
 extern "C" int rfsi_tiff_read(const rfsi_tiff_t* tp, void* out, size_t out_bytes, int threads) {
+    try {
+        return tiff_read_impl(tp, out, out_bytes, threads);
+    } catch (const std::exception& e) {
+        return fail(RFSI_IO_E_FORMAT, "tiff_read: %s", e.what());
+    }
+}
+extern "C" int rfsi_tiff_write(const char* path, const rfsi_tiff_write_args_t* a) {
+    try {
+        return tiff_write_impl(path, a);
+    } catch (const std::exception& e) {
+        return fail(RFSI_IO_E_ARG, "tiff_write: %s", e.what());
+    }
+}
+
+namespace {
+int tiff_read_impl(const rfsi_tiff_t* tp, void* out, size_t out_bytes, int threads) {
     if (!tp || !out) return fail(RFSI_IO_E_ARG, "tiff_read: NULL argument");
     const rfsi_tiff& t = *tp;
     const int B = t.bits / 8;
@@ -560,6 +605,8 @@ extern "C" int rfsi_tiff_read(const rfsi_tiff_t* tp, void* out, size_t out_bytes
     });
 }
 
+}  // namespace
+
 // ---- writer --------------------------------------------------------------------------
 
 namespace {
@@ -580,9 +627,7 @@ OutTag make_tag(uint16_t id, uint16_t type, const std::vector<T>& v) {
 
 bool write_all(FILE* f, const void* p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
 
-}  // namespace
-
-extern "C" int rfsi_tiff_write(const char* path, const rfsi_tiff_write_args_t* a) {
+int tiff_write_impl(const char* path, const rfsi_tiff_write_args_t* a) {
     if (!path || !a) return fail(RFSI_IO_E_ARG, "tiff_write: NULL argument");
     if (a->struct_size != sizeof(rfsi_tiff_write_args_t))
         return fail(RFSI_IO_E_ARG, "tiff_write: struct_size %zu != %zu (header/library mismatch)", a->struct_size,
@@ -739,3 +784,5 @@ extern "C" int rfsi_tiff_write(const char* path, const rfsi_tiff_write_args_t* a
     if (!ok) return fail(RFSI_IO_E_OPEN, "short write to %s: %s", path, strerror(errno));
     return RFSI_IO_OK;
 }
+
+}  // namespace

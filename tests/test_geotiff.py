@@ -294,6 +294,52 @@ def test_errors(tmp_path):
     assert e.value.code == -1
 
 
+def test_reader_survives_mutated_files(tmp_path):
+    """A reader of files from disk must reject damage, not crash on it (tools/fuzz_geotiff.cpp is the
+    long-running ASan version of this; it found a 64-bit offset wrap-around in BigTIFF chunk checks)."""
+    rng = np.random.default_rng(7)
+    a = _data("int16", (2, 24, 40), 1)
+    seeds = [_build_tiff(a, **l) for l in (dict(), dict(be=True), dict(big=True), dict(tile=(16, 16)),
+                                           dict(chunky=True, compression=8, predictor=2),
+                                           dict(tile=(16, 16), compression=8, big=True, be=True))]
+    gt.write_geotiff(tmp_path / "lzw.tif", _data("int16", (50, 60), 3), 0, 50, 1, 1, nodata=-32767, epsg=4326)
+    seeds.append((tmp_path / "lzw.tif").read_bytes())
+    # the wrap-around case itself: a BigTIFF whose strip offset + byte count overflows 64 bits
+    big = bytearray(_build_tiff(_data("uint8", (1, 7, 8)), big=True))
+    ifd = struct.unpack_from("<Q", big, 8)[0]
+    n = struct.unpack_from("<Q", big, ifd)[0]
+    for e in range(n):
+        at = ifd + 8 + 20 * e
+        if struct.unpack_from("<H", big, at)[0] == 273:
+            struct.pack_into("<Q", big, at + 12, 0xFFFFFFFFFFFFFFF0)
+    (tmp_path / "wrap.tif").write_bytes(bytes(big))
+    with pytest.raises(gt.GeoTiffError):
+        gt.GeoTiff(tmp_path / "wrap.tif")
+    ok = bad = 0
+    p = tmp_path / "m.tif"
+    for base in seeds:
+        for _ in range(150):
+            v = bytearray(base)
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(0, len(v)))
+                if rng.random() < 0.5:      # aim at the directory
+                    ifd = struct.unpack_from(">I" if v[:2] == b"MM" else "<I", v, 4)[0]
+                    if ifd < len(v):
+                        pos = min(len(v) - 1, ifd + int(rng.integers(0, 300)))
+                v[pos] = int(rng.integers(0, 256))
+            if rng.random() < 0.1:
+                v = v[:int(rng.integers(1, len(v)))]
+            p.write_bytes(bytes(v))
+            try:
+                with gt.GeoTiff(p) as t:
+                    if t.info.ncol * t.info.nrow * t.info.nlayers < 10_000_000:
+                        t.read(threads=2)
+                ok += 1
+            except gt.GeoTiffError:
+                bad += 1
+    assert ok + bad == 150 * len(seeds) and bad > 100
+
+
 @pytest.mark.skipif(not Path("/root/reference/prcp_catalonia").exists(), reason="reference data not on this box")
 def test_reference_geotiffs_decode_to_the_golden_digests():
     gold = json.loads((GOLD / "geotiff_reference.json").read_text())
