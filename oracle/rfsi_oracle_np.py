@@ -113,3 +113,39 @@ def forest_quantiles(forest, X, probs):
         vals = np.array([rnv[int(roff[t]) + tn[r, t]] for t in range(tn.shape[1])])
         out[r] = quantile7(vals, probs)
     return out
+
+
+def raster_extract(data, x_ul, y_ul, dx, dy, nodata, xy, layer=0, scale=1.0, offset=0.0, divide=False):
+    """raster::extract(r, points), method "simple", plus the unit change the scripts apply to it
+    (prcp_catalonia/5_prcp_prediction.R:253-276: `extract(tmin, gg) / 10`).
+
+    The value of the cell each point falls in: col = floor((x - xmin)/xres), row counted from
+    the top, the right and bottom outer edges belong to the last column / row
+    (raster::cellFromXY); NA outside the raster and where the cell holds the NAvalue.
+    UNPINNED against the raster package (R cannot run here); the arithmetic is two IEEE
+    operations, `raw / scale` (or `raw * scale`) then `+ offset`."""
+    d = data if data.ndim == 3 else data[None]
+    nrow, ncol = d.shape[1:]
+    xy = np.asarray(xy, dtype=np.float64)
+    x, y = xy[:, 0], xy[:, 1]
+    inside = (x >= x_ul) & (x <= x_ul + ncol * dx) & (y <= y_ul) & (y >= y_ul - nrow * dy)
+    with np.errstate(invalid="ignore"):
+        c = np.clip(np.nan_to_num(np.minimum(np.floor((x - x_ul) / dx), ncol - 1)), 0, ncol - 1).astype(np.int64)
+        r = np.clip(np.nan_to_num(np.minimum(np.floor((y_ul - y) / dy), nrow - 1)), 0, nrow - 1).astype(np.int64)
+    raw = d[layer][r, c].astype(np.float64)
+    ok = inside & ~(raw == nodata) & ~np.isnan(raw)
+    out = np.full(len(x), NA_REAL)
+    out[ok] = (raw[ok] / scale if divide else raw[ok] * scale) + offset
+    return out
+
+
+def cov_fix(target, other, delta):
+    """`df$tmin <- ifelse(df$tmin > df$tmax, df$tmax-1, df$tmin)` (5_prcp_prediction.R:258):
+    NA where either side is NA (R's ifelse on an NA test)."""
+    target = np.asarray(target, dtype=np.float64)
+    other = np.asarray(other, dtype=np.float64)
+    na = np.isnan(target) | np.isnan(other)
+    with np.errstate(invalid="ignore"):
+        out = np.where(target > other, other - delta, target)
+    out[na] = NA_REAL
+    return out

@@ -6,6 +6,7 @@ import pytest
 
 import oracle
 import rfsi_b200 as rb
+from oracle import rfsi_oracle_np as onp
 from rfsi_b200 import grow, synth
 from tests.util import same_mean
 
@@ -13,17 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 def np_extract(data, x_ul, y_ul, dx, dy, nodata, scale, offset, xy, layer=0, divide=False):
-    d = data if data.ndim == 3 else data[None]
-    nrow, ncol = d.shape[1:]
-    x, y = xy[:, 0], xy[:, 1]
-    inside = (x >= x_ul) & (x <= x_ul + ncol * dx) & (y <= y_ul) & (y >= y_ul - nrow * dy)
-    c = np.minimum(np.floor((x - x_ul) / dx), ncol - 1).astype(np.int64)
-    r = np.minimum(np.floor((y_ul - y) / dy), nrow - 1).astype(np.int64)
-    out = np.full(len(x), np.nan)
-    raw = d[layer][np.clip(r, 0, nrow - 1), np.clip(c, 0, ncol - 1)].astype(np.float64)
-    ok = inside & ~(raw == nodata) & ~np.isnan(raw)
-    out[ok] = (raw[ok] / scale if divide else raw[ok] * scale) + offset
-    return out
+    return onp.raster_extract(data, x_ul, y_ul, dx, dy, nodata, xy, layer, scale, offset, divide)
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32", "int32", "int16", "uint16", "uint8"])
@@ -123,7 +114,7 @@ def test_fused_covariate_repair_and_separate_sampling_coordinates():
     bad = host["tmin"] > host["tmax"]
     assert 0.05 < bad.mean() < 0.5
     fixed = dict(host)
-    fixed["tmin"] = np.where(bad, host["tmax"] - 1, host["tmin"])           # ifelse(tmin > tmax, tmax-1, tmin)
+    fixed["tmin"] = onp.cov_fix(host["tmin"], host["tmax"], 1.0)            # ifelse(tmin > tmax, tmax-1, tmin)
 
     def station_cov(k):                             # the training table samples the same rasters at the stations
         def f(xy, d):

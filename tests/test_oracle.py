@@ -214,3 +214,34 @@ def test_oracle_reproduces_real_geometry_golden():
     np.testing.assert_array_equal(d, g["dist"]); np.testing.assert_array_equal(i, g["idx"])
     # median nearest-station distance of the real network is ~12.7 km
     assert 5e3 < np.median(g["dist"][:, 0]) < 4e4
+
+
+def test_raster_extract_and_covariate_repair_hand_cases():
+    """raster::extract (method "simple") + `/ 10` + the tmin > tmax repair
+    (prcp_catalonia/5_prcp_prediction.R:253-258), by hand on a 2 x 3 raster."""
+    data = np.array([[10, 20, 3], [40, -32767, 60]], dtype=np.int16)        # row 0 = north
+    geo = dict(x_ul=100.0, y_ul=50.0, dx=2.0, dy=1.0, nodata=-32767)
+    pts = np.array([[100.0, 50.0],      # the upper-left corner belongs to cell (0, 0)
+                    [101.9, 49.1],      # inside cell (0, 0)
+                    [102.0, 49.5],      # a left cell edge belongs to the cell on its right
+                    [106.0, 48.0],      # the outer right / bottom edges belong to the last column / row
+                    [103.0, 48.5],      # the NAvalue cell
+                    [99.99, 49.0], [103.0, 50.01], [106.01, 49.0], [103.0, 47.99],      # outside
+                    [105.0, 49.0]])     # a horizontal cell edge belongs to the row below
+    got = onp.raster_extract(data, xy=pts, **geo)
+    exp = np.array([10, 10, 20, 60, np.nan, np.nan, np.nan, np.nan, np.nan, 60.0])
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+    np.testing.assert_array_equal(got[~np.isnan(exp)], exp[~np.isnan(exp)])
+    # `/ 10` is a division: 3 / 10 is the double nearest to 0.3, 3 * 0.1 is 0.30000000000000004
+    div = onp.raster_extract(data, xy=pts[:1] + [4.5, 0.0], scale=10.0, divide=True, **geo)
+    mul = onp.raster_extract(data, xy=pts[:1] + [4.5, 0.0], scale=0.1, **geo)
+    assert div[0] == 0.3 and mul[0] == 3 * 0.1 and mul[0] != 0.3
+    # layers and offset
+    stack = np.stack([data, data + 1])
+    assert onp.raster_extract(stack, xy=pts[1:2], layer=1, offset=-0.5, **geo)[0] == 10.5
+    # ifelse(tmin > tmax, tmax - 1, tmin), NA if either side is NA
+    tmin = np.array([5.0, 9.0, 3.0, np.nan, 2.0])
+    tmax = np.array([7.0, 8.0, 3.0, 4.0, np.nan])
+    fixed = onp.cov_fix(tmin, tmax, 1.0)
+    np.testing.assert_array_equal(fixed[:3], [5.0, 7.0, 3.0])
+    assert np.isnan(fixed[3]) and np.isnan(fixed[4])
