@@ -677,7 +677,9 @@ int tiff_write_impl(const char* path, const rfsi_tiff_write_args_t* a) {
         counts[s] = a->compression == 1 ? n : packed[s].size();
         data_bytes += counts[s] + (counts[s] & 1);
     }
-    const bool big = data_bytes + nstrips * 16 + 4096 > 0xFFFF0000ull;
+    // BigTIFF above 4 GB (RFSI_IO_FORCE_BIGTIFF=1 forces it, so that the tests can cover the layout)
+    const char* force = getenv("RFSI_IO_FORCE_BIGTIFF");
+    const bool big = data_bytes + nstrips * 16 + 4096 > 0xFFFF0000ull || (force && force[0] == '1');
     const uint64_t hdr = big ? 16 : 8;
     std::vector<uint64_t> offs(nstrips);
     uint64_t at = hdr;

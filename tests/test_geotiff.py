@@ -69,6 +69,21 @@ def test_write_read_round_trip(tmp_path, dtype, compression):
         assert i.compression == gt.COMPRESSION[compression]
 
 
+def test_bigtiff_writer_layout(tmp_path, monkeypatch):
+    """The writer switches to BigTIFF above 4 GB; the layout is forced here and must read back
+    the same (our reader) with the same tags."""
+    monkeypatch.setenv("RFSI_IO_FORCE_BIGTIFF", "1")
+    for dtype, comp in (("int16", "lzw"), ("float64", "none"), ("uint8", "deflate")):
+        a = _data(dtype, (2, 301, 97), seed=9)
+        p = tmp_path / f"big_{dtype}.tif"
+        gt.write_geotiff(p, a, 10.0, 20.0, 0.5, 0.25, nodata=-32767, epsg=4326, compression=comp)
+        assert p.read_bytes()[:4] == b"II\x2b\x00"
+        with gt.GeoTiff(p) as t:
+            assert t.info.big and (t.info.x_ul, t.info.y_ul, t.info.dx, t.info.dy, t.info.nodata, t.info.epsg) == \
+                (10.0, 20.0, 0.5, 0.25, -32767.0, 4326)
+            np.testing.assert_array_equal(t.read(), a)
+
+
 def test_lzw_codec_corner_cases(tmp_path):
     """Streams that cross every code-width switch, fill the table (ClearCode), and hit the
     KwKwK case; each is also decoded by libtiff (PIL) and libtiff's encoding by us."""

@@ -94,3 +94,65 @@ def test_synth_cases_have_the_named_shapes():
     x0, y0, dx, dy, ncol = c3.grid
     p = np.arange(1000, 1500)
     np.testing.assert_array_equal(c3.locations(1000, 500)[:, 0], x0 + (p % ncol) * dx)
+
+
+def _stump_model():
+    from rfsi_b200.forest import FlatForest
+    return rb.RangerForest(FlatForest(1, np.array([0, 3], dtype=np.int64), np.array([1, 0, 0], dtype=np.int32),
+                                      np.array([2, 0, 0], dtype=np.int32), np.array([0, 0, 0], dtype=np.int32),
+                                      np.array([0.5, 1.0, 2.0]), ["tmin"]))
+
+
+def test_predict_fused_checks_its_python_level_arguments_before_the_engine():
+    """Names and shapes are resolved on the host: a wrong one is a ValueError here, not an engine status."""
+    model = _stump_model()
+    loc = np.zeros((4, 2))
+    kw = dict(obs_xy=np.zeros((3, 2)), obs_z=np.zeros((2, 3)), n_obs=1, locations=loc)
+    with pytest.raises(ValueError, match="neither dist/obs"):
+        rb.predict_fused(model, covariates={"tmax": np.zeros(4)}, **kw)                    # model wants tmin
+    with pytest.raises(ValueError, match="shape"):
+        rb.predict_fused(model, covariates={"tmin": np.zeros(5)}, **kw)
+    with pytest.raises(ValueError, match="cov_fix"):
+        rb.predict_fused(model, covariates={"tmin": np.zeros(4)}, cov_fix=[("tmin", "tmax", 1.0)], **kw)
+    with pytest.raises(ValueError, match="cov_locations"):
+        rb.predict_fused(model, covariates={"tmin": np.zeros(4)}, cov_locations=np.zeros((3, 2)), **kw)
+    with pytest.raises(ValueError, match="nobs"):
+        rb.predict_fused(model, covariates={"tmin": np.zeros(4)}, obs_xy=np.zeros((2, 2)), obs_z=np.zeros((2, 3)),
+                         n_obs=1, locations=loc)
+    with pytest.raises(ValueError, match="raster dtype"):
+        rb.predict_fused(model, covariates={"tmin": rb.Raster(np.zeros((2, 2), dtype=np.int64), 0, 2, 1, 1)}, **kw)
+
+
+def test_engine_validates_repairs_and_device_lists_on_the_host(has_gpu):
+    """rfsi_predict_fused(_multi): argument errors are found before any device work (RFSI_E_ARG),
+    so they show even on a box without a GPU, where everything else is RFSI_E_NO_DEVICE."""
+    import ctypes as C
+    from rfsi_b200 import _lib
+    lib = _lib.load()
+    model = _stump_model()
+    loc = np.zeros((4, 2))
+    a = _lib.FusedArgs()
+    a.struct_size = C.sizeof(_lib.FusedArgs)
+    x = np.zeros(4); z = np.zeros((1, 3)); fmap = np.array([0], dtype=np.int32)
+    ptr = lambda v: v.ctypes.data_as(C.c_void_p)
+    a.loc_x, a.loc_y, a.npix, a.grid_ncol = ptr(x), ptr(x), 4, 1
+    a.obs_x, a.obs_y, a.obs_z, a.nobs, a.ndays, a.n_obs = ptr(x), ptr(x), ptr(z), 3, 1, 1
+    cols = (C.c_void_p * 1)(x.ctypes.data); strides = (C.c_int64 * 1)(0)
+    a.ncov, a.cov, a.cov_day_stride = 1, C.cast(cols, C.POINTER(C.c_void_p)), C.cast(strides, C.POINTER(C.c_int64))
+    a.feat_map = fmap.ctypes.data_as(C.POINTER(C.c_int32))
+    out = np.zeros(4); a.out_mean = ptr(out)
+    fix = (_lib.CovFix * 1)(_lib.CovFix(0, 0, 1.0))              # a covariate repaired against itself
+    a.cov_fix, a.ncov_fix = C.cast(fix, C.POINTER(_lib.CovFix)), 1
+    assert lib.rfsi_predict_fused(model.handle, C.byref(a), 0) == _lib.RFSI_E_ARG
+    assert b"cov_fix" in lib.rfsi_last_error()
+    a.ncov_fix = 0
+    a.cov_loc_x = ptr(x)                                         # x without y
+    assert lib.rfsi_predict_fused(model.handle, C.byref(a), 0) == _lib.RFSI_E_ARG
+    a.cov_loc_x = None
+    devs = (C.c_int * 2)(0, 0)
+    assert lib.rfsi_predict_fused_multi(model.handle, C.byref(a), devs, 0) == _lib.RFSI_E_ARG
+    assert lib.rfsi_predict_fused_multi(model.handle, C.byref(a), None, 2) == _lib.RFSI_E_ARG
+    rc = lib.rfsi_predict_fused_multi(model.handle, C.byref(a), devs, 2)
+    assert rc == (0 if has_gpu else _lib.RFSI_E_NO_DEVICE)
+    a.struct_size = 8                                            # header / library mismatch
+    assert lib.rfsi_predict_fused_multi(model.handle, C.byref(a), devs, 2) == _lib.RFSI_E_ARG
