@@ -118,10 +118,51 @@ def croatia_llocv_inputs():
                         ref_rmse=np.sqrt(np.mean((obs[ok] - pred[ok]) ** 2)), ref_n=int(ok.sum()))
 
 
+def croatia_idw_cv():
+    """A reference-produced output vector that depends on near.obs's substance: the stored
+    predictions of the nested 10-fold IDW cross-validation on the Croatian temperatures
+    (temp_croatia/1_models.R:405-536 -> temp_data/IDW_10f_pred.rda, computed in R by gstat with
+    `nmax = n, idp = p` on the UTM33 station coordinates).  An IDW prediction is a function of
+    exactly what near.obs returns -- the n nearest stations with an observation that day, their
+    distances and their observed values: pred = sum(z_i d_i^-p) / sum(d_i^-p).  The per-fold
+    (n, p) the script's tuning loop arrived at are not recorded in the script; they are
+    recovered here by searching its tuning grid (p = 1.0 .. 3.5 step 0.1, n = 2 .. 40): for every
+    fold exactly one pair reproduces all of the fold's stored predictions to < 3e-14 (the next
+    best pair is off by > 1e-3).  Inputs (coordinates, TEMP, folds) are in croatia_llocv.npz."""
+    from rfsi_b200 import rda
+    base = Path("/root/reference/temp_croatia/temp_data")
+    g = np.load(OUT / "croatia_llocv.npz")
+    xy, temp, fold = g["xy"], g["TEMP"], g["fold"]
+    obs = np.asarray(list(rda.read_rda(base / "IDW_10f_obs.rda").values())[0], dtype=np.float64)
+    pred = np.asarray(list(rda.read_rda(base / "IDW_10f_pred.rda").values())[0], dtype=np.float64)
+    assert len(pred) == 55746 and not np.isnan(pred).any()
+    ps = np.round(np.arange(1.0, 3.51, 0.1), 1)
+    n_of, p_of, pos = [], [], 0
+    for k in range(1, 11):
+        val, dev = np.flatnonzero(fold == k), np.flatnonzero(fold != k)
+        D, Z, rows = [], [], []
+        for d in range(temp.shape[0]):
+            tr, te = dev[~np.isnan(temp[d, dev])], val[~np.isnan(temp[d, val])]
+            if len(te):
+                dist, ob, _, _ = oracle.near_obs(xy[te], xy[tr], temp[d, tr], 40)
+                D.append(dist); Z.append(ob); rows.append(temp[d, te])
+        o, Dm, Zm = np.concatenate(rows), np.concatenate(D), np.concatenate(Z)
+        assert np.array_equal(obs[pos:pos + len(o)], o)            # the stored vectors run fold by fold, day by day
+        errs = sorted((float(np.max(np.abs((Dm[:, :n] ** -p * Zm[:, :n]).sum(1) / (Dm[:, :n] ** -p).sum(1) - pred[pos:pos + len(o)]))), n, p)
+                      for n in range(2, 41) for p in ps)
+        assert errs[0][0] < 3e-14 and errs[1][0] > 1e-3, errs[:2]
+        n_of.append(errs[0][1]); p_of.append(errs[0][2])
+        pos += len(o)
+    assert pos == len(pred)
+    np.savez_compressed(OUT / "croatia_idw_cv.npz", pred=pred, n=np.array(n_of), p=np.array(p_of))
+    print("IDW (n, p) per fold:", list(zip(n_of, p_of)))
+
+
 if __name__ == "__main__":
     if Path("/root/reference").exists():
         knn_croatia_real()
         croatia_llocv_inputs()
+        croatia_idw_cv()
     knn_lattice()
     knn_realgeom()
     forest_small()

@@ -206,6 +206,16 @@ def test_near_obs_days_training_table_and_prediction_shapes():
         _same(pd_[d], ed); _same(po_[d], eo)
 
 
+def test_cuda_near_obs_reproduces_the_reference_s_stored_idw_cv_predictions():
+    """The CUDA kNN against an output vector the REFERENCE produced: the 55 746 stored predictions of
+    its nested 10-fold IDW cross-validation (temp_croatia/1_models.R:405-536, temp_data/IDW_10f_pred.rda,
+    gstat in R) are functions of exactly near.obs's output -- see tests/util.py::reference_idw_cv."""
+    from tests.util import RTOL, reference_idw_cv
+    got, stored = reference_idw_cv(lambda obs_xy, obs_z, n, loc: rb.near_obs_days(obs_xy, obs_z, n, locations=loc))
+    assert got.shape == stored.shape == (55746,)
+    np.testing.assert_allclose(got, stored, rtol=RTOL, atol=0)
+
+
 def test_near_obs_f32_twin():
     """float buffers in/out: same neighbours as the fp64 call on the same coordinates,
     distances/observations within 1e-5 relative (north_star's fp32 mode)."""
