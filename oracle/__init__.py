@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs.  The product (rfsi_b200/) never
-imports this package.  PARITY UNPINNED -- see the header of rfsi_oracle.c.
+imports this package.  near.obs is pinned against the reference's stored IDW cross-validation
+vectors, the forest half is PARITY UNPINNED -- see the header of rfsi_oracle.c.
 """
 from __future__ import annotations
 

@@ -4,8 +4,9 @@
 //
 // TEST / BENCH INFRASTRUCTURE ONLY (same rule as rfsi_oracle.c): only tests/,
 // smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
-// PARITY UNPINNED for the same reason as rfsi_oracle.c: R, meteo, nabor and ranger
-// cannot run here.  It is a second, independent restatement: tests require it to
+// Pinning as for rfsi_oracle.c: the kd-tree near.obs reproduces the reference's stored IDW
+// cross-validation predictions (tests/test_oracle.py); the forest half is PARITY UNPINNED (R and
+// ranger cannot run here, no saved forest in the reference).  It is a second, independent restatement: tests require it to
 // agree bit for bit with rfsi_oracle.c (brute force) on ties, self matches and
 // short station lists.
 //

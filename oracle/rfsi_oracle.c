@@ -5,8 +5,13 @@
  * link or execute this file; only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs use it, and only as the checker.
  *
- * PARITY UNPINNED: the reference (AleksandarSekulic/RFSI) holds no golden
- * vectors, known-answer tests or fixtures for this path (SURVEY.md section 4 and
+ * PINNING: stage 1 (near.obs) IS pinned against an output of the reference itself -- the 55 746
+ * stored predictions of its nested 10-fold IDW cross-validation (temp_croatia/1_models.R:405-536,
+ * temp_data/IDW_10f_pred.rda, computed in R by gstat), each a function of exactly near.obs's output
+ * (the n nearest observed stations, their distances and values), are reproduced to 2e-14
+ * (tests/test_oracle.py, tests/util.py::reference_idw_cv).  Stage 2 (ranger predict / quantiles) is
+ * PARITY UNPINNED: the reference (AleksandarSekulic/RFSI) holds no saved forest, golden
+ * vectors, known-answer tests or fixtures for it (SURVEY.md section 4 and
  * 8c), and its arithmetic lives in un-vendored, un-pinned R packages
  * (meteo::near.obs, nabor::knn / libnabo, ranger::predict.ranger, stats::quantile)
  * that cannot be run in this container (no R).  This file restates the published

@@ -3,7 +3,12 @@
 TEST INFRASTRUCTURE ONLY -- only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline leg may import this; the product (rfsi_b200/) never does.
 
-PARITY UNPINNED: the reference holds no golden vectors for this path and its
+PINNING: stage 1 (near.obs) IS pinned against an output of the reference itself -- the 55 746
+stored predictions of its nested 10-fold IDW cross-validation (temp_croatia/1_models.R:405-536,
+temp_data/IDW_10f_pred.rda, computed in R by gstat), each a function of exactly near.obs's output
+(the n nearest observed stations, their distances and values), are reproduced to 2e-14
+(tests/test_oracle.py, tests/util.py::reference_idw_cv).  Stage 2 (ranger predict / quantiles) is
+PARITY UNPINNED: the reference holds no saved forest or golden vectors for it and its
 arithmetic lives in un-vendored R packages that cannot run here.
 Semantics follow SURVEY.md Appendix A, anchored on the reference call sites:
 near.obs -> simulation/simulation.R:191-196; predict -> simulation.R:214;
