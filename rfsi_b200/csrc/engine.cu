@@ -209,6 +209,9 @@ struct rfsi_forest {
     };
     mutable std::mutex mu;
     mutable std::map<int, Image> images;
+    // host copy of the rank form of the sample table (of whichever image layout is in use), built on first upload
+    mutable std::vector<double> sample_dict_h;
+    mutable std::vector<uint32_t> leaf_rank_h;
 };
 
 namespace {
@@ -294,9 +297,10 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
             // 4-byte form: the distinct sample values (at most one per training row) sorted in
             // the total order of their bit patterns (-0.0 < +0.0 stay distinct entries, so the
             // values that come back are the very doubles ranger stored), and each leaf's rank
-            std::vector<double> dict;
-            std::vector<uint32_t> rank;
-            sample_ranks(ls, dict, rank);
+            // built once per forest (f->mu is held), shared by the images of all devices
+            std::vector<double>& dict = f->sample_dict_h;
+            std::vector<uint32_t>& rank = f->leaf_rank_h;
+            if (rank.size() != ls.size()) sample_ranks(ls, dict, rank);
             CU_TRY(cudaMalloc(&im.leaf_rank, std::max<size_t>(rank.size(), 1) * sizeof(uint32_t)));
             CU_TRY(cudaMemcpy(im.leaf_rank, rank.data(), rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             CU_TRY(cudaMalloc(&im.sample_dict, std::max<size_t>(dict.size(), 1) * sizeof(double)));
