@@ -93,6 +93,22 @@ typedef struct rfsi_tiff_write_args {
  * switches to BigTIFF above 4 GB. */
 int rfsi_tiff_write(const char* path, const rfsi_tiff_write_args_t* a);
 
+/* ---- border polygons ------------------------------------------------------------------
+ * The mapping scripts cut every product to the country border:
+ *   border <- readOGR("borders/osm/union_of_selected_boundaries_AL2-AL2.shp"); border <- spTransform(border, CRS(utm33))
+ *   p = crop(p, border); p = mask(p, border)            (temp_croatia/2_predictions.R:27-28,108-109,113-114,...)
+ * rfsi_shp_read_polygons is the readOGR half for polygon shapefiles (ESRI shape types 5 / 15 / 25; Z and M values
+ * are ignored): all rings of all records, concatenated.  *xy receives 2*npoints doubles (x0, y0, x1, y1, ...),
+ * *ring_start receives nrings+1 offsets into the points; both are released with rfsi_io_free.
+ * rfsi_polygon_mask is the mask() half: out[row*ncol + col] = 1 where the CENTRE of the cell lies inside the
+ * polygons (even-odd rule over all rings, so holes and multi-part borders come out right), else 0 -- the
+ * pix_mask argument of rfsi_predict_fused.  Vertices are used as given: project them first when the raster is
+ * projected (the scripts' spTransform moves the vertices only, too). */
+int rfsi_shp_read_polygons(const char* path, double** xy, int64_t* npoints, int64_t** ring_start, int64_t* nrings);
+void rfsi_io_free(void* p);
+int rfsi_polygon_mask(const double* xy, const int64_t* ring_start, int64_t nrings, double x_ul, double y_ul, double dx,
+                      double dy, int64_t ncol, int64_t nrow, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,9 +28,11 @@
 #include <vector>
 
 namespace {
-
 thread_local std::string g_err;
+}  // namespace
 
+// shared with shape.cpp: one error slot per thread for the whole library
+namespace rfsi_io_detail {
 int fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -40,6 +42,10 @@ int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+}  // namespace rfsi_io_detail
+using rfsi_io_detail::fail;
+
+namespace {
 
 // TIFF field types -> element size
 const int kTypeSize[19] = {0, 1, 1, 2, 4, 8, 1, 1, 2, 4, 8, 4, 8, 4, 0, 0, 8, 8, 8};

@@ -62,6 +62,10 @@ _SIGNATURES = [
     ("rfsi_tiff_read", C.c_int, [_P, _P, C.c_size_t, C.c_int]),
     ("rfsi_tiff_tag", C.c_int64, [_P, C.c_int32, C.POINTER(C.c_int32), _P, C.c_size_t]),
     ("rfsi_tiff_write", C.c_int, [C.c_char_p, C.POINTER(_WriteArgs)]),
+    ("rfsi_shp_read_polygons", C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int64),
+                                         C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_int64)]),
+    ("rfsi_io_free", None, [_P]),
+    ("rfsi_polygon_mask", C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int64, _P]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 _lib = None
@@ -235,3 +239,43 @@ def write_product(path, values_i16: np.ndarray, like: GeoTiffInfo, compression: 
         raise ValueError("write_product: Int16 centi-units expected (predict_fused(..., centi_int16=True))")
     write_geotiff(path, v.reshape(like.nrow, like.ncol), like.x_ul, like.y_ul, like.dx, like.dy, nodata=-32767,
                   epsg=like.epsg, geokeys=like.geokeys, compression=compression)
+
+
+@dataclass
+class Polygons:
+    """readOGR(<polygon shapefile>): all rings of all records.  xy (npoints, 2); ring r is
+    xy[ring_start[r]:ring_start[r + 1]] (outer rings and holes alike: masks use the even-odd rule)."""
+    xy: np.ndarray
+    ring_start: np.ndarray
+
+    def transformed(self, fn) -> "Polygons":
+        """spTransform(border, crs): fn(x, y) -> (x', y') on the vertices (e.g. proj.lonlat_to_utm)."""
+        x, y = fn(self.xy[:, 0], self.xy[:, 1])
+        return Polygons(np.column_stack([x, y]), self.ring_start)
+
+
+def read_polygons(path) -> Polygons:
+    """readOGR("borders/...shp") for polygon shapefiles (temp_croatia/2_predictions.R:27)."""
+    lib = load()
+    xy = C.POINTER(C.c_double)()
+    rs = C.POINTER(C.c_int64)()
+    n, nr = C.c_int64(), C.c_int64()
+    _check(lib.rfsi_shp_read_polygons(os.fsencode(str(path)), C.byref(xy), C.byref(n), C.byref(rs), C.byref(nr)))
+    try:
+        pts = np.ctypeslib.as_array(xy, shape=(max(n.value, 1) * 2,))[:n.value * 2].reshape(-1, 2).copy()
+        start = np.ctypeslib.as_array(rs, shape=(nr.value + 1,)).copy()
+    finally:
+        lib.rfsi_io_free(xy)
+        lib.rfsi_io_free(rs)
+    return Polygons(pts, start)
+
+
+def polygon_mask(poly: Polygons, x_ul: float, y_ul: float, dx: float, dy: float, ncol: int, nrow: int) -> np.ndarray:
+    """mask(r, border) as a (nrow, ncol) uint8 array: 1 where the centre of the cell lies inside the
+    polygons (temp_croatia/2_predictions.R:108-109); feed it to predict_fused(pix_mask=...)."""
+    xy = np.ascontiguousarray(poly.xy, dtype=np.float64)
+    rs = np.ascontiguousarray(poly.ring_start, dtype=np.int64)
+    out = np.empty((int(nrow), int(ncol)), dtype=np.uint8)
+    _check(load().rfsi_polygon_mask(xy.ctypes.data_as(_P), rs.ctypes.data_as(_P), len(rs) - 1, float(x_ul), float(y_ul),
+                                    float(dx), float(dy), int(ncol), int(nrow), out.ctypes.data_as(_P)))
+    return out

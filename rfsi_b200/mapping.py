@@ -51,14 +51,18 @@ class PredictionGrid:
         return full.reshape(self.info.nrow, self.info.ncol)
 
 
-def grid_from_dem(dem_path, utm_zone: Optional[int] = None) -> PredictionGrid:
+def grid_from_dem(dem_path, utm_zone: Optional[int] = None, border: Optional[geotiff.Polygons] = None) -> PredictionGrid:
     """gg <- as(readGDAL(dem), "SpatialPixelsDataFrame") (drops NA cells);
-    gg2 <- spTransform(gg, utm<zone>) when utm_zone is given (5_prcp_prediction.R:38-46)."""
+    gg2 <- spTransform(gg, utm<zone>) when utm_zone is given (5_prcp_prediction.R:38-46).
+    border (in the DEM's CRS): additionally `crop(p, border); mask(p, border)` -- only cells whose
+    centre lies inside the polygons are predicted (temp_croatia/2_predictions.R:108-109)."""
     r, info = geotiff.read_geotiff(dem_path)
     d = r.data if r.data.ndim == 2 else r.data[0]
     valid = ~np.isnan(d.astype(np.float64))
     if info.nodata is not None:
         valid &= d != d.dtype.type(info.nodata)
+    if border is not None:
+        valid &= geotiff.polygon_mask(border, info.x_ul, info.y_ul, info.dx, info.dy, info.ncol, info.nrow).astype(bool)
     cell = np.flatnonzero(valid.ravel())
     row, col = np.divmod(cell, info.ncol)
     x = info.x_ul + (col + 0.5) * info.dx
