@@ -19,7 +19,7 @@ ROOT = Path(__file__).resolve().parents[1]
 @pytest.fixture(scope="module")
 def lib(tmp_path_factory):
     so = tmp_path_factory.mktemp("proto") / "libsector_image.so"
-    subprocess.run(["g++", "-O2", "-fPIC", "-std=c++17", "-shared", "-o", str(so),
+    subprocess.run(["g++", "-O2", "-fPIC", "-std=c++17", "-shared", "-Wno-unknown-pragmas", "-o", str(so),
                     str(ROOT / "tools" / "prototypes" / "sector_image.cpp")], check=True)
     L = C.CDLL(str(so))
     L.sector_stats.restype = C.c_int64
@@ -27,6 +27,7 @@ def lib(tmp_path_factory):
     L.sector_walk.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sector_build.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_void_p)]
     L.sector_free.argtypes = [C.c_void_p]
+    L.sector_walk_lockstep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -79,4 +80,11 @@ def test_sector_image_walk_equals_the_oracle_and_touches_fewer_sectors(lib):
           f"{lib.sector_stats(h, 4)} child slots unreachable), mean depth {d.mean():.1f}: "
           f"{new.mean():.2f} sectors per tree walk vs {old.mean():.2f} with 128-byte blocks ({old.mean() / new.mean():.2f}x)")
     assert old.mean() / new.mean() > 1.8
+    # the device loop itself (tools/prototypes/sector_walk.cuh compiled for the host): J chains in lock step, finished
+    # chains parked on the idle block, tree counts that are not a multiple of J (60 trees: J = 8 leaves a tail of 4)
+    for J in (1, 3, 4, 8):
+        s2 = np.empty(len(Q)); n2 = np.empty_like(node)
+        assert lib.sector_walk_lockstep(h, p(Xt), len(Q), len(Q), J, p(s2), p(n2)) == 0
+        np.testing.assert_array_equal(n2, node, err_msg=f"J={J}")
+        np.testing.assert_array_equal(s2, total, err_msg=f"J={J}")
     lib.sector_free(h)

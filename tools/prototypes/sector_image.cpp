@@ -55,6 +55,8 @@ extern "C" int sector_build(int ntrees, const int64_t* off, const int32_t* left,
     for (auto& u : im->uvals) { std::sort(u.begin(), u.end()); u.erase(std::unique(u.begin(), u.end()), u.end()); }
     for (auto& u : im->uvals) if (u.size() >= 0xFFFFFFu) { delete im; return -1; }
     std::vector<uint32_t>& W = im->w;
+    W.assign(8, kPass);          // block 0: the idle block of finished chains -- all pass-through,
+    W[0] = 0u;                   // and its first child is itself
     auto new_blocks = [&](int n) { const size_t b = W.size() / 8; W.resize(W.size() + 8 * (size_t)n, 0u); return (uint32_t)b; };
     struct Todo { int64_t node; uint32_t block; };
     for (int t = 0; t < ntrees; ++t) {
@@ -165,3 +167,30 @@ extern "C" void sector_walk(const void* h, const double* X, int64_t npix, int64_
 }
 
 extern "C" void sector_free(void* h) { delete static_cast<Image*>(h); }
+
+// ---- the device loop (sector_walk.cuh), compiled for the host: J chains in lock step -----------------
+#define RFSI_PROTO_HOST 1
+#include "sector_walk.cuh"
+
+template <int J>
+static void lockstep(const Image* im, const double* X, int64_t npix, int64_t ldx, double* out_sum, int32_t* out_node) {
+    rfsi_proto::SectorForest q{im->w.data(), im->root.data(), 0u};
+    std::vector<uint32_t> rk((size_t)im->F), leaf((size_t)im->T);
+    for (int64_t p = 0; p < npix; ++p) {
+        for (int f = 0; f < im->F; ++f) rk[(size_t)f] = rank_of(im->uvals[(size_t)f], X[(int64_t)f * ldx + p]) << 8;
+        out_sum[p] = rfsi_proto::traverse_s<1, J>(q, 0, im->T, 0.0, rk.data(), leaf.data());
+        for (int t = 0; t < im->T; ++t) out_node[p * im->T + t] = im->leaf_rid[leaf[(size_t)t]];
+    }
+}
+
+extern "C" int sector_walk_lockstep(const void* h, const double* X, int64_t npix, int64_t ldx, int J, double* out_sum,
+                                    int32_t* out_node) {
+    const Image* im = static_cast<const Image*>(h);
+    switch (J) {
+        case 1: lockstep<1>(im, X, npix, ldx, out_sum, out_node); return 0;
+        case 3: lockstep<3>(im, X, npix, ldx, out_sum, out_node); return 0;
+        case 4: lockstep<4>(im, X, npix, ldx, out_sum, out_node); return 0;
+        case 8: lockstep<8>(im, X, npix, ldx, out_sum, out_node); return 0;
+        default: return -1;
+    }
+}

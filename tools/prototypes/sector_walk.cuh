@@ -5,6 +5,17 @@
 // step, leaf values are added in tree order.
 #pragma once
 #include <cstdint>
+#include <cstddef>
+
+#if defined(RFSI_PROTO_HOST)   // the same loop compiled for the host (sector_image.cpp: sector_walk_lockstep)
+#include <algorithm>
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+struct uint2 { uint32_t x, y; };
+template <class T> inline T __ldg(const T* p) { return *p; }
+using std::min;
+#endif
 
 namespace rfsi_proto {
 
