@@ -194,3 +194,92 @@ extern "C" int sector_walk_lockstep(const void* h, const double* X, int64_t npix
         default: return -1;
     }
 }
+
+// ---- warp-level traffic of both images for the SAME walks (no GPU needed) ----------------------------------
+// X holds groups of 32 pixels (one warp: an 8 x 4 patch of the raster).  For every tree the 32 lanes walk in lock
+// step, level by level; a warp-level load costs one request and as many sectors as the lanes' addresses cover.
+//   blocked image (product, csrc/common.cuh): block = 4 levels rooted at depth 0, 4, 8 ...; heap slots 1-7 live
+//     in sector 0 of the block's 128-byte line, slots 8-15 in sector 1, exit words 16-23 / 24-31 in sectors 2 / 3;
+//     five loads per block visit (four levels + the exit word), then one 8-byte leaf-value gather per tree;
+//   sector image (this file): block = 3 levels = one sector; three loads per block visit, the leaf is a block.
+// out[0..5] = {requests, sector lookups} of the blocked image, the same of the sector image, then the sectors each
+// touches for the first time within a block visit (what has to come from L2 when nothing is left in L1).
+extern "C" void warp_traffic(int ntrees, const int64_t* off, const int32_t* left, const int32_t* right, const int32_t* var,
+                             const double* val, const double* X, int64_t npix, int64_t ldx, int64_t* out) {
+    int64_t req4 = 0, sec4 = 0, req3 = 0, sec3 = 0, miss4 = 0, miss3 = 0;
+    std::vector<int64_t> key(32), seen;
+    auto distinct = [&](int n) { std::sort(key.begin(), key.begin() + n); return (int64_t)(std::unique(key.begin(), key.begin() + n) - key.begin()); };
+    for (int64_t g = 0; g + 32 <= npix; g += 32) {
+        for (int t = 0; t < ntrees; ++t) {
+            const int64_t base = off[t];
+            // per lane: the path (node ids) to its leaf
+            std::vector<std::vector<int32_t>> path(32);
+            size_t longest = 0;
+            for (int l = 0; l < 32; ++l) {
+                int32_t n = 0;
+                for (;;) {
+                    path[l].push_back(n);
+                    const int64_t q = base + n;
+                    if (left[q] == 0 && right[q] == 0) break;
+                    n = (X[(int64_t)var[q] * ldx + g + l] <= val[q]) ? left[q] : right[q];
+                }
+                longest = std::max(longest, path[l].size() - 1);      // internal nodes on the path
+            }
+            // a lane's position at depth d: its node there, or its leaf once it is past it (padding / idle block)
+            auto at = [&](int l, size_t d) { return path[l][std::min(d, path[l].size() - 1)]; };
+            // a lane visits the block rooted at depth d iff its node there is internal (else the previous exit was a leaf)
+            auto visits = [&](int l, size_t d) { return d == 0 || d < path[l].size() - 1; };
+            for (int levels : {4, 3}) {
+                int64_t& req = levels == 4 ? req4 : req3;
+                int64_t& sec = levels == 4 ? sec4 : sec3;
+                int64_t& miss = levels == 4 ? miss4 : miss3;      // sectors touched for the first time in a block visit
+                for (size_t d0 = 0; d0 < std::max<size_t>(longest, 1); d0 += (size_t)levels) {
+                    // lanes whose leaf lies above this block's root have left the tree: they idle on a shared block
+                    seen.clear();
+                    for (int lev = 0; lev < levels; ++lev) {
+                        int n = 0;
+                        for (int l = 0; l < 32; ++l) {
+                            if (!visits(l, d0)) { key[n++] = -1; continue; }                     // idle block
+                            const int64_t root = at(l, d0);
+                            // heap slot inside the block from the path bits below the block root
+                            int h = 1;
+                            for (int k = 0; k < lev; ++k) {
+                                const size_t d = d0 + (size_t)k;
+                                const bool right_turn = d + 1 < path[l].size() && path[l][d + 1] == right[base + path[l][d]] && !(left[base + path[l][d]] == 0 && right[base + path[l][d]] == 0);
+                                h = 2 * h + (right_turn ? 1 : 0);
+                            }
+                            const int sector = levels == 4 ? (h >= 8 ? 1 : 0) : 0;
+                            key[n++] = root * 4 + sector;
+                        }
+                        ++req; sec += distinct(n);
+                        for (int i = 0; i < n; ++i) if (key[i] >= 0) seen.push_back(key[i]);
+                    }
+                    if (levels == 4) {                                  // the exit word
+                        int n = 0;
+                        for (int l = 0; l < 32; ++l) {
+                            if (!visits(l, d0)) { key[n++] = -1; continue; }
+                            int h = 1;
+                            for (int k = 0; k < 4; ++k) {
+                                const size_t d = d0 + (size_t)k;
+                                const bool right_turn = d + 1 < path[l].size() && path[l][d + 1] == right[base + path[l][d]] && !(left[base + path[l][d]] == 0 && right[base + path[l][d]] == 0);
+                                h = 2 * h + (right_turn ? 1 : 0);
+                            }
+                            key[n++] = (int64_t)at(l, d0) * 4 + (h >= 24 ? 3 : 2);
+                        }
+                        ++req; sec += distinct(n);
+                        for (int i = 0; i < n; ++i) if (key[i] >= 0) seen.push_back(key[i]);
+                    }
+                    std::sort(seen.begin(), seen.end());
+                    miss += (int64_t)(std::unique(seen.begin(), seen.end()) - seen.begin());
+                }
+                // the leaf: blocked image gathers leaf_val[leaf] (8 B, 4 leaves per sector, leaves numbered in order ~ node id / 2);
+                // sector image reads the leaf's own block (one more block visit: 1 request)
+                int n = 0;
+                for (int l = 0; l < 32; ++l) key[n++] = levels == 4 ? (int64_t)path[l].back() / 8 : (int64_t)path[l].back();
+                const int64_t dl = distinct(n);
+                ++req; sec += dl; miss += dl;
+            }
+        }
+    }
+    out[0] = req4; out[1] = sec4; out[2] = req3; out[3] = sec3; out[4] = miss4; out[5] = miss3;
+}
