@@ -6,8 +6,11 @@ rfsi   = near.obs on the training stations (locations == observations, per day) 
 pred_rfsi = near.obs + cbind + predict for new locations, in one fused engine call.
 
 Inputs are data frames (the README's `data.frame` branch: data.staid.x.y.z names the station
-id, x, y and time columns; time None/NA = purely spatial).  sf / SpatVector / SpatRaster
-objects have no Python counterpart here; pass their attribute table + coordinates.
+id, x, y and time columns; time None/NA = purely spatial).  sf / SpatVector objects have no
+Python counterpart here: pass their attribute table + coordinates.  A SpatRaster of covariates
+(README.md:121-125, `newdata <- terra::rast(meuse.grid)`) is a dict of api.Raster layers on one
+grid (e.g. read with geotiff.read_geotiff); with output_format="SpatRaster" the prediction
+comes back as layers on that grid (README.md:133,150-153).
 """
 from __future__ import annotations
 
@@ -90,8 +93,12 @@ def pred_rfsi(model: RfsiModel, data: pd.DataFrame, obs_col, data_staid_x_y_z: S
     """README.md:127-143.  Returns newdata's id/x/y(/time) + `pred` (+ `quantile..p` columns)."""
     if zero_tol != 0 or soil3d:
         raise NotImplementedError("pred_rfsi: zero.tol = 0 and soil3d = FALSE only")
+    if isinstance(newdata, dict) and all(isinstance(v, api.Raster) for v in newdata.values()):
+        if output_format != "SpatRaster":
+            raise NotImplementedError("pred_rfsi: a raster newdata gives output.format = 'SpatRaster'")
+        return _pred_rfsi_raster(model, data, obs_col, data_staid_x_y_z, newdata, type, quantiles, device)
     if output_format != "data.frame":
-        raise NotImplementedError("pred_rfsi: only output.format = 'data.frame' exists without terra/sf")
+        raise NotImplementedError("pred_rfsi: output.format = 'data.frame' (or a raster newdata with 'SpatRaster')")
     if type not in ("response", "quantiles"):
         raise ValueError("type must be 'response' or 'quantiles'")
     if type == "quantiles" and not model.quantreg:
@@ -122,3 +129,75 @@ def pred_rfsi(model: RfsiModel, data: pd.DataFrame, obs_col, data_staid_x_y_z: S
                 part[f"quantile..{p}"] = res["quantiles"][j, 0]
         out_parts.append(part)
     return pd.concat(out_parts, ignore_index=True)
+
+
+@dataclass
+class RasterPrediction:
+    """pred.rfsi(..., output.format = "SpatRaster"): layers `pred` (+ `quantile..p`) on newdata's grid,
+    NaN where a covariate layer is NA (README.md:150-153)."""
+    layers: dict
+    x_ul: float
+    y_ul: float
+    dx: float
+    dy: float
+
+    def __getitem__(self, name):
+        return self.layers[name]
+
+    def names(self):
+        return list(self.layers)
+
+
+def raster_cells(r: "api.Raster"):
+    """Cell centres of a north-up raster in row-major order (xyFromCell) and its (nrow, ncol)."""
+    d = r.data if r.data.ndim == 2 else r.data[0]
+    nrow, ncol = d.shape
+    x = r.x_ul + (np.arange(ncol) + 0.5) * r.dx
+    y = r.y_ul - (np.arange(nrow) + 0.5) * r.dy
+    return np.column_stack([np.tile(x, nrow), np.repeat(y, ncol)]), (nrow, ncol)
+
+
+def raster_valid(r: "api.Raster") -> np.ndarray:
+    """!is.na(values(r)) of the first layer, row-major."""
+    d = (r.data if r.data.ndim == 2 else r.data[0]).astype(np.float64)
+    ok = ~np.isnan(d)
+    if not np.isnan(r.nodata):
+        ok &= d != r.nodata
+    return ok.ravel()
+
+
+def _pred_rfsi_raster(model: RfsiModel, data: pd.DataFrame, obs_col, data_staid_x_y_z, newdata: dict, type: str,
+                      quantiles, device: int) -> RasterPrediction:
+    if type not in ("response", "quantiles"):
+        raise ValueError("type must be 'response' or 'quantiles'")
+    if type == "quantiles" and not model.quantreg:
+        raise ValueError("Error: Set quantreg=TRUE in rfsi(...) for quantile prediction.")
+    missing = [c for c in model.covariates if c not in newdata]
+    if missing:
+        raise ValueError(f"pred_rfsi: newdata has no layer for {missing}")
+    sid, xc, yc, tc = [None if c is None else _col(data, c) for c in data_staid_x_y_z]
+    if tc is not None and data[tc].nunique() > 1:
+        raise NotImplementedError("pred_rfsi: a raster newdata is purely spatial (one time step)")
+    obs_col = _col(data, obs_col)
+    layers = {c: newdata[c] for c in model.covariates}
+    first = next(iter(newdata.values()))
+    loc, (nrow, ncol) = raster_cells(first)
+    for name, r in layers.items():
+        d = r.data if r.data.ndim == 2 else r.data[0]
+        if (d.shape, r.x_ul, r.y_ul, r.dx, r.dy) != ((nrow, ncol), first.x_ul, first.y_ul, first.dx, first.dy):
+            raise ValueError(f"pred_rfsi: layer {name!r} is not on the grid of the first layer")
+    valid = np.ones(nrow * ncol, dtype=bool)
+    for r in layers.values():
+        valid &= raster_valid(r)
+    if not layers:
+        valid &= raster_valid(first)
+    probs = list(quantiles) if type == "quantiles" else None
+    z = data[obs_col].to_numpy(dtype=np.float64)[None, :]
+    res = api.predict_fused(model.forest, obs_xy=data[[xc, yc]].to_numpy(dtype=np.float64), obs_z=z, n_obs=model.n_obs,
+                            locations=loc, covariates=layers, quantiles=probs, pix_mask=valid.astype(np.uint8),
+                            device=device)
+    out = {"pred": res["mean"][0].reshape(nrow, ncol)}
+    if probs is not None:
+        for j, p in enumerate(probs):
+            out[f"quantile..{p}"] = res["quantiles"][j, 0].reshape(nrow, ncol)
+    return RasterPrediction(out, first.x_ul, first.y_ul, first.dx, first.dy)

@@ -156,3 +156,46 @@ def test_engine_validates_repairs_and_device_lists_on_the_host(has_gpu):
     assert rc == (0 if has_gpu else _lib.RFSI_E_NO_DEVICE)
     a.struct_size = 8                                            # header / library mismatch
     assert lib.rfsi_predict_fused_multi(model.handle, C.byref(a), devs, 2) == _lib.RFSI_E_ARG
+
+
+def test_pred_rfsi_with_a_raster_newdata_wires_grid_mask_and_layers(monkeypatch):
+    """README.md:121-153: newdata <- terra::rast(...), output.format = "SpatRaster".  The engine call is
+    replaced by a recorder here (the GPU side is the fused call of tests/test_gpu_raster.py): what is
+    checked is the host wiring -- cell centres in row-major order, the NA mask over all covariate
+    layers, layers handed over as rasters, results put back on the grid."""
+    from rfsi_b200 import rfsi as R
+    seen = {}
+
+    def fake(model, **kw):
+        seen.update(kw)
+        n = len(kw["locations"])
+        out = {"mean": np.arange(n, dtype=np.float64)[None, :]}
+        if kw["quantiles"] is not None:
+            out["quantiles"] = np.stack([np.full((1, n), q) for q in kw["quantiles"]])
+        return out
+    monkeypatch.setattr(R.api, "predict_fused", fake)
+    dist = np.array([[0.1, 0.2, np.nan], [0.4, 0.5, 0.6]])
+    soil = np.array([[1, 2, 3], [-9, 2, 1]], dtype=np.int16)
+    newdata = {"dist": rb.Raster(dist, 178000.0, 334000.0, 40.0, 40.0), "soil": rb.Raster(soil, 178000.0, 334000.0, 40.0, 40.0, nodata=-9),
+               "unused": rb.Raster(np.full((2, 3), np.nan), 178000.0, 334000.0, 40.0, 40.0)}
+    model = R.RfsiModel(forest=None, formula="zinc ~ dist + soil", response="zinc", covariates=["dist", "soil"], n_obs=5,
+                        num_trees=250, quantreg=True)
+    data = pd.DataFrame({"id": [1, 2, 3], "x": [178010.0, 178050.0, 178090.0], "y": [333990.0, 333950.0, 333970.0],
+                         "zinc": [100.0, np.nan, 300.0]})
+    out = R.pred_rfsi(model, data, "zinc", ("id", "x", "y", None), newdata, None, output_format="SpatRaster",
+                      type="quantiles", quantiles=(0.1, 0.9))
+    np.testing.assert_array_equal(seen["locations"], [[178020, 333980], [178060, 333980], [178100, 333980],
+                                                      [178020, 333940], [178060, 333940], [178100, 333940]])
+    np.testing.assert_array_equal(seen["pix_mask"], [1, 1, 0, 0, 1, 1])           # NA in dist, NAvalue in soil; `unused` is not a model column
+    assert list(seen["covariates"]) == ["dist", "soil"] and seen["n_obs"] == 5
+    np.testing.assert_array_equal(seen["obs_z"], [[100.0, np.nan, 300.0]])
+    assert out.names() == ["pred", "quantile..0.1", "quantile..0.9"]
+    np.testing.assert_array_equal(out["pred"], [[0, 1, 2], [3, 4, 5]])
+    assert out["quantile..0.9"].shape == (2, 3) and (out.x_ul, out.y_ul, out.dx, out.dy) == (178000.0, 334000.0, 40.0, 40.0)
+    with pytest.raises(NotImplementedError):
+        R.pred_rfsi(model, data, "zinc", ("id", "x", "y", None), newdata, None, output_format="data.frame")
+    bad = dict(newdata, soil=rb.Raster(soil[:, :2], 178000.0, 334000.0, 40.0, 40.0))
+    with pytest.raises(ValueError, match="grid"):
+        R.pred_rfsi(model, data, "zinc", ("id", "x", "y", None), bad, None, output_format="SpatRaster")
+    with pytest.raises(ValueError, match="no layer"):
+        R.pred_rfsi(model, data, "zinc", ("id", "x", "y", None), {"dist": newdata["dist"]}, None, output_format="SpatRaster")
