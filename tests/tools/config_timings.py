@@ -2,7 +2,7 @@
 """DT / PT timings of the reference's own configs through the R-call-shaped host API
 (host buffers in, host buffers out -- what simulation.R:190-215 times as DT and PT).
 
-python tools/config_timings.py > profiles/r01_config_timings.md   (on a B200)
+python tests/tools/config_timings.py > profiles/r01_config_timings.md   (on a B200)
 """
 import sys
 import time
@@ -10,7 +10,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import rfsi_b200 as rb  # noqa: E402
 from rfsi_b200 import grow, synth  # noqa: E402

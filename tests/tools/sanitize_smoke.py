@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """Small end-to-end pass over every kernel for compute-sanitizer (memcheck):
-   compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+   compute-sanitizer --tool memcheck python tests/tools/sanitize_smoke.py"""
 import sys
 from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import rfsi_b200 as rb  # noqa: E402
 from rfsi_b200 import grow, synth  # noqa: E402

@@ -2,13 +2,13 @@
 """Scale run: half of the 10^4 x 10^4 C5 raster (5 x 10^7 pixels) x 4 days through the HOST API in one
 call -- covariates as per-day rasters sampled on the device, products as Int16 (what the mapping
 scripts write) -- with a sample checked against the CPU oracle.
-python tools/scale_run.py [rows] [days] [ndevices] [trees]
+python tests/tools/scale_run.py [rows] [days] [ndevices] [trees]
 With ndevices > 1 the same call is repeated with devices=0..ndevices-1 (rfsi_predict_fused_multi:
 one band of rows per GPU inside ONE process) and must return the same bits."""
 import sys, time
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import oracle
 import rfsi_b200 as rb

@@ -2,7 +2,7 @@
 """Warp-level memory traffic of the product's 128-byte block image and of the prototype sector image
 (tools/prototypes/sector_image.cpp) for the SAME walks, on the bench workload's geometry: C5 stations,
 8 x 4 pixel patches (one warp each), a forest grown like the bench forest.  CPU only.
-python tools/prototypes/traffic_model.py [trees] [patches]"""
+python tests/tools/traffic_model.py [trees] [patches]"""
 import ctypes as C
 import subprocess
 import sys
