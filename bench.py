@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--qrf", action="store_true", help="also time mean + 3 quantiles (IQR maps) on 2 days of the band")
+    ap.add_argument("--forest-cache", default=None, help="npz file to keep the grown bench forest between runs (setup only)")
     return ap.parse_args()
 
 
@@ -62,14 +63,26 @@ def build_case(days):
     return synth.make_case("c5", ndays=max(days, TRAIN_DAYS))
 
 
-def grow(case, near_obs_fn, trees, quantreg=False):
+def grow(case, near_obs_fn, trees, quantreg=False, cache=None):
     from rfsi_b200 import grow as grower, synth
+    from rfsi_b200.forest import FlatForest
+    if cache and Path(cache).exists():
+        z = np.load(cache)
+        if int(z["ntrees"]) == trees and bool(z["quantreg"]) >= bool(quantreg):
+            log(f"[bench] forest from {cache}")
+            return FlatForest(trees, z["node_offsets"], z["left"], z["right"], z["split_var"], z["split_val"],
+                              case.feature_names, z["rnv_offsets"] if quantreg else None, z["rnv"] if quantreg else None)
     t0 = time.time()
     X, y = synth.training_table(case, near_obs_fn)
     t1 = time.time()
     flat = grower.grow_forest(X, y, case.feature_names, num_trees=trees, min_node_size=5, seed=42, quantreg=quantreg)
     log(f"[bench] training table {X.shape} in {t1 - t0:.1f}s; grew {trees} trees "
         f"({int(flat.node_offsets[-1])} nodes) in {time.time() - t1:.1f}s")
+    if cache:
+        np.savez(cache, ntrees=trees, quantreg=bool(quantreg), node_offsets=flat.node_offsets, left=flat.left, right=flat.right,
+                 split_var=flat.split_var, split_val=flat.split_val,
+                 rnv_offsets=flat.rnv_offsets if quantreg else np.zeros(0, np.int64),
+                 rnv=flat.random_node_values if quantreg else np.zeros(0))
     return flat
 
 
@@ -237,7 +250,7 @@ def main_ours(args):
         return a[:, :n], a[:, n:]
 
     if rank == 0:
-        flat = grow(case, gpu_near_obs, args.trees, quantreg=args.qrf and world == 1)
+        flat = grow(case, gpu_near_obs, args.trees, quantreg=args.qrf and world == 1, cache=args.forest_cache)
         parts = [flat.node_offsets, flat.left, flat.right, flat.split_var, flat.split_val]
     else:
         flat, parts = None, None
@@ -386,8 +399,9 @@ def main_ours(args):
     fused_ms, fused_n = prof["fused"]
     units_per_launch = P * D * args.steps / max(1, fused_n)
     achieved = b_rf * units_per_launch / (fused_ms / max(1, fused_n) * 1e-3) / 1e9 if fused_ms > 0 else None
-    image = {0: "wide 16-byte fp64 nodes", 1: "compact 8-byte rank nodes", 2: "blocked 4-byte rank nodes, 4 levels per 128-byte line"}
-    image_code = int(info.get("image", 2))
+    image = {0: "wide 16-byte fp64 nodes", 1: "compact 8-byte rank nodes", 2: "blocked 4-byte rank nodes, 4 levels per 128-byte line",
+             3: "sector image: 4-byte rank nodes, 3 levels + implicit children per 32-byte sector, leaf payload in the leaf's block"}
+    image_code = int(info.get("image", 3))
     roofline = {
         "bound": "hbm", "kernel": f"fused_kernel<256,J> on the {image[image_code]} "
                                   "(per-day candidate compaction + forest traversal)",

@@ -84,7 +84,9 @@ int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix
                           const double* obs_x, const double* obs_y, const double* obs_z,
                           int32_t nobs, int32_t n_obs, int32_t rm_dupl,
                           double* out_dist, double* out_obs, int32_t* out_idx,
-                          int32_t* warn_flag /* device int, nullable */,
+                          int32_t* warn_flag /* device int, nullable, OR-ed into: bit 0 = rows with fewer
+                                                neighbours than n.obs (NA-filled), bit 1 = locations with an NA
+                                                coordinate (their rows are NA): the caller zeroes it */,
                           int device, void* stream);
 
 /* near.obs for EVERY day of a station table in one call -- the per-day feature table, above

@@ -189,14 +189,23 @@ struct rfsi_forest {
     std::vector<int32_t> uoff;
     std::vector<double> rpar;         // [F][2] bucket function of rank_of()
     std::vector<int32_t> rtab;        // [F][kRankBuckets+1]
+    // The two block images are derived from the compact one on first use (forest_image / rfsi_forest_info), under `mu`:
+    // only the image a process actually walks is built (the sector image of the bench forest is 2.8 GB).
     // blocked format (common.cuh)
-    bool blocked_ok = false;
-    std::vector<uint32_t> blocks;     // 32 words per block, block 0 = all pass-through
-    std::vector<uint32_t> broot;      // [T]
-    // leaf tables of the blocked image: leaves renumbered left to right within each tree, so the
+    mutable int blocked_state = 0;            // 0 = not tried, 1 = built, -1 = does not fit
+    mutable std::vector<uint32_t> blocks;     // 32 words per block, block 0 = all pass-through
+    mutable std::vector<uint32_t> broot;      // [T]
+    // sector format (sector.cuh)
+    mutable int sector_state = 0;
+    mutable std::vector<uint32_t> sect;       // 8 words per block, block 0 = idle
+    mutable std::vector<uint32_t> sroot;      // [T]
+    mutable bool sect_keys = false;           // word 5 of the leaf blocks holds the quantile keys
+    // leaf tables of the block images: leaves renumbered left to right within each tree, so the
     // leaves under any subtree are contiguous (neighbouring pixels end in neighbouring leaves)
-    std::vector<double> leaf_val_c, leaf_sample_c;
-    std::vector<int32_t> leaf_rid_c;
+    mutable bool leaf_tables = false;
+    mutable std::vector<uint32_t> leaf_no;    // per device node
+    mutable std::vector<double> leaf_val_c, leaf_sample_c;
+    mutable std::vector<int32_t> leaf_rid_c;
     struct Image {
         Node* nodes = nullptr;
         double* leaf_sample = nullptr;     // per-leaf samples (fp64 form of the quantile kernel), or
@@ -205,7 +214,9 @@ struct rfsi_forest {
         int32_t* leaf_rid = nullptr;
         bool compact = false;
         bool blocked = false;
-        QForest q{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+        bool sector = false;
+        bool direct_keys = false;          // sector image whose leaf blocks carry the quantile keys (no leaf table on the device)
+        QForest q{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 32u, 0u};
     };
     mutable std::mutex mu;
     mutable std::map<int, Image> images;
@@ -255,45 +266,183 @@ void sample_ranks(const std::vector<double>& ls, std::vector<double>& dict, std:
     for (auto& x : th) x.join();
 }
 
+
+// ---- block images, derived from the compact one on first use (f->mu held) ------------------------------
+inline uint32_t rank_at(const rfsi_forest* f, const Node& nd) {
+    const double* u0 = f->uvals.data() + f->uoff[nd.feat];
+    const double* u1 = f->uvals.data() + f->uoff[nd.feat + 1];
+    return (uint32_t)(std::lower_bound(u0, u1, nd.val) - u0);
+}
+
+// leaf numbers: in-order (left to right) within each tree, trees one after the other
+void ensure_leaf_tables(const rfsi_forest* f) {
+    if (f->leaf_tables) return;
+    const int F = f->nfeat, T = f->ntrees;
+    const size_t n = f->nodes.size();
+    const bool has_s = !f->leaf_sample.empty();
+    f->leaf_no.assign(n, 0u);
+    f->leaf_val_c.clear(); f->leaf_sample_c.clear(); f->leaf_rid_c.clear();
+    f->leaf_val_c.reserve(n / 2 + T); f->leaf_rid_c.reserve(n / 2 + T);
+    if (has_s) f->leaf_sample_c.reserve(n / 2 + T);
+    std::vector<uint32_t> stack;
+    for (int t = 0; t < T; ++t) {
+        stack.assign(1, (uint32_t)t);
+        while (!stack.empty()) {
+            const uint32_t nd = stack.back();
+            stack.pop_back();
+            const Node& n0 = f->nodes[nd];
+            if (n0.feat >= F) {
+                f->leaf_no[nd] = (uint32_t)f->leaf_val_c.size();
+                f->leaf_val_c.push_back(n0.val);
+                f->leaf_rid_c.push_back(f->leaf_rid[nd]);
+                if (has_s) f->leaf_sample_c.push_back(f->leaf_sample[nd]);
+            } else {
+                stack.push_back((uint32_t)n0.child + 1);   // right, popped after the whole left subtree
+                stack.push_back((uint32_t)n0.child);
+            }
+        }
+    }
+    f->leaf_tables = true;
+}
+
+// blocked image: 4 levels per 128-byte block (common.cuh)
+bool ensure_blocked(const rfsi_forest* f) {
+    if (f->blocked_state != 0) return f->blocked_state > 0;
+    f->blocked_state = -1;
+    const int F = f->nfeat, T = f->ntrees;
+    if (!f->compact_ok || F > kBMaxFeat) return false;
+    for (int j = 0; j < F; ++j)
+        if ((size_t)(f->uoff[j + 1] - f->uoff[j]) > (size_t)kBMaxRank) return false;
+    ensure_leaf_tables(f);
+    const std::vector<uint32_t>& leaf_no = f->leaf_no;
+    std::vector<uint32_t>& B = f->blocks;
+    B.assign(32, kBPassWord);   // block 0: pass-through everywhere; its exits are never used
+    f->broot.assign((size_t)T, 0u);
+    struct Pending { uint32_t node, block; };
+    std::vector<Pending> todo;
+    bool fits = true;
+    // fill the heap of block `blk` below slot `pos` with the subtree rooted at wide node `nd`
+    auto place = [&](auto&& self, uint32_t blk, uint32_t nd, uint32_t pos) -> void {
+        const Node& n0 = f->nodes[nd];
+        const bool leaf = n0.feat >= F;
+        if (pos >= 16) {   // an exit
+            if (leaf) { B[(size_t)blk * 32 + pos] = kBLeafFlag | leaf_no[nd]; return; }
+            const size_t nb = B.size() / 32;
+            if (nb >= 0x7fffffffu) { fits = false; return; }
+            B.resize(B.size() + 32, kBPassWord);
+            B[(size_t)blk * 32 + pos] = (uint32_t)nb;
+            todo.push_back({nd, (uint32_t)nb});
+            return;
+        }
+        if (leaf) {        // pad down to the exits
+            B[(size_t)blk * 32 + pos] = kBPassWord;
+            self(self, blk, nd, 2 * pos);
+            self(self, blk, nd, 2 * pos + 1);
+            return;
+        }
+        B[(size_t)blk * 32 + pos] = ~((rank_at(f, n0) << 8) | (uint32_t)n0.feat);
+        self(self, blk, (uint32_t)n0.child, 2 * pos);
+        self(self, blk, (uint32_t)n0.child + 1, 2 * pos + 1);
+    };
+    for (int t = 0; t < T && fits; ++t) {
+        if (f->nodes[t].feat >= F) { f->broot[t] = kBLeafFlag | leaf_no[t]; continue; }
+        const size_t nb = B.size() / 32;
+        B.resize(B.size() + 32, kBPassWord);
+        f->broot[t] = (uint32_t)nb;
+        todo.clear();
+        todo.push_back({(uint32_t)t, (uint32_t)nb});
+        for (size_t i = 0; i < todo.size() && fits; ++i) {   // blocks of a tree in BFS order
+            const Pending pd = todo[i];
+            place(place, pd.block, pd.node, 1);
+        }
+    }
+    if (!fits) { B.clear(); B.shrink_to_fit(); f->broot.clear(); return false; }
+    f->blocked_state = 1;
+    return true;
+}
+
+// sector image: 3 levels per 32-byte block, implicit children, leaves are blocks (sector.cuh).  Trees are
+// independent: built on all host cores with tree-local block indices, then moved to their place.
+bool ensure_sector(const rfsi_forest* f) {
+    if (f->sector_state != 0) return f->sector_state > 0;
+    f->sector_state = -1;
+    const int F = f->nfeat, T = f->ntrees;
+    if (!f->compact_ok || F > kSMaxFeat) return false;
+    for (int j = 0; j < F; ++j)
+        if ((size_t)(f->uoff[j + 1] - f->uoff[j]) > (size_t)kSMaxRank) return false;
+    ensure_leaf_tables(f);
+    auto node_at = [&](uint32_t i) {
+        const Node& n0 = f->nodes[i];
+        SectorNode sn{n0.feat >= F, 0u, (uint32_t)n0.child, f->leaf_no[i], n0.val};
+        if (!sn.leaf) sn.word = sector_node_word(rank_at(f, n0), (uint32_t)n0.feat);
+        return sn;
+    };
+    std::vector<std::vector<uint32_t>> part((size_t)T);
+    {
+        std::atomic<int> next{0};
+        auto work = [&] { for (int t; (t = next.fetch_add(1)) < T;) sector_build_tree((uint32_t)t, node_at, part[(size_t)t]); };
+        const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (unsigned i = 0; i + 1 < hw && (int)i + 1 < T; ++i) th.emplace_back(work);
+        work();
+        for (auto& x : th) x.join();
+    }
+    size_t total = 1;
+    for (const auto& v : part) total += v.size() / 8;
+    if (total >= (size_t)0x7fffffff) return false;
+    std::vector<uint32_t>& W = f->sect;
+    W.clear();
+    W.resize(total * 8);
+    W[0] = 0u;                                          // block 0: idle, its first child is itself
+    for (int i = 1; i < 8; ++i) W[(size_t)i] = kSPassWord;
+    f->sroot.assign((size_t)T, 0u);
+    size_t at = 1;
+    for (int t = 0; t < T; ++t) {
+        std::vector<uint32_t>& v = part[(size_t)t];
+        sector_relocate(v.data(), v.size() / 8, (uint32_t)at);
+        memcpy(W.data() + at * 8, v.data(), v.size() * sizeof(uint32_t));
+        f->sroot[(size_t)t] = (uint32_t)at;
+        at += v.size() / 8;
+        std::vector<uint32_t>().swap(v);
+    }
+    f->sect_keys = false;
+    f->sector_state = 1;
+    return true;
+}
+
+// RFSI_B200_COMPACT selects the forest image: 0 = 16-byte fp64 nodes, 1 = 8-byte rank nodes, 2 = 4-byte rank nodes in
+// 128-byte blocks of 4 levels, 3 (default) = 32-byte sector blocks of 3 levels; a forest an image cannot hold falls
+// back to the next lower one.  Returns the image in use (and builds it).
+int forest_image_code(const rfsi_forest* f) {
+    const int want = env_int("RFSI_B200_COMPACT", 3);
+    if (!f->compact_ok || want <= 0) return 0;
+    if (want >= 3 && ensure_sector(f)) return 3;
+    if (want >= 2 && ensure_blocked(f)) return 2;
+    return 1;
+}
+
 int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
     std::lock_guard<std::mutex> lk(f->mu);
     auto it = f->images.find(device);
     if (it != f->images.end()) { *out = it->second; return RFSI_OK; }
     rfsi_forest::Image im;
-    // RFSI_B200_COMPACT: 0 = 16-byte fp64 nodes, 1 = 8-byte rank nodes, 2 (default) = 4-byte blocked
-    const int want = env_int("RFSI_B200_COMPACT", 2);
-    im.compact = f->compact_ok && want != 0;
-    const bool blocked = im.compact && f->blocked_ok && want >= 2;
-    im.blocked = blocked;
-    if (im.compact) {
-        auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
-            void* d = nullptr;
-            CU_TRY(cudaMalloc(&d, bytes ? bytes : 8));
-            CU_TRY(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
-            *dst = d;
-            return RFSI_OK;
-        };
-        if (blocked) {
-            RF_TRY(up(f->blocks.data(), f->blocks.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.blocks)));
-            RF_TRY(up(f->broot.data(), f->broot.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.broot)));
-            im.q.rank_shift = 8;
-        } else {
-            RF_TRY(up(f->qnodes.data(), f->qnodes.size() * sizeof(uint64_t), reinterpret_cast<const void**>(&im.q.nodes)));
-        }
-        RF_TRY(up(f->qroots.data(), f->qroots.size() * sizeof(QRoot), reinterpret_cast<const void**>(&im.q.roots)));
-        const std::vector<double>& lv = blocked ? f->leaf_val_c : f->leaf_val;
-        RF_TRY(up(lv.data(), lv.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.leaf_val)));
-        RF_TRY(up(f->uvals.data(), f->uvals.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.uvals)));
-        RF_TRY(up(f->uoff.data(), f->uoff.size() * sizeof(int32_t), reinterpret_cast<const void**>(&im.q.uoff)));
-        RF_TRY(up(f->rpar.data(), f->rpar.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.rpar)));
-        RF_TRY(up(f->rtab.data(), f->rtab.size() * sizeof(int32_t), reinterpret_cast<const void**>(&im.q.rtab)));
-    } else {
-        CU_TRY(cudaMalloc(&im.nodes, f->nodes.size() * sizeof(Node)));
-        CU_TRY(cudaMemcpy(im.nodes, f->nodes.data(), f->nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
-    }
+    const int code = forest_image_code(f);
+    im.compact = code >= 1;
+    im.blocked = code == 2;
+    im.sector = code == 3;
+    const bool renumbered = code >= 2;     // leaf tables indexed by the in-order leaf number
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+        void* d = nullptr;
+        CU_TRY(cudaMalloc(&d, bytes ? bytes : 8));
+        CU_TRY(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+        *dst = d;
+        return RFSI_OK;
+    };
+    // quantile samples first: the sector image carries their dictionary ranks inside its leaf blocks
+    const bool ranks = !f->leaf_sample.empty() && env_int("RFSI_B200_QRF_RANKS", 1) != 0;
     if (!f->leaf_sample.empty()) {
-        const std::vector<double>& ls = blocked ? f->leaf_sample_c : f->leaf_sample;
-        if (env_int("RFSI_B200_QRF_RANKS", 1) != 0 && ls.size() < 0xFFFFFFFFull) {
+        const std::vector<double>& ls = renumbered ? f->leaf_sample_c : f->leaf_sample;
+        if (ranks && ls.size() < 0xFFFFFFFFull) {
             // 4-byte form: the distinct sample values (at most one per training row) sorted in
             // the total order of their bit patterns (-0.0 < +0.0 stay distinct entries, so the
             // values that come back are the very doubles ranger stored), and each leaf's rank
@@ -301,14 +450,48 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
             std::vector<double>& dict = f->sample_dict_h;
             std::vector<uint32_t>& rank = f->leaf_rank_h;
             if (rank.size() != ls.size()) sample_ranks(ls, dict, rank);
-            CU_TRY(cudaMalloc(&im.leaf_rank, std::max<size_t>(rank.size(), 1) * sizeof(uint32_t)));
-            CU_TRY(cudaMemcpy(im.leaf_rank, rank.data(), rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            if (im.sector) {
+                if (!f->sect_keys) {       // key of every leaf into word 5 of its block
+                    uint32_t* W = f->sect.data();
+                    const size_t nb = f->sect.size() / 8;
+                    for (size_t b = 1; b < nb; ++b)
+                        if (W[b * 8] & kSLeafFlag) W[b * 8 + kSWordKey] = rank[W[b * 8 + kSWordLeafNo]];
+                    f->sect_keys = true;
+                }
+                im.direct_keys = true;     // no per-leaf table on the device at all
+            } else {
+                CU_TRY(cudaMalloc(&im.leaf_rank, std::max<size_t>(rank.size(), 1) * sizeof(uint32_t)));
+                CU_TRY(cudaMemcpy(im.leaf_rank, rank.data(), rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            }
             CU_TRY(cudaMalloc(&im.sample_dict, std::max<size_t>(dict.size(), 1) * sizeof(double)));
             CU_TRY(cudaMemcpy(im.sample_dict, dict.data(), dict.size() * sizeof(double), cudaMemcpyHostToDevice));
         } else {
             CU_TRY(cudaMalloc(&im.leaf_sample, ls.size() * sizeof(double)));
             CU_TRY(cudaMemcpy(im.leaf_sample, ls.data(), ls.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
+    }
+    if (im.compact) {
+        if (im.sector) {
+            RF_TRY(up(f->sect.data(), f->sect.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.sect)));
+            RF_TRY(up(f->sroot.data(), f->sroot.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.sroot)));
+            im.q.rank_shift = 8;
+        } else if (im.blocked) {
+            RF_TRY(up(f->blocks.data(), f->blocks.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.blocks)));
+            RF_TRY(up(f->broot.data(), f->broot.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.broot)));
+            im.q.rank_shift = 8;
+            RF_TRY(up(f->leaf_val_c.data(), f->leaf_val_c.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.leaf_val)));
+        } else {
+            RF_TRY(up(f->qnodes.data(), f->qnodes.size() * sizeof(uint64_t), reinterpret_cast<const void**>(&im.q.nodes)));
+            RF_TRY(up(f->qroots.data(), f->qroots.size() * sizeof(QRoot), reinterpret_cast<const void**>(&im.q.roots)));
+            RF_TRY(up(f->leaf_val.data(), f->leaf_val.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.leaf_val)));
+        }
+        RF_TRY(up(f->uvals.data(), f->uvals.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.uvals)));
+        RF_TRY(up(f->uoff.data(), f->uoff.size() * sizeof(int32_t), reinterpret_cast<const void**>(&im.q.uoff)));
+        RF_TRY(up(f->rpar.data(), f->rpar.size() * sizeof(double), reinterpret_cast<const void**>(&im.q.rpar)));
+        RF_TRY(up(f->rtab.data(), f->rtab.size() * sizeof(int32_t), reinterpret_cast<const void**>(&im.q.rtab)));
+    } else {
+        CU_TRY(cudaMalloc(&im.nodes, f->nodes.size() * sizeof(Node)));
+        CU_TRY(cudaMemcpy(im.nodes, f->nodes.data(), f->nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
     }
     f->images[device] = im;
     *out = im;
@@ -320,7 +503,7 @@ int forest_leaf_rid(const rfsi_forest* f, int device, const int32_t** out) {
     std::lock_guard<std::mutex> lk(f->mu);
     rfsi_forest::Image& im = f->images[device];
     if (!im.leaf_rid) {
-        const std::vector<int32_t>& lr = im.blocked ? f->leaf_rid_c : f->leaf_rid;
+        const std::vector<int32_t>& lr = (im.blocked || im.sector) ? f->leaf_rid_c : f->leaf_rid;
         CU_TRY(cudaMalloc(&im.leaf_rid, lr.size() * sizeof(int32_t)));
         CU_TRY(cudaMemcpy(im.leaf_rid, lr.data(), lr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
@@ -417,81 +600,6 @@ void build_compact(rfsi_forest* f) {
     }
     if (!ok) { f->qnodes.clear(); f->qroots.clear(); f->leaf_val.clear(); return; }
     f->compact_ok = true;
-
-    // ---- blocked image: 4 levels per 128-byte block (common.cuh) ----
-    f->blocked_ok = false;
-    if (F > kBMaxFeat) return;
-    for (int j = 0; j < F; ++j)
-        if (u[j].size() > (size_t)kBMaxRank) return;
-    // leaf numbers: in-order (left to right) within each tree, trees one after the other
-    std::vector<uint32_t> leaf_no(n, 0u);
-    {
-        const bool has_s = !f->leaf_sample.empty();
-        f->leaf_val_c.clear(); f->leaf_sample_c.clear(); f->leaf_rid_c.clear();
-        f->leaf_val_c.reserve(n / 2 + T); f->leaf_rid_c.reserve(n / 2 + T);
-        if (has_s) f->leaf_sample_c.reserve(n / 2 + T);
-        std::vector<uint32_t> stack;
-        for (int t = 0; t < T; ++t) {
-            stack.assign(1, (uint32_t)t);
-            while (!stack.empty()) {
-                const uint32_t nd = stack.back();
-                stack.pop_back();
-                const Node& n0 = f->nodes[nd];
-                if (n0.feat >= F) {
-                    leaf_no[nd] = (uint32_t)f->leaf_val_c.size();
-                    f->leaf_val_c.push_back(n0.val);
-                    f->leaf_rid_c.push_back(f->leaf_rid[nd]);
-                    if (has_s) f->leaf_sample_c.push_back(f->leaf_sample[nd]);
-                } else {
-                    stack.push_back((uint32_t)n0.child + 1);   // right, popped after the whole left subtree
-                    stack.push_back((uint32_t)n0.child);
-                }
-            }
-        }
-    }
-    std::vector<uint32_t>& B = f->blocks;
-    B.assign(32, kBPassWord);   // block 0: pass-through everywhere; its exits are never used
-    f->broot.assign((size_t)T, 0u);
-    struct Pending { uint32_t node, block; };
-    std::vector<Pending> todo;
-    bool fits = true;
-    // fill the heap of block `blk` below slot `pos` with the subtree rooted at wide node `nd`
-    auto place = [&](auto&& self, uint32_t blk, uint32_t nd, uint32_t pos) -> void {
-        const Node& n0 = f->nodes[nd];
-        const bool leaf = n0.feat >= F;
-        if (pos >= 16) {   // an exit
-            if (leaf) { B[(size_t)blk * 32 + pos] = kBLeafFlag | leaf_no[nd]; return; }
-            const size_t nb = B.size() / 32;
-            if (nb >= 0x7fffffffu) { fits = false; return; }
-            B.resize(B.size() + 32, kBPassWord);
-            B[(size_t)blk * 32 + pos] = (uint32_t)nb;
-            todo.push_back({nd, (uint32_t)nb});
-            return;
-        }
-        if (leaf) {        // pad down to the exits
-            B[(size_t)blk * 32 + pos] = kBPassWord;
-            self(self, blk, nd, 2 * pos);
-            self(self, blk, nd, 2 * pos + 1);
-            return;
-        }
-        B[(size_t)blk * 32 + pos] = ~((rank_at(n0) << 8) | (uint32_t)n0.feat);
-        self(self, blk, (uint32_t)n0.child, 2 * pos);
-        self(self, blk, (uint32_t)n0.child + 1, 2 * pos + 1);
-    };
-    for (int t = 0; t < T && fits; ++t) {
-        if (f->nodes[t].feat >= F) { f->broot[t] = kBLeafFlag | leaf_no[t]; continue; }
-        const size_t nb = B.size() / 32;
-        B.resize(B.size() + 32, kBPassWord);
-        f->broot[t] = (uint32_t)nb;
-        todo.clear();
-        todo.push_back({(uint32_t)t, (uint32_t)nb});
-        for (size_t i = 0; i < todo.size() && fits; ++i) {   // blocks of a tree in BFS order
-            const Pending pd = todo[i];
-            place(place, pd.block, pd.node, 1);
-        }
-    }
-    if (!fits) { B.clear(); f->broot.clear(); return; }
-    f->blocked_ok = true;
 }
 
 }  // namespace
@@ -596,6 +704,7 @@ extern "C" void rfsi_forest_destroy(rfsi_forest_t* f) {
             cudaFree(const_cast<int32_t*>(kv.second.q.uoff));
             cudaFree(const_cast<double*>(kv.second.q.rpar)); cudaFree(const_cast<int32_t*>(kv.second.q.rtab));
             cudaFree(const_cast<uint32_t*>(kv.second.q.blocks)); cudaFree(const_cast<uint32_t*>(kv.second.q.broot));
+            cudaFree(const_cast<uint32_t*>(kv.second.q.sect)); cudaFree(const_cast<uint32_t*>(kv.second.q.sroot));
         }
         cudaSetDevice(cur);
     }
@@ -617,18 +726,24 @@ extern "C" int64_t rfsi_forest_info(const rfsi_forest_t* f, int what) {
         case 2: return (int64_t)f->nodes.size();
         case 3: return f->max_depth;
         case 4: return f->leaf_sample.empty() ? 0 : 1;
-        case 5:
-            if (f->compact_ok && f->blocked_ok && env_int("RFSI_B200_COMPACT", 2) >= 2)
-                return (int64_t)(f->blocks.size() * 4 + f->leaf_val_c.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
-                                 f->leaf_sample_c.size() * sample_entry_bytes());
-            if (f->compact_ok && env_int("RFSI_B200_COMPACT", 2) != 0)
-                return (int64_t)(f->qnodes.size() * 8 + f->leaf_val.size() * 8 + f->uvals.size() * 8 + f->rtab.size() * 4 +
-                                 f->qroots.size() * sizeof(QRoot) + f->leaf_sample.size() * sample_entry_bytes());
+        case 5: case 7: case 9: {
+            std::lock_guard<std::mutex> lk(f->mu);
+            const int code = forest_image_code(f);
+            if (what == 7) return code;
+            if (what == 9) return code == 3 ? (int64_t)f->sect.size() / 8 : (code == 2 ? (int64_t)f->blocks.size() / 32 : 0);
+            const int64_t tabs = (int64_t)(f->uvals.size() * 8 + f->rtab.size() * 4);
+            const bool ranks = env_int("RFSI_B200_QRF_RANKS", 1) != 0;
+            if (code == 3)   // values, numbers and quantile keys live in the leaf blocks; the fp64 form keeps its table
+                return (int64_t)(f->sect.size() * 4) + tabs + (ranks ? 0 : (int64_t)f->leaf_sample_c.size() * 8);
+            if (code == 2)
+                return (int64_t)(f->blocks.size() * 4 + f->leaf_val_c.size() * 8) + tabs +
+                       (int64_t)(f->leaf_sample_c.size() * sample_entry_bytes());
+            if (code == 1)
+                return (int64_t)(f->qnodes.size() * 8 + f->leaf_val.size() * 8 + f->qroots.size() * sizeof(QRoot)) + tabs +
+                       (int64_t)(f->leaf_sample.size() * sample_entry_bytes());
             return (int64_t)(f->nodes.size() * sizeof(Node) + f->leaf_sample.size() * sample_entry_bytes());
+        }
         case 6: return f->n_internal;
-        case 7: return !(f->compact_ok && env_int("RFSI_B200_COMPACT", 2) != 0) ? 0
-                       : ((f->blocked_ok && env_int("RFSI_B200_COMPACT", 2) >= 2) ? 2 : 1);
-        case 9: return (int64_t)f->blocks.size() / 32;
         case 8: return (int64_t)f->uvals.size();
         default: return -1;
     }
@@ -820,7 +935,7 @@ int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, const int
 // trees in flight per thread: measured best 12 for the 16-byte format, 8 for the compact one
 thread_local int g_default_J = 12;
 int forest_J() {
-    static int j = env_int("RFSI_B200_J", 0);
+    const int j = env_int("RFSI_B200_J", 0);
     return j > 0 ? j : g_default_J;
 }
 
@@ -841,10 +956,12 @@ std::vector<int> tree_chunks(const rfsi_forest* f) {
 }
 
 template <int P, int J>
-int launch_forest_xq_pj(const rfsi_forest* f, const QForest& q, const double* X, int64_t npix, int64_t ldx,
+int launch_forest_xq_pj(const rfsi_forest* f, const QForest& q_in, const double* X, int64_t npix, int64_t ldx,
                         const ForestOut& o, unsigned long long* visits, int* na_flag, cudaStream_t stream)
 {
     const int T = f->ntrees, F = f->nfeat;
+    QForest q = q_in;
+    q.sect_tile_stride = (uint32_t)(P * sizeof(uint32_t));
     const size_t smem = forest_q_smem_bytes<P>(F);
     const unsigned grid = (unsigned)((npix + P - 1) / P);
     const std::vector<int> cb = tree_chunks(f);
@@ -929,12 +1046,12 @@ constexpr int kMaxProbs = 128;
 inline int64_t leaf_ids_ld(int T) { return ((int64_t)T + 7) & ~int64_t(7); }
 inline size_t leaf_ids_bytes(int64_t rows, int T) { return sizeof(uint32_t) * (size_t)rows * (size_t)leaf_ids_ld(T); }
 
-template <int R, class K>
+template <int R, class K, bool DIRECT>
 int launch_qrf_r(const uint32_t* leaf_ids, const K* leaf_key, const double* dict, const unsigned char* skip, int64_t nrows,
                  int T, const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr,
                  cudaStream_t stream)
 {
-    auto kern = qrf_quantile_kernel<R, K>;
+    auto kern = qrf_quantile_kernel<R, K, DIRECT>;
     const size_t smem = qrf_smem_bytes<R, K>();
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, per_sm = 0;
@@ -949,34 +1066,19 @@ int launch_qrf_r(const uint32_t* leaf_ids, const K* leaf_key, const double* dict
     return RFSI_OK;
 }
 
-// strip form of the quantile kernel (qrf.cuh): rank keys, up to 512 trees
-template <int R>
-int launch_qrf_strip(const uint32_t* leaf_ids, const uint32_t* leaf_rank, const double* dict, const unsigned char* skip,
-                     int64_t nrows, int T, const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr,
-                     cudaStream_t stream)
-{
-    auto kern = qrf_quantile_strip_kernel<R>;
-    const size_t smem = qrf_strip_smem<R>();
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 0, per_sm = 0;
-    CU_TRY(cudaGetDevice(&dev));
-    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kStripRows, smem));
-    const int64_t groups = (nrows + kStripRows - 1) / kStripRows;   // persistent CTAs, a contiguous run of tiles each
-    const unsigned grid = (unsigned)std::min<int64_t>(groups, (int64_t)sms * std::max(per_sm, 1));
-    kern<<<grid, 32 * kStripRows, smem, stream>>>(leaf_ids, leaf_ids_ld(T), leaf_rank, dict, skip, nrows, T, probs_dev, nprobs,
-                                                  out_q, ld_q, out_iqr);
-    return RFSI_OK;
-}
-
 // the leaf table of an image in whichever form it was uploaded (ranks by default)
 struct LeafSamples {
     const double* sample = nullptr;
     const uint32_t* rank = nullptr;
     const double* dict = nullptr;
-    explicit operator bool() const { return sample || rank; }
+    bool direct = false;      // the walk stored the keys themselves (sector image): nothing to gather
+    explicit operator bool() const { return sample || rank || direct; }
 };
-inline LeafSamples leaf_samples(const rfsi_forest::Image& im) { return LeafSamples{im.leaf_sample, im.leaf_rank, im.sample_dict}; }
+inline LeafSamples leaf_samples(const rfsi_forest::Image& im) {
+    return LeafSamples{im.leaf_sample, im.leaf_rank, im.sample_dict, im.direct_keys};
+}
+// the word of a sector leaf block the walk stores for the quantile pass
+inline int leaf_ids_word(const rfsi_forest::Image& im) { return im.direct_keys ? kSWordKey : kSWordLeafNo; }
 
 int launch_qrf(const uint32_t* leaf_ids, const LeafSamples& ls, const unsigned char* skip, int64_t nrows, int T,
                const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr, cudaStream_t stream)
@@ -984,17 +1086,14 @@ int launch_qrf(const uint32_t* leaf_ids, const LeafSamples& ls, const unsigned c
     if (nrows == 0) return RFSI_OK;
     const int R = (T + 31) / 32;
     ProfScope ps(PROF_QRF, stream);
-    // strip form: parity-green but measured slower (18.8 vs 15.3 ms per 4e6 rows): opt-in
-    static const int strip = env_int("RFSI_B200_QRF_STRIP", 0);
 #define RFSI_QRF_CASE(RR)                                                                                              \
     do {                                                                                                               \
-        if (ls.rank && strip && RR <= 16)                                                                              \
-            RF_TRY((launch_qrf_strip<(RR <= 16 ? RR : 16)>(leaf_ids, ls.rank, ls.dict, skip, nrows, T, probs_dev, nprobs, \
-                                                           out_q, ld_q, out_iqr, stream)));                            \
-        else if (ls.rank) RF_TRY((launch_qrf_r<RR, uint32_t>(leaf_ids, ls.rank, ls.dict, skip, nrows, T, probs_dev, nprobs,  \
-                                                         out_q, ld_q, out_iqr, stream)));                              \
-        else RF_TRY((launch_qrf_r<RR, double>(leaf_ids, ls.sample, nullptr, skip, nrows, T, probs_dev, nprobs, out_q,   \
-                                              ld_q, out_iqr, stream)));                                                \
+        if (ls.direct) RF_TRY((launch_qrf_r<RR, uint32_t, true>(leaf_ids, nullptr, ls.dict, skip, nrows, T, probs_dev, nprobs, \
+                                                                out_q, ld_q, out_iqr, stream)));                       \
+        else if (ls.rank) RF_TRY((launch_qrf_r<RR, uint32_t, false>(leaf_ids, ls.rank, ls.dict, skip, nrows, T, probs_dev, nprobs, \
+                                                                    out_q, ld_q, out_iqr, stream)));                   \
+        else RF_TRY((launch_qrf_r<RR, double, false>(leaf_ids, ls.sample, nullptr, skip, nrows, T, probs_dev, nprobs, out_q, \
+                                                     ld_q, out_iqr, stream)));                                         \
     } while (0)
     if (R <= 1) RFSI_QRF_CASE(1);
     else if (R <= 2) RFSI_QRF_CASE(2);
@@ -1057,12 +1156,12 @@ extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, i
         if (rc >= 0) rc = build_loc_perm(L, npix, pw, &perm, st);
         if (rc >= 0)
             rc = launch_knn_cells<KNN_FINAL>(L, npix, c, perm, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx,
-                                             npix, warn_flag, nullptr, st);
+                                             npix, warn_flag, warn_flag, st);
         cudaFreeAsync(cw, st);
         if (pw) cudaFreeAsync(pw, st);
     } else {
         rc = launch_knn<KNN_FINAL>(L, npix, xy, nobs, n_obs + 1, obs_z, rm_dupl, out_dist, out_obs, out_idx, npix,
-                                   warn_flag, nullptr, st);
+                                   warn_flag, warn_flag, st);
     }
     cudaFreeAsync(xy, st);   // stream-ordered: released after the kernels above have run
     return rc;
@@ -1260,8 +1359,8 @@ extern "C" int rfsi_near_obs_days_f64(const double* loc_x, const double* loc_y, 
     for (int32_t s = 0; s < S; ++s) xy[s] = make_double2(obs_x[s], obs_y[s]);
     const int64_t chunk = std::min<int64_t>(npix, 1 << 18);
     const int db = (int)std::max<int64_t>(1, std::min<int64_t>(ndays, (int64_t(256) << 20) / (chunk * n_obs * 20)));
-    DevBuf d_xy, d_z, d_lx, d_ly, d_cd2, d_cid, d_cells, d_dist, d_obs, d_idx, d_flags;
-    Stream st;
+    DevBuf d_xy, d_z, d_lx, d_ly, d_cd2, d_cid, d_cells, d_dist, d_obs, d_idx, d_flags, d_perm;
+    Stream st;   // declared after every buffer its work touches: destroyed (and synchronised) first on any return
     RF_TRY(st.create());
     RF_TRY(d_xy.alloc(sizeof(double2) * xy.size()));
     RF_TRY(d_z.alloc(sizeof(double) * (size_t)std::max(S, 1) * ndays));
@@ -1272,7 +1371,6 @@ extern "C" int rfsi_near_obs_days_f64(const double* loc_x, const double* loc_y, 
     RF_TRY(d_flags.alloc(16));
     const bool use_cells = S >= cells_min_S();
     CellsWs cells;
-    DevBuf d_perm;
     if (use_cells) {
         RF_TRY(d_cells.alloc(cells_ws_bytes(S)));
         cells = carve_cells(d_cells.p, S);
@@ -1343,7 +1441,8 @@ extern "C" int rfsi_near_obs_days_f64(const double* loc_x, const double* loc_y, 
 // ------------------------------------------------------------------------------------
 extern "C" size_t rfsi_dev_forest_scratch_bytes(const rfsi_forest_t* f, int64_t npix, int32_t nprobs) {
     if (!f || npix <= 0 || nprobs <= 0) return 256;
-    return align_up(leaf_ids_bytes(npix, f->ntrees), 256) + align_up(sizeof(double) * kMaxProbs, 256);
+    return align_up(leaf_ids_bytes(npix, f->ntrees), 256) + align_up(sizeof(double) * kMaxProbs, 256) +
+           align_up((size_t)npix, 256);   // leaf ids | quantile levels | per-row skip bytes
 }
 
 extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t ldx,
@@ -1357,7 +1456,7 @@ extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, 
     rfsi_forest::Image im;
     RF_TRY(forest_image(f, device, &im));
     cudaStream_t st = (cudaStream_t)stream;
-    ForestOut o{out_mean, nullptr, leaf_ids_ld(f->ntrees), out_terminal, nullptr, npix};
+    ForestOut o{out_mean, nullptr, leaf_ids_ld(f->ntrees), out_terminal, nullptr, npix, leaf_ids_word(im), nullptr};
     if (out_terminal) RF_TRY(forest_leaf_rid(f, device, &o.leaf_rid));
     double* probs_dev = nullptr;
     if (out_q) {
@@ -1368,10 +1467,12 @@ extern "C" int rfsi_dev_forest_predict(const rfsi_forest_t* f, const double* X, 
         o.leaf_ids = reinterpret_cast<uint32_t*>(scratch);
         probs_dev = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) +
                                               align_up(leaf_ids_bytes(npix, f->ntrees), 256));
+        // rows with NA in a used column are not walked: their leaf ids are never written and the quantile pass skips them
+        o.row_skip = reinterpret_cast<unsigned char*>(probs_dev) + align_up(sizeof(double) * kMaxProbs, 256);
         CU_TRY(cudaMemcpyAsync(probs_dev, probs_host, sizeof(double) * nprobs, cudaMemcpyHostToDevice, st));
     }
     RF_TRY(launch_forest_x(f, im, X, npix, ldx, o, visits, na_flag, st));
-    if (out_q) RF_TRY(launch_qrf(o.leaf_ids, leaf_samples(im), nullptr, npix, f->ntrees, probs_dev, nprobs, out_q, npix, nullptr, st));
+    if (out_q) RF_TRY(launch_qrf(o.leaf_ids, leaf_samples(im), o.row_skip, npix, f->ntrees, probs_dev, nprobs, out_q, npix, nullptr, st));
     return RFSI_OK;
 }
 
@@ -1574,6 +1675,20 @@ int validate_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
                     return fail(RFSI_E_ARG, "fused: covariate raster %d has %d layers for %d days", c,
                                 a->cov_raster[c].nlayers, a->ndays);
             }
+    if (a->ncov > 0) {
+        const bool any_plain = [&] {
+            for (int c = 0; c < a->ncov; ++c)
+                if (!(a->cov_raster && a->cov_raster[c].data)) return true;
+            return false;
+        }();
+        if (any_plain && (!a->cov || !a->cov_day_stride))
+            return fail(RFSI_E_ARG, "fused: ncov = %d but cov / cov_day_stride is NULL", a->ncov);
+        for (int c = 0; c < a->ncov; ++c)
+            if (!(a->cov_raster && a->cov_raster[c].data) && a->npix > 0 && !a->cov[c])
+                return fail(RFSI_E_ARG, "fused: covariate %d has neither a column (cov[%d] is NULL) nor a raster", c, c);
+    }
+    if (a->npix > 0 && !a->out_mean && !a->out_q && !a->out_mean_i16 && !a->out_iqr_i16)
+        return fail(RFSI_E_ARG, "fused: no output requested (out_mean, out_q, out_mean_i16, out_iqr_i16 are all NULL)");
     if ((a->cov_loc_x == nullptr) != (a->cov_loc_y == nullptr)) return fail(RFSI_E_ARG, "fused: cov_loc_x/cov_loc_y go together");
     if (a->ncov_fix < 0 || (a->ncov_fix > 0 && !a->cov_fix)) return fail(RFSI_E_ARG, "fused: bad cov_fix list");
     for (int k = 0; k < a->ncov_fix; ++k) {
@@ -1634,7 +1749,9 @@ int kc_extra_default() {
 }
 
 template <int P, int J, bool FALLBACK, bool Q>
-int launch_fused_pj(const FusedParams& fp, unsigned grid, int k, bool count, cudaStream_t st) {
+int launch_fused_pj(const FusedParams& fp_in, unsigned grid, int k, bool count, cudaStream_t st) {
+    FusedParams fp = fp_in;
+    fp.q.sect_tile_stride = (uint32_t)(P * sizeof(uint32_t));
     const size_t smem = fused_smem_bytes<P, Q>(fp.F, k, FALLBACK);
     ProfScope ps(FALLBACK ? PROF_FALLBACK : PROF_FUSED, st);
     const int carve = env_int("RFSI_B200_CARVEOUT", -1);   // experiment knob: shared-memory carveout in percent
@@ -1711,10 +1828,10 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
             const CellsWs c = carve_cells(ws + pl.off_cells, a->nobs);
             RF_TRY(build_cells(xy, a->nobs, c, st));
             RF_TRY(launch_knn_cells<KNN_RAW>(L, a->npix, c, perm, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id,
-                                             a->npix, nullptr, nullptr, st));
+                                             a->npix, nullptr, na_flag, st));
         } else {
             RF_TRY(launch_knn<KNN_RAW>(L, a->npix, xy, a->nobs, pl.KC, nullptr, 0, cand_d2, nullptr, cand_id, a->npix,
-                                       nullptr, nullptr, st));
+                                       nullptr, na_flag, st));
         }
     }
     if (pl.want_q)
@@ -1774,6 +1891,7 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         fp.out_mean = a->out_mean ? a->out_mean + obase : nullptr;
         fp.out_mean_i16 = a->out_mean_i16 ? a->out_mean_i16 + obase : nullptr;
         fp.leaf_ids = leaf_ids; fp.ld_ids = leaf_ids_ld(f->ntrees); fp.row_skip = skip;
+        fp.ids_word = leaf_ids_word(im);
         CU_TRY(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int), st));
         const unsigned grid = (unsigned)(ntiles * nd);
         for (size_t c = 0; c + 1 < cb.size(); ++c) {  // one sweep of all tiles per L2-sized forest chunk
@@ -2052,6 +2170,7 @@ int host_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device, i
         CU_TRY(cudaMemcpy(&v, reinterpret_cast<char*>(slot[s].ws.p) + pl.off_misc + 16, sizeof v, cudaMemcpyDeviceToHost));
         na |= v;
     }
+    if (na & 2) return fail(RFSI_E_NA_INPUT, "fused: a location has an NA coordinate (outputs NA there)");
     if (na) return fail(RFSI_E_NA_INPUT, "fused: missing data in a covariate column the forest uses (outputs NA there)");
     if (cnt[3]) {
         char buf[160];

@@ -17,6 +17,7 @@
 // order in fp64, which makes the mean bit-identical to the sequential CPU sum.
 #pragma once
 #include "common.cuh"
+#include "sector.cuh"
 
 namespace rfsi {
 
@@ -31,7 +32,11 @@ struct QForest {
     const int32_t* rtab;      // [F][kRankBuckets+1] number of thresholds in buckets < b
     const uint32_t* blocks;   // blocked format (common.cuh): 32 words per block; nullptr = use `nodes`
     const uint32_t* broot;    // [T] root block of each tree (or a leaf marker)
-    int rank_shift;           // ranks are stored in shared memory shifted left by this (8 when blocked)
+    int rank_shift;           // ranks are stored in shared memory shifted left by this (8 when blocked / sector)
+    const uint32_t* sect;     // sector format (sector.cuh): 8 words per block; nullptr = use `blocks` / `nodes`
+    const uint32_t* sroot;    // [T] root block of each tree
+    uint32_t sect_block_bytes;  // 32, and the byte stride between features of the rank tile (4 * pixels per CTA):
+    uint32_t sect_tile_stride;  // run-time values on purpose, see SectorView
 };
 
 // number of thresholds of feature f strictly below x (x is never NaN here).  The bucket
@@ -57,6 +62,9 @@ struct ForestOut {
     int32_t* terminal;        // [T][ld_term] tree-local terminal node ids (nullable)
     const int32_t* leaf_rid;  // per device-node ranger node id, needed if terminal
     long long ld_term;
+    int ids_word;             // sector image: the word of the leaf block that goes into leaf_ids (leaf number, or
+                              // the quantile key itself: the quantile kernel then has nothing left to gather)
+    unsigned char* row_skip;  // [npix] matrix-input kernels: 1 = the row has NA in a used column (nullable)
 };
 
 // Quantile path: the leaves one group of J trees ended in, 4 bytes per tree (the sample
@@ -244,6 +252,40 @@ __device__ __forceinline__ double traverse_b(const QForest& q, int t_begin, int 
     return sum;
 }
 
+// Sector-format walk (sector.cuh): the leaf's value, number and quantile key sit in the leaf's own block.
+template <int P, int J, bool COUNT>
+__device__ __forceinline__ double traverse_sect(const QForest& q, int t_begin, int t_end, int T, double sum,
+                                                const uint32_t* __restrict__ rs, const ForestOut& o, long long row,
+                                                unsigned& nvisit)
+{
+    const SectorView v{q.sect, q.sroot, q.sect_block_bytes, q.sect_tile_stride};
+    auto sink = [&](int t0, int remaining, const uint32_t (&lb)[J]) {
+        if (o.terminal) {
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+                if (j < remaining)
+                    o.terminal[(long long)(t0 + j) * o.ld_term + row] = o.leaf_rid[__ldg(q.sect + (size_t)lb[j] * 8u + kSWordLeafNo)];
+        }
+        if (o.leaf_ids) {
+            uint32_t key[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) key[j] = __ldg(q.sect + (size_t)lb[j] * 8u + o.ids_word);
+            store_leaf_ids<J>(o, row * o.ld_ids + t0, remaining, key);
+        }
+    };
+    return traverse_s<P, J, COUNT>(v, t_begin, t_end, sum, rs, sink, nvisit);
+}
+
+// A row with NA/NaN in a column the forest uses (ranger: "Missing data in columns ..." is an error): nothing is
+// walked; every output of the row is NA, the quantile pass is told to skip it, and the host reports RFSI_E_NA_INPUT.
+__device__ __forceinline__ void forest_na_row(const ForestOut& o, long long p, int t_begin, int t_end, int* na_flag) {
+    if (na_flag) *na_flag = 1;
+    if (o.mean) o.mean[p] = na_real();
+    if (o.row_skip) o.row_skip[p] = 1;
+    if (o.terminal)
+        for (int t = t_begin; t < t_end; ++t) o.terminal[(long long)t * o.ld_term + p] = kNaInteger;
+}
+
 template <int P>
 __host__ __device__ constexpr size_t forest_q_smem_bytes(int F) {
     return (size_t)F * P * sizeof(uint32_t);
@@ -270,13 +312,14 @@ forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* 
     unsigned nvisit = 0;
     if (in_range) {
         if (has_na) {
-            if (na_flag) *na_flag = 1;
-            if (o.mean) o.mean[p] = na_real();
+            forest_na_row(o, p, t_begin, t_end, na_flag);
         } else {
             double sum = (t_begin > 0 && o.mean) ? o.mean[p] : 0.0;
-            if (q.blocks) sum = traverse_b<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
+            if (q.sect) sum = traverse_sect<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
+            else if (q.blocks) sum = traverse_b<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
             else sum = traverse_q<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
             if (o.mean) o.mean[p] = (t_end == T) ? sum / (double)T : sum;
+            if (o.row_skip) o.row_skip[p] = 0;
         }
     }
     if (COUNT && visits) {
@@ -317,12 +360,12 @@ forest_x_kernel(const Node* __restrict__ nodes, int t_begin, int t_end, int T, i
     unsigned nvisit = 0;
     if (in_range) {
         if (has_na) {
-            if (na_flag) *na_flag = 1;  // ranger: "Missing data in columns" -> error upstream
-            if (o.mean) o.mean[p] = na_real();
+            forest_na_row(o, p, t_begin, t_end, na_flag);
         } else {
             double sum = (t_begin > 0 && o.mean) ? o.mean[p] : 0.0;
             sum = traverse_all<P, J, COUNT>(nodes, t_begin, t_end, T, F, sum, fs, o, p, nvisit);
             if (o.mean) o.mean[p] = (t_end == T) ? sum / (double)T : sum;
+            if (o.row_skip) o.row_skip[p] = 0;
         }
     }
     if (COUNT && visits) {

@@ -58,6 +58,7 @@ struct FusedParams {
     int16_t* out_mean_i16;
     uint32_t* leaf_ids;          // [ndays*npix][ld_ids] leaf index per tree (quantile pass; nullable)
     long long ld_ids;
+    int ids_word;                // sector image: word of the leaf block stored into leaf_ids (forest.cuh)
     unsigned char* row_skip;     // [ndays*npix]
     // fallback list
     int2* fb_list;
@@ -224,7 +225,7 @@ fused_kernel(const __grid_constant__ FusedParams a)
         }
         if (has_na) {  // ranger refuses NA in a used column: report it, emit NA
             ok = false;
-            if (a.na_flag && a.t_begin == 0) *a.na_flag = 1;
+            if (a.na_flag && a.t_begin == 0) atomicOr(a.na_flag, 1);   // bit 1 belongs to the geometry pass (NA coordinates)
             if (a.out_mean) a.out_mean[row] = na_real();
             if (a.out_mean_i16) a.out_mean_i16[row] = (int16_t)-32767;
             if (a.row_skip) a.row_skip[row] = 1;
@@ -240,9 +241,14 @@ fused_kernel(const __grid_constant__ FusedParams a)
         o.terminal = nullptr;
         o.leaf_rid = nullptr;
         o.ld_term = 0;
+        o.ids_word = a.ids_word;
+        o.row_skip = nullptr;
         if (!Q) fs[a.F * P] = __longlong_as_double(0xFFF0000000000000LL);  // sentinel row: -inf
         double sum = a.t_begin > 0 ? a.acc[row] : 0.0;
-        if (Q && a.q.blocks)
+        if (Q && a.q.sect)
+            sum = traverse_sect<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
+                                             reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
+        else if (Q && a.q.blocks)
             sum = traverse_b<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
                                           reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
         else if (Q)

@@ -126,7 +126,7 @@ knn_brute_kernel(LocSpec L, long long npix, const double2* __restrict__ st_xy, i
     const bool in_range = p < npix;
     double px = 0.0, py = 0.0;
     if (in_range) get_loc(L, p, px, py);
-    if (in_range && (px != px || py != py) && na_flag) *na_flag = 1;
+    if (in_range && (px != px || py != py) && na_flag) atomicOr(na_flag, 2);   // bit 1: a location has an NA coordinate
 
     for (int j = 0; j < k; ++j) {
         ld2[j * P] = __longlong_as_double(0x7FF0000000000000LL);  // +inf
@@ -197,7 +197,7 @@ knn_brute_kernel(LocSpec L, long long npix, const double2* __restrict__ st_xy, i
                 shortl = true;
             }
         }
-        if (shortl && warn) *warn = 1;
+        if (shortl && warn) atomicOr(warn, 1);                                   // bit 0: fewer neighbours than n.obs
     }
 }
 

@@ -223,7 +223,7 @@ knn_cells_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
     double px = 0.0, py = 0.0;
     if (in_range) get_loc(L, p, px, py);
     const bool bad = in_range && (px != px || py != py);
-    if (bad && na_flag) *na_flag = 1;
+    if (bad && na_flag) atomicOr(na_flag, 2);   // bit 1: a location has an NA coordinate
     const bool act = in_range && !bad;
 
     const double inf = __longlong_as_double(0x7FF0000000000000LL);
@@ -240,9 +240,9 @@ knn_cells_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
     }
     __syncthreads();
     const int cx0 = s_box[0], cx1 = s_box[1], cy0 = s_box[2], cy1 = s_box[3];
-    if (cx1 < cx0) return;  // no active pixel in this tile (uniform)
-
-    for (int r = 0;; ++r) {
+    // cx1 < cx0: no searchable pixel in this tile (uniform) -- nothing to scan, but the rows of pixels with NA
+    // coordinates are still written below (empty lists: NA neighbours)
+    for (int r = 0; cx1 >= cx0; ++r) {
         const int x_lo = max(cx0 - r, 0), x_hi = min(cx1 + r, G - 1);
         const int y_lo = max(cy0 - r, 0), y_hi = min(cy1 + r, G - 1);
         for (int y = y_lo; y <= y_hi; ++y) {
@@ -302,7 +302,7 @@ knn_cells_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
                 shortl = true;
             }
         }
-        if (shortl && warn) *warn = 1;
+        if (shortl && warn) atomicOr(warn, 1);   // bit 0: fewer neighbours than n.obs
     }
 }
 

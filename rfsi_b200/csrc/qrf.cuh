@@ -340,11 +340,13 @@ __device__ __forceinline__ void qrf_cp_async16(void* smem_dst, const void* gsrc)
 
 // leaf_ids: [nrows][ld_ids] pixel-major leaf index per tree (written by the forest walk);
 // leaf_key: the forest's per-leaf table (samples, or their dictionary ranks with NA = 0xFFFFFFFF);
+// DIRECT (rank keys only): leaf_ids already holds the KEYS -- the sector image keeps each leaf's key in the leaf's own
+// block, so the walk stores it instead of the leaf number and nothing is left to gather: rows are read coalesced.
 // dict: the sorted distinct sample values (rank form only); skip (nullable): rows whose outputs
 // are NA (their ids were never written).
 // out_q[j*ld_q + row] for j < nprobs (nullable); out_iqr_i16[row] (nullable) =
 // round-half-even((q[nprobs-1]-q[0])/2*100), NA -> -32767.
-template <int R, class K>
+template <int R, class K, bool DIRECT>
 __global__ void __launch_bounds__(32 * kQrfWarps, qrf_min_blocks<R>())
 qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, const K* __restrict__ leaf_key,
                     const double* __restrict__ dict, const unsigned char* __restrict__ skip, long long nrows, int T,
@@ -388,7 +390,8 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int t = r * 32 + lane;
-            vn[r] = (rw < row_end && !skipped && t < T) ? __ldg(leaf_key + s.ids[t]) : KT::na();
+            if constexpr (DIRECT) vn[r] = (rw < row_end && !skipped && t < T) ? (K)s.ids[t] : KT::na();
+            else vn[r] = (rw < row_end && !skipped && t < T) ? __ldg(leaf_key + s.ids[t]) : KT::na();
         }
         __syncwarp();                          // every lane has read s.ids: it may be refilled
     };
@@ -419,124 +422,6 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
         qrf_row_finish<R, K>(s, valid, mn, mx, lane, row, probs, nprobs, dict, out_q, ld_q, out_iqr_i16);
         __syncwarp();   // the row's shared memory is free again
     }
-}
-
-// ---- strip form (rank keys, T <= 512) ------------------------------------------------------
-// The gathers of the kernel above are bound by the NUMBER of sectors they request (one per tree
-// per row, 32 different trees per warp-level load).  Here a CTA takes 16 adjacent rows at a time
-// and, during the gather, a half-warp is 16 adjacent ROWS of the same four trees: neighbouring
-// pixels end in the same or adjacent leaves (leaves are numbered left to right), so a warp-level
-// load touches a few sectors instead of 32.  The gathers are issued as 4-byte cp.async straight
-// into a double-buffered shared-memory tile [16 rows][T] -- no registers are held across the
-// selection -- while the 16 warps each select the quantiles of one row of the previous tile.
-constexpr int kStripRows = 16;     // rows per tile = warps per CTA
-template <int R> __host__ __device__ constexpr int qrf_strip_ld() { return R * 32 + 4; }   // = 4 (mod 32) words: 128-bit row-strided accesses are conflict-free
-template <int R>
-__host__ __device__ constexpr size_t qrf_strip_smem() {
-    return (size_t)3 * kStripRows * qrf_strip_ld<R>() * 4 + (size_t)kStripRows * (256 * 4 + 256 * 4 + 32 * 4);
-}
-
-__device__ __forceinline__ void qrf_cp_async4(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-                 : "memory");
-}
-
-template <int R>
-__global__ void __launch_bounds__(32 * kStripRows, 1)
-qrf_quantile_strip_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, const uint32_t* __restrict__ leaf_rank,
-                          const double* __restrict__ dict, const unsigned char* __restrict__ skip, long long nrows, int T,
-                          const double* __restrict__ probs, int nprobs,
-                          double* __restrict__ out_q, long long ld_q, int16_t* __restrict__ out_iqr_i16)
-{
-    constexpr int LD = qrf_strip_ld<R>();
-    constexpr int NJ = (R * 8 + 31) / 32;                 // 4-tree chunks per thread: 32 chunk slots x NJ cover R*32 trees
-    extern __shared__ __align__(16) unsigned char qrf_smem[];
-    uint32_t* ids_s = reinterpret_cast<uint32_t*>(qrf_smem);            // [16][LD] leaf ids of the tile being gathered
-    uint32_t* sv_s = ids_s + kStripRows * LD;                            // [2][16][LD] ranks: tile being selected / tile landing
-    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    QrfWarp<uint32_t> s;
-    {
-        unsigned char* base = reinterpret_cast<unsigned char*>(sv_s + 2 * kStripRows * LD) + (size_t)wib * (256 * 4 + 256 * 4 + 32 * 4);
-        s.hist0 = reinterpret_cast<int*>(base);
-        s.hist1 = reinterpret_cast<int*>(base + 256 * 4);
-        s.mem = reinterpret_cast<uint32_t*>(base + 512 * 4);
-        s.ids = nullptr;
-        s.sv = nullptr;
-    }
-    const long long ngroups = (nrows + kStripRows - 1) / kStripRows;
-    const long long per_cta = (ngroups + gridDim.x - 1) / gridDim.x;
-    const long long g_begin = (long long)blockIdx.x * per_cta;
-    const long long g_end = min(ngroups, g_begin + per_cta);
-    if (g_begin >= g_end) return;                          // whole CTA
-    const int nchunk = (int)(ld_ids >> 2);                 // 16-byte pieces of one id row
-    constexpr uint32_t NA = 0xFFFFFFFFu;
-
-    auto fetch_ids = [&](long long g) {                    // ids of tile g -> ids_s (asynchronous)
-        if (g < g_end) {
-            const int pieces = kStripRows * nchunk;
-            for (int q = tid; q < pieces; q += 32 * kStripRows) {
-                const int i = q / nchunk, c = q - i * nchunk;
-                const long long rw = g * kStripRows + i;
-                if (rw < nrows && !(skip && skip[rw])) qrf_cp_async16(ids_s + i * LD + 4 * c, leaf_ids + rw * ld_ids + 4 * c);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto gather = [&](long long g, uint32_t* sv) {         // ids_s -> ranks of tile g landing in sv (asynchronous)
-        if (g < g_end) {
-            const int l = tid & (kStripRows - 1);          // row of the tile: 16 adjacent lanes = 16 adjacent rows
-            const long long rw = g * kStripRows + l;
-            const bool live = rw < nrows && !(skip && skip[rw]);
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int c = (tid >> 4) + 32 * j;         // chunk of four trees
-                if (c >= R * 8) continue;
-                const int t0 = 4 * c;
-                uint32_t* dst = sv + l * LD + t0;
-                if (live && t0 < (int)ld_ids) {
-                    const uint4 id = *reinterpret_cast<const uint4*>(ids_s + l * LD + t0);
-                    if (t0 + 0 < T) qrf_cp_async4(dst + 0, leaf_rank + id.x); else dst[0] = NA;
-                    if (t0 + 1 < T) qrf_cp_async4(dst + 1, leaf_rank + id.y); else dst[1] = NA;
-                    if (t0 + 2 < T) qrf_cp_async4(dst + 2, leaf_rank + id.z); else dst[2] = NA;
-                    if (t0 + 3 < T) qrf_cp_async4(dst + 3, leaf_rank + id.w); else dst[3] = NA;
-                } else {
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(NA, NA, NA, NA);
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    // prologue: ids(g0) -> gathers(g0) landing in sv[0], ids(g0 + 1) in flight
-    fetch_ids(g_begin);
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
-    gather(g_begin, sv_s);
-    __syncthreads();                                       // every thread has read ids_s
-    fetch_ids(g_begin + 1);
-
-    int buf = 0;
-    for (long long g = g_begin; g < g_end; ++g, buf ^= 1) {
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();                                   // sv[buf] = ranks of tile g; ids_s = ids of tile g + 1; sv[buf ^ 1] is free
-        gather(g + 1, sv_s + (buf ^ 1) * kStripRows * LD);
-        __syncthreads();                                   // ids_s may be refilled
-        fetch_ids(g + 2);
-
-        const long long row = g * kStripRows + wib;        // this warp's row of the tile
-        if (row < nrows) {
-            s.sv = sv_s + buf * kStripRows * LD + wib * LD;
-            unsigned valid = 0;
-            uint32_t mn = NA, mx = 0u;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t x = s.sv[r * 32 + lane];
-                if (x != NA) { valid |= 1u << r; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }   // na.rm = TRUE
-            }
-            qrf_row_finish<R, uint32_t>(s, valid, mn, mx, lane, row, probs, nprobs, dict, out_q, ld_q, out_iqr_i16);
-        }
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");       // nothing may land after the CTA is gone
 }
 
 }  // namespace rfsi

@@ -1,0 +1,240 @@
+// sector.cuh -- the "sector" forest image and its walk (stage 2, default image).
+//
+// Same job as traverse_b / traverse_q in forest.cuh: the forward pass of
+// ranger::predict.ranger (simulation/simulation.R:214, temp_croatia/2_predictions.R:167,174-176,
+// prcp_catalonia/5_prcp_prediction.R:287-291), decisions made on threshold RANKS so that they are
+// bit-identical to the fp64 compare (common.cuh).
+//
+// Layout.  One block = 8 words = ONE 32-byte sector = three tree levels:
+//     word 0      index of the first of the block's 8 child blocks (children are contiguous and
+//                 come after their parent: child = w0 + exit, exit = heap slot - 8)
+//     words 1..7  implicit heap of 7 nodes, children of slot h at 2h, 2h+1;
+//                 node word = (~rank << 8) | feature (rank: 24 bits): the walk goes right iff
+//                 (rank(x) << 8) + word carries out of 32 bits, i.e. iff rank(x) > rank -- the
+//                 feature byte cannot make up the difference because rank(x) << 8 ends in 00; it is
+//                 stored as it is, so the shared-memory address is one AND and one multiply-add
+//     a LEAF is a block of its own:
+//                 word 0 = 0x80000000 | its own block index
+//                 words 1, 2, 4 = pass-through nodes (the only heap slots a walk can touch: 1 -> 2 -> 4 -> exit 0)
+//                 word 3 = leaf number (left to right within the tree, trees one after the other)
+//                 word 5 = quantile-forest key of the leaf (rank of ranger's random.node.values
+//                          entry in the forest-wide sorted dictionary, 0xFFFFFFFF = NA)
+//                 words 6..7 = the leaf's prediction (fp64)
+//     block 0 is the idle block: word 0 = 0, all nodes pass-through (= 8 zero words).
+// A leaf met before a block's third level is padded with pass-through nodes (rank 0xFFFFFF:
+// never exceeded) down to ONE exit; the child slots to the right of padding are never visited
+// and stay zero.
+//
+// Why (profiles/r01_g): the 128-byte blocked image needs three dependent sector fetches per four
+// levels (levels 1-3 | level 4 | exit word) plus a leaf-value gather; here a block visit is one
+// sector -- one L1 miss, then two L1 hits -- per three levels, no exit load, and the leaf's value,
+// number and quantile key arrive with the leaf's own sector.
+//
+// Walk state per chain: ONE register bb = block index, or 0x80000000 | leaf block once the
+// chain is finished.  Per block visit:
+//     idx = max((int)bb, 0)                 finished chains idle on block 0 (one shared sector)
+//     {w0, n1} = 64-bit load                three levels: node load, shared-memory rank load, add.cc/addc
+//     bb = umax(bb, w0 + h - 8)             children have larger indices than their parent, a leaf
+//                                           carries the flag bit, the idle block yields 0: no selects
+// and the lane leaves the loop as soon as every chain is finished or standing on a leaf block
+// (sign bit of AND_j (bb_j | w0_j)), so the last visit of the deepest chain costs one load.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#if defined(RFSI_SECTOR_HOST_CHECK)
+// tests/tools/sector_host.cpp compiles the very same loop for the host (no CUDA headers)
+#include <algorithm>
+#define RFSI_SECT_DEV inline
+struct uint2 { uint32_t x, y; };
+template <class T> inline T __ldg(const T* p) { return *p; }
+#else
+#define RFSI_SECT_DEV __device__ __forceinline__
+#endif
+
+namespace rfsi {
+
+constexpr uint32_t kSLeafFlag = 0x80000000u;
+constexpr uint32_t kSPassWord = 0x00000000u;       // rank 0xFFFFFF, feature 0: never carries
+constexpr uint32_t kSMaxRank = 0xFFFFFEu;
+constexpr int kSMaxFeat = 256;
+constexpr int kSWordLeafNo = 3, kSWordKey = 5, kSWordValue = 6;
+
+struct SectorView {
+    const uint32_t* words;   // 8 per block
+    const uint32_t* root;    // [T] block of each tree's root (a leaf block for a single-node tree)
+    // 32 (bytes per block) and P*4 (bytes between two features of the rank tile) as RUN-TIME values: given
+    // immediates, ptxas strength-reduces idx*32 + base into LEA + LEA.HI.X and feat*1024 + base into
+    // IMAD.SHL + LOP3 + IMAD.IADD; from the constant bank they stay one IMAD.WIDE / one IMAD (the walk is
+    // bound by integer issue slots: profiles/r02_sass_*.txt)
+    uint32_t block_bytes;
+    uint32_t tile_stride;
+};
+
+// h + h + carry(xs + w): one level.  xs = rank(x) << 8, w = (~rank << 8) | feature.
+RFSI_SECT_DEV uint32_t sector_step(uint32_t h, uint32_t w, uint32_t xs) {
+#if defined(RFSI_SECTOR_HOST_CHECK)
+    return 2u * h + (uint32_t)(((uint64_t)xs + (uint64_t)w) >> 32);
+#else
+    uint32_t out;
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, %3;\n\t}" : "=r"(out) : "r"(xs), "r"(w), "r"(h));
+    return out;
+#endif
+}
+
+RFSI_SECT_DEV uint32_t sector_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+inline uint32_t sector_node_word(uint32_t rank, uint32_t feat) { return ((~rank) << 8) | feat; }
+
+// address of block max(bb, 0): one signed max, one 32 x 32 -> 64-bit multiply-add
+RFSI_SECT_DEV const uint32_t* sector_block(const SectorView& q, uint32_t bb) {
+#if defined(RFSI_SECTOR_HOST_CHECK)
+    return reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(q.words) +
+                                             (size_t)((int32_t)bb > 0 ? bb : 0u) * q.block_bytes);
+#else
+    const uint32_t* out;
+    asm("{\n\t.reg .s32 t;\n\tmax.s32 t, %1, 0;\n\tmad.wide.u32 %0, t, %3, %2;\n\t}"
+        : "=l"(out) : "r"(bb), "l"(q.words), "r"(q.block_bytes));
+    return out;
+#endif
+}
+
+// Walk trees [t_begin, t_end) for the pixel whose pre-shifted ranks are rs[f * P] (feature-major tile in shared
+// memory), J trees in lock step.  `sum` carries the tree-order partial sum of the trees before; the updated sum is
+// returned.  After each group of J trees `sink(t0, remaining, leaf_block[J])` sees the leaf blocks the trees
+// t0 .. t0+J-1 ended in (entries beyond `remaining` are 0).  nvisit += internal nodes visited if COUNT.
+template <int P, int J, bool COUNT, class Sink>
+RFSI_SECT_DEV double traverse_s(const SectorView& q, int t_begin, int t_end, double sum, const uint32_t* rs, Sink&& sink,
+                                unsigned& nvisit)
+{
+    const char* rsb = reinterpret_cast<const char*>(rs);
+    for (int t0 = t_begin; t0 < t_end; t0 += J) {
+        uint32_t bb[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) bb[j] = (t0 + j < t_end) ? __ldg(q.root + t0 + j) : kSLeafFlag;   // no tree: finished, idles on block 0
+        for (;;) {
+            uint2 w01[J];
+            const uint32_t* blk[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                blk[j] = sector_block(q, bb[j]);
+                w01[j] = __ldg(reinterpret_cast<const uint2*>(blk[j]));     // w0 and the level-1 node: one request
+            }
+            uint32_t fin = kSLeafFlag;
+#pragma unroll
+            for (int j = 0; j < J; ++j) fin &= bb[j] | w01[j].x;
+            if (fin) {                                                        // every chain finished or on its leaf
+#pragma unroll
+                for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w01[j].x);
+                break;
+            }
+            uint32_t h[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w01[j].y & 0xFFu) * q.tile_stride);
+                h[j] = sector_step(1u, w01[j].y, xs);
+                if (COUNT) nvisit += (w01[j].y != kSPassWord) ? 1u : 0u;
+            }
+#pragma unroll
+            for (int lev = 1; lev < 3; ++lev) {
+                uint32_t w[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) w[j] = __ldg(blk[j] + h[j]);      // same sector: L1 hits
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w[j] & 0xFFu) * q.tile_stride);
+                    h[j] = sector_step(h[j], w[j], xs);
+                    if (COUNT) nvisit += (w[j] != kSPassWord) ? 1u : 0u;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w01[j].x + (h[j] - 8u));   // implicit child: no exit load
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) bb[j] &= ~kSLeafFlag;
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (t0 + j < t_end)                                                // the leaf's own sector: fetched by the walk
+                sum += __ldg(reinterpret_cast<const double*>(q.words + (size_t)bb[j] * 8u + kSWordValue));
+        sink(t0, t_end - t0, bb);
+    }
+    return sum;
+}
+
+// ---- host: build the image ---------------------------------------------------------------------
+// node(i) -> {is_leaf, feature, left child index (right = left + 1), complemented node word, leaf number, value}
+// for the wide device layout of engine.cu (tree t's root is node t).  Blocks of a tree are contiguous, in BFS order
+// (children after their parent); trees are built independently (`tree_begin`, `tree_end` let callers run them on
+// several threads) into `w` with LOCAL indices starting at 0, and `sector_relocate` moves a tree to its place.
+struct SectorNode {
+    bool leaf;
+    uint32_t word;      // sector_node_word(rank, feature)          (internal nodes)
+    uint32_t child;     // index of the left child, right = child+1 (internal nodes)
+    uint32_t leaf_no;   //                                          (leaves)
+    double value;       //                                          (leaves)
+};
+
+template <class NodeAt, class Vec>
+inline void sector_build_tree(uint32_t root_node, NodeAt&& node, Vec& w)
+{
+    struct Todo { uint32_t node, block; };
+    struct Item { uint32_t node; int h; bool dead; };
+    w.assign(8, 0u);
+    auto make_leaf = [&](uint32_t blk, const SectorNode& n) {
+        uint32_t* b = &w[(size_t)blk * 8];
+        b[0] = kSLeafFlag | blk;
+        b[1] = b[2] = b[4] = kSPassWord;
+        b[kSWordLeafNo] = n.leaf_no;
+        b[kSWordKey] = 0xFFFFFFFFu;
+        uint64_t bits;
+        static_assert(sizeof(double) == 8, "fp64");
+        __builtin_memcpy(&bits, &n.value, 8);
+        b[kSWordValue] = (uint32_t)bits;
+        b[kSWordValue + 1] = (uint32_t)(bits >> 32);
+    };
+    const SectorNode r = node(root_node);
+    if (r.leaf) { make_leaf(0, r); return; }
+    std::vector<Todo> todo(1, Todo{root_node, 0u});          // FIFO of inner blocks still to fill: BFS order
+    size_t head = 0;
+    Item stack[64];
+    while (head < todo.size()) {
+        const Todo cur = todo[head++];
+        const uint32_t kids = (uint32_t)(w.size() / 8);
+        w.resize(w.size() + 64, 0u);
+        w[(size_t)cur.block * 8] = kids;
+        int sp = 0;
+        stack[sp++] = Item{cur.node, 1, false};
+        while (sp > 0) {
+            const Item it = stack[--sp];
+            if (it.h >= 8) {                                   // an exit: child block kids + (h - 8)
+                if (it.dead) continue;                         // right of a pass-through node: never visited
+                const uint32_t child = kids + (uint32_t)(it.h - 8);
+                const SectorNode n = node(it.node);
+                if (n.leaf) make_leaf(child, n); else todo.push_back(Todo{it.node, child});
+                continue;
+            }
+            const SectorNode n = it.dead ? SectorNode{true, 0, 0, 0, 0.0} : node(it.node);
+            if (n.leaf) {                                      // pad down to one exit: always left
+                w[(size_t)cur.block * 8 + it.h] = kSPassWord;
+                stack[sp++] = Item{it.node, 2 * it.h + 1, true};
+                stack[sp++] = Item{it.node, 2 * it.h, it.dead};
+            } else {
+                w[(size_t)cur.block * 8 + it.h] = n.word;
+                stack[sp++] = Item{n.child + 1, 2 * it.h + 1, false};
+                stack[sp++] = Item{n.child, 2 * it.h, false};
+            }
+        }
+    }
+}
+
+// move a tree built with local indices to global block index `base` (in place)
+inline void sector_relocate(uint32_t* w, size_t nblocks, uint32_t base) {
+    for (size_t b = 0; b < nblocks; ++b) {
+        uint32_t& w0 = w[b * 8];
+        const bool unused = w0 == 0u && w[b * 8 + 1] == 0u;   // a child slot that is never visited
+        if (!unused) w0 += base;                               // leaf flag is the top bit: the sum stays below it
+    }
+}
+
+}  // namespace rfsi

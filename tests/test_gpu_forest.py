@@ -61,6 +61,44 @@ def test_missing_data_is_an_error_like_ranger():
         rb.predict(rb.RangerForest(plain), f["X"], type="quantiles")
 
 
+@pytest.mark.parametrize("image", ["3", "2", "1", "0"])
+def test_missing_data_in_quantiles_and_terminal_nodes(image, monkeypatch):
+    """NA in a used column with type="quantiles" / "terminalNodes" (ranger: "Missing data in columns"): the C ABI
+    returns RFSI_E_NA_INPUT, the NA rows come back NA, every other row is still right, and the device context
+    stays usable (the rows' leaf ids are never written: the quantile pass must skip them, not gather from them)."""
+    import ctypes as C
+    from rfsi_b200 import _lib
+    monkeypatch.setenv("RFSI_B200_COMPACT", image)
+    f, flat = _golden_forest()
+    model = rb.RangerForest(flat)
+    lib = _lib.load()
+    X = f["X"].copy()
+    bad = np.array([0, 5, 77, len(X) - 1])
+    X[bad, [3, 0, 1, 2]] = np.nan
+    Xt = np.ascontiguousarray(X.T)
+    npix = len(X)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    good = np.setdiff1d(np.arange(npix), bad)
+    probs = np.ascontiguousarray(f["probs"], dtype=np.float64)
+    for _ in range(2):                               # twice: the first failure must not poison the context
+        q = np.full((len(probs), npix), 7.0)
+        rc = lib.rfsi_forest_quantiles(model.handle, ptr(Xt), npix, npix, ptr(probs), len(probs), ptr(q), 0)
+        assert rc == -4, _lib.last_error()
+        assert np.isnan(q[:, bad]).all()
+        np.testing.assert_array_equal(q[:, good].T, f["q"][good])
+        term = np.full((flat.ntrees, npix), 7, dtype=np.int32)
+        assert lib.rfsi_forest_terminal_nodes(model.handle, ptr(Xt), npix, npix, ptr(term), 0) == -4
+        assert (term[:, bad] == np.iinfo(np.int32).min).all()            # NA_integer_
+        np.testing.assert_array_equal(term[:, good].T, f["term"][good])
+        mean = np.full(npix, 7.0)
+        assert lib.rfsi_forest_predict(model.handle, ptr(Xt), npix, npix, ptr(mean), 0) == -4
+        assert np.isnan(mean[bad]).all()
+        same_mean(mean[good], f["mean"][good])
+    # and a clean call on the same context afterwards
+    np.testing.assert_array_equal(rb.predict(model, f["X"], type="quantiles", quantiles=f["probs"]).predictions, f["q"])
+    np.testing.assert_array_equal(rb.predict(model, f["X"], type="terminalNodes").predictions, f["term"])
+
+
 def _random_forest_case(seed, n_train, F, T, min_leaf, quantreg=True):
     rng = np.random.default_rng(seed)
     X = rng.normal(size=(n_train, F))
@@ -188,18 +226,18 @@ def test_forest_properties_at_simulation_size():
 
 
 def test_wide_and_compact_node_formats_agree(monkeypatch):
-    """The blocked 4-byte image (default), the 8-byte rank-quantised image and the 16-byte fp64
-    image make identical decisions."""
+    """The sector image (default), the blocked 4-byte image, the 8-byte rank-quantised image and the
+    16-byte fp64 image make identical decisions."""
     flat, rng = _random_forest_case(11, 3000, 20, 64, 2)
     X = rng.normal(size=(20000, 20))
     X[::7, 3] = flat.split_val[flat.left != 0][:len(X[::7])][:X[::7].shape[0]]   # features exactly ON thresholds
     exp = oracle.forest_predict(flat.as_dict(), X, threads=8)
     probs = [0.25, 0.5, 0.75]
     expq = oracle.forest_quantiles(flat.as_dict(), X, probs, threads=8)
-    for compact in ("2", "1", "0"):
+    for compact in ("3", "2", "1", "0"):
         monkeypatch.setenv("RFSI_B200_COMPACT", compact)
         model = rb.RangerForest(flat)
-        assert model.info()["nodes"] > 0
+        assert model.info()["nodes"] > 0 and model.info()["image"] == int(compact)
         same_mean(rb.predict(model, X).predictions, exp)
         np.testing.assert_array_equal(rb.predict(model, X, type="quantiles", quantiles=probs).predictions, expq)
         np.testing.assert_array_equal(rb.predict(model, X, type="terminalNodes").predictions,

@@ -77,7 +77,7 @@ def _random_forest(rng, T, F, max_nodes, quantreg=True):
                       np.array(roff, dtype=np.int64) if quantreg else None, np.array(rnv) if quantreg else None)
 
 
-@pytest.mark.parametrize("fmt", ["2", "1", "0"])
+@pytest.mark.parametrize("fmt", ["3", "2", "1", "0"])
 def test_fuzz_forest(fmt, monkeypatch):
     monkeypatch.setenv("RFSI_B200_COMPACT", fmt)
     rng = np.random.default_rng(7 + int(fmt))
