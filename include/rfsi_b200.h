@@ -16,6 +16,12 @@
  *    RFSI_E_* error; rfsi_last_error() gives the thread-local message;
  *  - there is NO CPU fallback: without an sm_100 device calls fail with
  *    RFSI_E_NO_DEVICE;
+ *  - fork(): CUDA is initialised lazily, by the first call that needs a device.  Forked workers
+ *    (registerDoParallel + foreach %dopar%: simulation/simulation.R:113-114,
+ *    prcp_catalonia/5_prcp_prediction.R:243-244) each get their own context as long as the PARENT
+ *    has not made such a call before forking; rfsi_forest_create() never touches a device, so a
+ *    model imported in the parent is usable in every child.  A child of a parent that did use a
+ *    device gets RFSI_E_FORKED from every device call (a CUDA context does not survive fork);
  *  - rfsi_*      : HOST pointers in, HOST pointers out (copies are inside the call);
  *    rfsi_dev_*  : DEVICE pointers on `device`, enqueued on `stream` (a cudaStream_t
  *                  passed as void*; NULL = the legacy default stream), asynchronous.
@@ -40,7 +46,8 @@ enum {
     RFSI_E_ARG = -3,
     RFSI_E_NA_INPUT = -4, /* NA/NaN coordinate, or NA in a feature column the forest uses */
     RFSI_E_OOM = -5,
-    RFSI_E_FOREST = -6 /* malformed forest (child out of range, cycle, bad varID) */
+    RFSI_E_FOREST = -6, /* malformed forest (child out of range, cycle, bad varID) */
+    RFSI_E_FORKED = -7  /* this process was fork()ed from one that had already used the engine on a GPU */
 };
 
 /* feature-map codes for rfsi_predict_fused: which model column is what */

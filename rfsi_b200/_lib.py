@@ -21,6 +21,7 @@ RFSI_E_ARG = -3
 RFSI_E_NA_INPUT = -4
 RFSI_E_OOM = -5
 RFSI_E_FOREST = -6
+RFSI_E_FORKED = -7
 
 FEAT_DIST = 0x10000
 FEAT_OBS = 0x20000

@@ -16,6 +16,8 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/rfsi_b200.h"
@@ -63,7 +65,23 @@ int fail(int code, const char* fmt, ...) {
         if (rc__ < 0) return rc__; \
     } while (0)
 
+// fork-safety: the pid that first made a CUDA call through this library.  A forked child inherits the value and is
+// refused (a CUDA context does not survive fork()) with a message that says what to do instead of the runtime's
+// "initialization error" (prcp_catalonia/5_prcp_prediction.R:243-244 forks its day workers).
+std::atomic<long> g_cuda_pid{0};
+int check_fork() {
+    const long me = (long)getpid();
+    long seen = 0;
+    if (g_cuda_pid.compare_exchange_strong(seen, me) || seen == me) return RFSI_OK;
+    return fail(RFSI_E_FORKED,
+                "this process (pid %ld) was forked from pid %ld after that process had used the GPU through rfsi_b200; a CUDA "
+                "context does not survive fork(). Import models in the parent (rfsi_forest_create needs no device) and make "
+                "the first device call inside each worker, or start workers with spawn / PSOCK clusters",
+                me, seen);
+}
+
 int use_device(int device) {
+    RF_TRY(check_fork());
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -690,7 +708,9 @@ extern "C" int rfsi_forest_create(int32_t ntrees, const int64_t* node_offsets, c
 
 extern "C" void rfsi_forest_destroy(rfsi_forest_t* f) {
     if (!f) return;
+    const bool forked = g_cuda_pid.load() != 0 && g_cuda_pid.load() != (long)getpid();   // the parent's device images are not ours
     for (auto& kv : f->images) {
+        if (forked) break;
         int cur = 0;
         cudaGetDevice(&cur);
         if (cudaSetDevice(kv.first) == cudaSuccess) {
@@ -780,6 +800,7 @@ extern "C" int rfsi_profile_read(int kernel_class, double* total_ms, uint64_t* l
 }
 
 extern "C" int rfsi_device_count(void) {
+    RF_TRY(check_fork());
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     int ok = 0;
@@ -792,6 +813,7 @@ extern "C" int rfsi_device_count(void) {
 
 extern "C" int rfsi_host_alloc(void** out, size_t bytes) {
     if (!out) return fail(RFSI_E_ARG, "out is NULL");
+    RF_TRY(check_fork());
     CU_TRY(cudaMallocHost(out, bytes ? bytes : 1));
     return RFSI_OK;
 }

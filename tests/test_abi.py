@@ -93,3 +93,32 @@ def test_product_never_imports_the_oracle():
             txt = p.read_text(errors="ignore")
             assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt \
                 and "libcpubaseline" not in txt, f"{p} touches the oracle"
+
+
+def test_fork_after_a_device_call_is_refused_with_its_own_code():
+    """No GPU needed: the library remembers the pid of its first device call; a forked child is told so
+    (RFSI_E_FORKED) instead of meeting the CUDA runtime's "initialization error" (tests/test_gpu_fork.py is the
+    GPU twin with real work in the children)."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import os, sys
+        sys.path.insert(0, %r)
+        from rfsi_b200 import _lib
+        lib = _lib.load()
+        pid = os.fork()
+        if pid == 0:                          # forked BEFORE any device call: the child may make its own
+            os._exit(0 if lib.rfsi_device_count() >= 0 else 1)
+        assert os.waitpid(pid, 0)[1] == 0
+        assert lib.rfsi_device_count() >= 0   # first device call of the parent
+        pid = os.fork()
+        if pid == 0:
+            rc = lib.rfsi_device_count()
+            ok = rc == _lib.RFSI_E_FORKED and b"fork()" in lib.rfsi_last_error()
+            os._exit(0 if ok else 1)
+        assert os.waitpid(pid, 0)[1] == 0
+        print("OK")
+    ''') % str(ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
