@@ -15,7 +15,7 @@
 # write NAflag = -32767; hand them to writeRaster(..., datatype='INT2S') as before.
 pred.maps <- function(model, gg, gg2 = gg, obs.xy, obs.z, n.obs, covariates, divisor = NULL, cov.fix = NULL,
                       quantiles = c(0.25, 0.5, 0.75), device = 0L) {
-  fo <- if (is.null(model$rfsi_b200)) rfsi_import_ranger(model) else model$rfsi_b200
+  fo <- rfsi_forest_of(model)
   covn <- names(covariates)
   code <- vapply(fo$independent.variable.names, function(v) {
     if (grepl("^dist[0-9]+$", v)) 65536L + as.integer(sub("dist", "", v)) - 1L

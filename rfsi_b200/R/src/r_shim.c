@@ -142,6 +142,18 @@ SEXP C_rfsi_predict(SEXP h, SEXP X, SEXP probs, SEXP device)
     return out;
 }
 
+/* predict(type = "terminalNodes"): ranger's node ids, npix x num.trees integer matrix */
+SEXP C_rfsi_terminal_nodes(SEXP h, SEXP X, SEXP device)
+{
+    rfsi_forest_t* f = forest_of(h);
+    const R_xlen_t npix = Rf_nrows(X);
+    if (!Rf_isReal(X) || Rf_ncols(X) != (int)rfsi_forest_info(f, 1)) Rf_error("predict: X must be npix x nfeat double");
+    SEXP out = PROTECT(Rf_allocMatrix(INTSXP, (int)npix, (int)rfsi_forest_info(f, 0)));
+    check_rc(rfsi_forest_terminal_nodes(f, REAL(X), (int64_t)npix, (int64_t)npix, INTEGER(out), Rf_asInteger(device)));
+    UNPROTECT(1);
+    return out;
+}
+
 /* fused near.obs -> predict for explicit locations over ndays:
  * loc_xy npix x 2; obs_xy nobs x 2; obs_z nobs x ndays (column d = day d, NA = missing);
  * cov: list of numeric vectors (npix, static) or npix x ndays matrices; feat_map integer codes;
@@ -273,6 +285,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_rfsi_near_obs_days", (DL_FUNC)&C_rfsi_near_obs_days, 5},
     {"C_rfsi_forest_new", (DL_FUNC)&C_rfsi_forest_new, 7},
     {"C_rfsi_predict", (DL_FUNC)&C_rfsi_predict, 4},
+    {"C_rfsi_terminal_nodes", (DL_FUNC)&C_rfsi_terminal_nodes, 3},
     {"C_rfsi_pred_fused", (DL_FUNC)&C_rfsi_pred_fused, 9},
     {"C_rfsi_pred_maps", (DL_FUNC)&C_rfsi_pred_maps, 12},
     {NULL, NULL, 0}};

@@ -105,8 +105,20 @@ __host__ __device__ constexpr size_t fused_feature_bytes(int F) {
     return Q ? (((size_t)F * P * sizeof(uint32_t) + 15) & ~(size_t)15) : (size_t)(F + 1) * P * sizeof(double);
 }
 
+// Resident CTAs per SM the register budget is cut for (rank images): 4 x 256 threads at 64 registers with up to 8
+// trees in flight per thread; more trees in flight need more registers, so fewer, fatter CTAs (3 at J = 12, 2 at
+// J = 16: the same number of walks in flight per SM, less shared memory -> more L1 for the forest).
+template <int P, int J>
+__host__ __device__ constexpr int fused_min_blocks_q() {
+#ifdef RFSI_FUSED_MINB   // experiment builds (tools/build_variant.sh)
+    return (P * 64 * 4 <= 65536) ? (J >= 16 ? 2 : (J >= 12 ? (RFSI_FUSED_MINB < 3 ? RFSI_FUSED_MINB : 3) : RFSI_FUSED_MINB)) : 2;
+#else
+    return (P * 64 * 4 <= 65536) ? (J >= 16 ? 2 : (J >= 12 ? 3 : 4)) : 2;
+#endif
+}
+
 template <int P, int J, bool COUNT, bool FALLBACK, bool Q>
-__global__ void __launch_bounds__(P, Q ? ((P * 64 * 4 <= 65536) ? 4 : 2) : ((P * (20 + 6 * J) <= 32768) ? 2 : 1))
+__global__ void __launch_bounds__(P, Q ? fused_min_blocks_q<P, J>() : ((P * (20 + 6 * J) <= 32768) ? 2 : 1))
 fused_kernel(const __grid_constant__ FusedParams a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -43,11 +43,16 @@
 #include <cstdint>
 #include <vector>
 
+#ifndef RFSI_SECT_WIDE
+#define RFSI_SECT_WIDE 0
+#endif
+
 #if defined(RFSI_SECTOR_HOST_CHECK)
 // tests/tools/sector_host.cpp compiles the very same loop for the host (no CUDA headers)
 #include <algorithm>
 #define RFSI_SECT_DEV inline
 struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
 template <class T> inline T __ldg(const T* p) { return *p; }
 #else
 #define RFSI_SECT_DEV __device__ __forceinline__
@@ -114,6 +119,51 @@ RFSI_SECT_DEV double traverse_s(const SectorView& q, int t_begin, int t_end, dou
 #pragma unroll
         for (int j = 0; j < J; ++j) bb[j] = (t0 + j < t_end) ? __ldg(q.root + t0 + j) : kSLeafFlag;   // no tree: finished, idles on block 0
         for (;;) {
+#if RFSI_SECT_WIDE
+            // one 128-bit request brings w0 and the nodes of levels 1 and 2; level 3 is one more 32-bit load
+            uint4 w03[J];
+            const uint32_t* blk[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                blk[j] = sector_block(q, bb[j]);
+                w03[j] = __ldg(reinterpret_cast<const uint4*>(blk[j]));
+            }
+            uint32_t fin = kSLeafFlag;
+#pragma unroll
+            for (int j = 0; j < J; ++j) fin &= bb[j] | w03[j].x;
+            if (fin) {                                                        // every chain finished or on its leaf
+#pragma unroll
+                for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w03[j].x);
+                break;
+            }
+            uint32_t h[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w03[j].y & 0xFFu) * q.tile_stride);
+                h[j] = sector_step(1u, w03[j].y, xs);
+                if (COUNT) nvisit += (w03[j].y != kSPassWord) ? 1u : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const uint32_t w = (h[j] & 1u) ? w03[j].w : w03[j].z;         // heap slot 3 or 2
+                const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w & 0xFFu) * q.tile_stride);
+                h[j] = sector_step(h[j], w, xs);
+                if (COUNT) nvisit += (w != kSPassWord) ? 1u : 0u;
+            }
+            {
+                uint32_t w[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) w[j] = __ldg(blk[j] + h[j]);      // same sector
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w[j] & 0xFFu) * q.tile_stride);
+                    h[j] = sector_step(h[j], w[j], xs);
+                    if (COUNT) nvisit += (w[j] != kSPassWord) ? 1u : 0u;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w03[j].x + (h[j] - 8u));   // implicit child: no exit load
+#else
             uint2 w01[J];
             const uint32_t* blk[J];
 #pragma unroll
@@ -150,6 +200,7 @@ RFSI_SECT_DEV double traverse_s(const SectorView& q, int t_begin, int t_end, dou
             }
 #pragma unroll
             for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w01[j].x + (h[j] - 8u));   // implicit child: no exit load
+#endif
         }
 #pragma unroll
         for (int j = 0; j < J; ++j) bb[j] &= ~kSLeafFlag;

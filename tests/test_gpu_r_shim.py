@@ -105,3 +105,11 @@ def test_pred_fused_and_pred_maps_through_the_call_entries(R, case_model):
         return np.where(v == -32767, np.iinfo(np.int32).min, v)
     np.testing.assert_array_equal(maps[0].T, as_r_integer(ref["mean"]))
     np.testing.assert_array_equal(maps[1].T, as_r_integer((ref["quantiles"][2] - ref["quantiles"][0]) / 2))
+
+
+def test_terminal_nodes_through_the_call_entry(R, case_model):
+    case, flat, h = case_model
+    loc = case.locations(0, 500)
+    d, o, _, _ = oracle.near_obs(loc, case.obs_xy, case.obs_z[0], case.n_obs)
+    X = np.column_stack([d, o])
+    np.testing.assert_array_equal(R.call("C_rfsi_terminal_nodes", h, X, 0), oracle.forest_terminal_nodes(flat.as_dict(), X))
