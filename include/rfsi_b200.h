@@ -79,6 +79,15 @@ int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix,
                       int32_t nobs, int32_t n_obs, int32_t rm_dupl,
                       double* out_dist, double* out_obs, int32_t* out_idx, int device);
 
+/* The same call with one pointer PER COLUMN (dist_cols[j], obs_cols[j], idx_cols[j] (nullable array), each npix
+ * long): what an R binding needs to return the data.frame near.obs() returns -- a list of 2 * n.obs numeric
+ * vectors -- without going through an npix x n.obs matrix and as.data.frame() (a 100 MB copy at simulation.R's
+ * 250 000 x 50 columns). */
+int rfsi_near_obs_cols_f64(const double* loc_x, const double* loc_y, int64_t npix,
+                           const double* obs_x, const double* obs_y, const double* obs_z,
+                           int32_t nobs, int32_t n_obs, int32_t rm_dupl,
+                           double* const* dist_cols, double* const* obs_cols, int32_t* const* idx_cols, int device);
+
 /* fp32 twin (float buffers): coordinates are widened to fp64 on the device and searched with
  * the fp64 kernels, so indices equal those of the fp64 call on the same coordinates and
  * dist/obs are its results rounded to float (1e-5 relative, north_star's fp32 mode). */

@@ -15,10 +15,8 @@ near.obs <- function(locations, locations.x.y = c(1, 2), observations, observati
   obs <- xy(observations, observations.x.y)
   z <- if (inherits(observations, "Spatial")) observations@data[[zcol]] else as.data.frame(observations)[[zcol]]
   storage.mode(loc) <- "double"; storage.mode(obs) <- "double"
-  res <- .Call(C_rfsi_near_obs, loc, obs, as.double(z), as.integer(n.obs), as.logical(rm.dupl), as.integer(device))
-  dist <- as.data.frame(res$dist); names(dist) <- paste0("dist", seq_len(n.obs))
-  ob <- as.data.frame(res$obs); names(ob) <- paste0("obs", seq_len(n.obs))
-  cbind(dist, ob)
+  # the engine fills the 2 * n.obs columns of the returned data.frame in place (no matrix, no as.data.frame copy)
+  .Call(C_rfsi_near_obs_df, loc, obs, as.double(z), as.integer(n.obs), as.logical(rm.dupl), as.integer(device))
 }
 
 # near.obs.days -- all days of a station table in one engine call: what

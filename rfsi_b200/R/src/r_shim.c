@@ -17,6 +17,8 @@
  * (prcp_catalonia/5_prcp_prediction.R:243-244) each get their own as long as the parent has
  * not touched the engine before forking.
  */
+#include <stdio.h>
+
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
@@ -55,6 +57,41 @@ SEXP C_rfsi_near_obs(SEXP loc_xy, SEXP obs_xy, SEXP obs_z, SEXP n_obs, SEXP rm_d
     SET_STRING_ELT(names, 2, Rf_mkChar("idx"));
     Rf_setAttrib(out, R_NamesSymbol, names);
     UNPROTECT(5);
+    return out;
+}
+
+/* near.obs as the data.frame meteo::near.obs returns: a list of 2 * n.obs numeric vectors named dist1..distN,
+ * obs1..obsN with class "data.frame" and compact row names, every column filled in place by the engine
+ * (rfsi_near_obs_cols_f64) -- no npix x n.obs matrix and no as.data.frame() copy on the R side. */
+SEXP C_rfsi_near_obs_df(SEXP loc_xy, SEXP obs_xy, SEXP obs_z, SEXP n_obs, SEXP rm_dupl, SEXP device)
+{
+    const R_xlen_t npix = Rf_nrows(loc_xy), nobs = Rf_nrows(obs_xy);
+    const int n = Rf_asInteger(n_obs);
+    if (!Rf_isReal(loc_xy) || !Rf_isReal(obs_xy) || !Rf_isReal(obs_z)) Rf_error("near.obs: numeric inputs expected");
+    if (Rf_ncols(loc_xy) != 2 || Rf_ncols(obs_xy) != 2 || XLENGTH(obs_z) != nobs || n < 1) Rf_error("near.obs: bad shapes");
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2 * (R_xlen_t)n));
+    SEXP names = PROTECT(Rf_allocVector(STRSXP, 2 * (R_xlen_t)n));
+    double** cols = (double**)R_alloc((size_t)2 * n, sizeof(double*));
+    char buf[32];
+    for (int j = 0; j < 2 * n; ++j) {
+        SEXP col = Rf_allocVector(REALSXP, npix);
+        SET_VECTOR_ELT(out, j, col);                  /* reachable from `out` at once: no PROTECT of its own needed */
+        cols[j] = REAL(col);
+        snprintf(buf, sizeof buf, "%s%d", j < n ? "dist" : "obs", (j < n ? j : j - n) + 1);
+        SET_STRING_ELT(names, j, Rf_mkChar(buf));
+    }
+    const double* l = REAL(loc_xy);
+    const double* o = REAL(obs_xy);
+    const int rc = rfsi_near_obs_cols_f64(l, l + npix, (int64_t)npix, o, o + nobs, REAL(obs_z), (int32_t)nobs, n,
+                                          Rf_asLogical(rm_dupl) ? 1 : 0, cols, cols + n, NULL, Rf_asInteger(device));
+    check_rc(rc);
+    Rf_setAttrib(out, R_NamesSymbol, names);
+    SEXP rn = PROTECT(Rf_allocVector(INTSXP, 2));     /* compact row names c(NA_integer_, -npix) */
+    INTEGER(rn)[0] = NA_INTEGER; INTEGER(rn)[1] = -(int)npix;
+    Rf_setAttrib(out, R_RowNamesSymbol, rn);
+    SEXP cls = PROTECT(Rf_mkString("data.frame"));
+    Rf_setAttrib(out, R_ClassSymbol, cls);
+    UNPROTECT(4);
     return out;
 }
 
@@ -282,6 +319,7 @@ SEXP C_rfsi_pred_maps(SEXP h, SEXP loc_xy, SEXP cov_loc, SEXP obs_xy, SEXP obs_z
 
 static const R_CallMethodDef call_methods[] = {
     {"C_rfsi_near_obs", (DL_FUNC)&C_rfsi_near_obs, 6},
+    {"C_rfsi_near_obs_df", (DL_FUNC)&C_rfsi_near_obs_df, 6},
     {"C_rfsi_near_obs_days", (DL_FUNC)&C_rfsi_near_obs_days, 5},
     {"C_rfsi_forest_new", (DL_FUNC)&C_rfsi_forest_new, 7},
     {"C_rfsi_predict", (DL_FUNC)&C_rfsi_predict, 4},

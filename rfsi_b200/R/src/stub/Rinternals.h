@@ -10,14 +10,14 @@ typedef int Rboolean;
 #define TRUE 1
 #define FALSE 0
 enum { INTSXP = 13, REALSXP = 14, STRSXP = 16, VECSXP = 19 };
-extern SEXP R_NilValue, R_NamesSymbol;
+extern SEXP R_NilValue, R_NamesSymbol, R_ClassSymbol, R_RowNamesSymbol;
 double* REAL(SEXP); int* INTEGER(SEXP); R_xlen_t XLENGTH(SEXP);
 int Rf_nrows(SEXP); int Rf_ncols(SEXP); int Rf_isReal(SEXP); int Rf_asInteger(SEXP); int Rf_asLogical(SEXP);
 SEXP Rf_allocMatrix(int, int, int); SEXP Rf_allocVector(int, R_xlen_t); SEXP Rf_protect(SEXP); void Rf_unprotect(int);
 #define PROTECT(x) Rf_protect(x)
 #define UNPROTECT(n) Rf_unprotect(n)
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP); SEXP VECTOR_ELT(SEXP, R_xlen_t); void SET_STRING_ELT(SEXP, R_xlen_t, SEXP);
-SEXP Rf_mkChar(const char*); SEXP Rf_setAttrib(SEXP, SEXP, SEXP); SEXP Rf_install(const char*);
+SEXP Rf_mkChar(const char*); SEXP Rf_mkString(const char*); SEXP Rf_setAttrib(SEXP, SEXP, SEXP); SEXP Rf_install(const char*);
 void Rf_error(const char*, ...); void Rf_warning(const char*, ...);
 char* R_alloc(size_t, int);
 int TYPEOF(SEXP);

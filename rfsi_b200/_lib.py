@@ -96,6 +96,7 @@ _SIGNATURES = [
     ("rfsi_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("rfsi_host_free", None, [_P]),
     ("rfsi_near_obs_f64", C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int]),
+    ("rfsi_near_obs_cols_f64", C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int]),
     ("rfsi_near_obs_f32", C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int]),
     ("rfsi_dev_near_obs_f64", C.c_int,
      [_P, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int, _P]),

@@ -81,16 +81,17 @@ def near_obs(locations, observations, zcol=2, n_obs: int = 10, locations_x_y=(0,
     npix, nobs = loc.shape[0], obs.shape[0]
     lx, ly = _f64(loc[:, 0]), _f64(loc[:, 1])
     ox, oy, oz = _f64(obs[:, 0]), _f64(obs[:, 1]), _f64(z)
-    dist = np.empty((n_obs, npix), dtype=np.float64)   # column-major npix x n_obs
-    val = np.empty((n_obs, npix), dtype=np.float64)
+    # one array per column, filled in place by the engine (rfsi_near_obs_cols_f64): the frame below wraps them
+    cols = [np.empty(npix, dtype=np.float64) for _ in range(2 * n_obs)]
     idx = np.empty((n_obs, npix), dtype=np.int32) if return_idx else None
-    rc = _lib.load().rfsi_near_obs_f64(_ptr(lx), _ptr(ly), npix, _ptr(ox), _ptr(oy), _ptr(oz), nobs, n_obs,
-                                      1 if rm_dupl else 0, _ptr(dist), _ptr(val), _ptr(idx), device)
+    cptr = (C.c_void_p * (2 * n_obs))(*[c.ctypes.data for c in cols])
+    iptr = (C.c_void_p * n_obs)(*[idx[j].ctypes.data for j in range(n_obs)]) if return_idx else None
+    rc = _lib.load().rfsi_near_obs_cols_f64(_ptr(lx), _ptr(ly), npix, _ptr(ox), _ptr(oy), _ptr(oz), nobs, n_obs,
+                                           1 if rm_dupl else 0, cptr, C.byref(cptr, n_obs * C.sizeof(C.c_void_p)), iptr, device)
     if _lib.check(rc) == _lib.RFSI_W_TOO_FEW_OBS:
         warnings.warn(_lib.last_error())
     names = [f"dist{j + 1}" for j in range(n_obs)] + [f"obs{j + 1}" for j in range(n_obs)]
-    cols = [dist[j] for j in range(n_obs)] + [val[j] for j in range(n_obs)]
-    out = pd.DataFrame(dict(zip(names, cols))) if pd is not None else dict(zip(names, cols))
+    out = pd.DataFrame(dict(zip(names, cols)), copy=False) if pd is not None else dict(zip(names, cols))
     return (out, idx.T) if return_idx else out
 
 

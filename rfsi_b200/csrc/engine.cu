@@ -185,6 +185,75 @@ struct Trace {
     }
 };
 
+
+// ---- host staging ------------------------------------------------------------------------------------
+// The R-shaped entry points hand over PAGEABLE memory, and their outputs are freshly allocated R vectors whose
+// pages have never been touched.  Measured on the B200 hosts (profiles/r02_a_host_copy_bench.txt, 100 MB): D2H into
+// pinned memory 1.8 ms, cudaMemcpy into mapped pageable memory 5.4 ms, into FRESH pageable memory 46.5 ms (the
+// driver's single staging thread takes every page fault); memcpy pinned -> fresh pages with 4 / 8 host threads
+// 5.3 / 3.5 ms.  So results travel device -> pinned slot -> caller's array, the last hop on several host threads,
+// each thread driving its own chunks through its own stream (chunk k, k + W, ... on worker k of W).
+class PinnedPool {
+public:
+    static PinnedPool& get() { static PinnedPool p; return p; }
+    void* acquire(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (auto& b : bufs_)
+                if (!b.busy && b.bytes >= bytes && b.pid == (long)getpid()) { b.busy = true; return b.p; }
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        std::lock_guard<std::mutex> lk(mu_);
+        bufs_.push_back({p, bytes, true, (long)getpid()});
+        return p;
+    }
+    void release(void* p) {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto& b : bufs_) if (b.p == p) b.busy = false;
+    }
+private:
+    struct Buf { void* p; size_t bytes; bool busy; long pid; };
+    std::mutex mu_;
+    std::vector<Buf> bufs_;
+};
+struct PinnedBuf {
+    void* p = nullptr;
+    ~PinnedBuf() { if (p) PinnedPool::get().release(p); }
+    int alloc(size_t bytes) {
+        p = PinnedPool::get().acquire(bytes);
+        if (!p) return fail(RFSI_E_OOM, "pinned staging buffer of %zu bytes", bytes);
+        return RFSI_OK;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+inline int host_workers(int64_t nchunks) {
+    const int want = env_int("RFSI_B200_HOST_THREADS", 4);
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(want, hw), nchunks));
+}
+// run fn(worker) on `workers` host threads (the caller's thread is worker 0); first error wins, messages carried over
+template <class Fn>
+int run_workers(int workers, int device, Fn&& fn) {
+    std::vector<int> rc((size_t)workers, RFSI_OK);
+    std::vector<std::string> msg((size_t)workers);
+    std::vector<std::thread> th;
+    for (int w = 1; w < workers; ++w)
+        th.emplace_back([&, w] {
+            if (cudaSetDevice(device) != cudaSuccess) { rc[(size_t)w] = RFSI_E_CUDA; msg[(size_t)w] = "cudaSetDevice failed in a staging thread"; return; }
+            rc[(size_t)w] = fn(w);
+            if (rc[(size_t)w] != RFSI_OK) msg[(size_t)w] = g_err;   // g_err is thread-local
+        });
+    rc[0] = fn(0);
+    if (rc[0] != RFSI_OK) msg[0] = g_err;
+    for (auto& t : th) t.join();
+    for (int w = 0; w < workers; ++w)
+        if (rc[(size_t)w] < 0) { g_err = msg[(size_t)w]; return rc[(size_t)w]; }
+    for (int w = 0; w < workers; ++w)
+        if (rc[(size_t)w] > 0) { g_err = msg[(size_t)w]; return rc[(size_t)w]; }
+    return RFSI_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------
@@ -1068,12 +1137,12 @@ constexpr int kMaxProbs = 128;
 inline int64_t leaf_ids_ld(int T) { return ((int64_t)T + 7) & ~int64_t(7); }
 inline size_t leaf_ids_bytes(int64_t rows, int T) { return sizeof(uint32_t) * (size_t)rows * (size_t)leaf_ids_ld(T); }
 
-template <int R, class K, bool DIRECT>
+template <int R, class K>
 int launch_qrf_r(const uint32_t* leaf_ids, const K* leaf_key, const double* dict, const unsigned char* skip, int64_t nrows,
                  int T, const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr,
                  cudaStream_t stream)
 {
-    auto kern = qrf_quantile_kernel<R, K, DIRECT>;
+    auto kern = qrf_quantile_kernel<R, K>;
     const size_t smem = qrf_smem_bytes<R, K>();
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, per_sm = 0;
@@ -1085,6 +1154,24 @@ int launch_qrf_r(const uint32_t* leaf_ids, const K* leaf_key, const double* dict
     const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * std::max(per_sm, 1));
     kern<<<grid, 32 * kQrfWarps, smem, stream>>>(leaf_ids, leaf_ids_ld(T), leaf_key, dict, skip, nrows, T, probs_dev, nprobs,
                                                  out_q, ld_q, out_iqr);
+    return RFSI_OK;
+}
+
+// direct form (qrf.cuh): the scratch rows hold the keys, nothing to gather
+template <int R>
+int launch_qrf_direct(const uint32_t* keys, const double* dict, const unsigned char* skip, int64_t nrows, int T,
+                      const double* probs_dev, int nprobs, double* out_q, int64_t ld_q, int16_t* out_iqr, cudaStream_t stream)
+{
+    auto kern = qrf_direct_kernel<R>;
+    const size_t smem = qrf_direct_smem_bytes<R>();
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0, per_sm = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kQrfWarps, smem));
+    const int64_t want = (nrows + kQrfWarps - 1) / kQrfWarps;   // persistent warps: one resident wave, a contiguous run of rows per CTA
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * std::max(per_sm, 1));
+    kern<<<grid, 32 * kQrfWarps, smem, stream>>>(keys, leaf_ids_ld(T), dict, skip, nrows, T, probs_dev, nprobs, out_q, ld_q, out_iqr);
     return RFSI_OK;
 }
 
@@ -1110,12 +1197,12 @@ int launch_qrf(const uint32_t* leaf_ids, const LeafSamples& ls, const unsigned c
     ProfScope ps(PROF_QRF, stream);
 #define RFSI_QRF_CASE(RR)                                                                                              \
     do {                                                                                                               \
-        if (ls.direct) RF_TRY((launch_qrf_r<RR, uint32_t, true>(leaf_ids, nullptr, ls.dict, skip, nrows, T, probs_dev, nprobs, \
-                                                                out_q, ld_q, out_iqr, stream)));                       \
-        else if (ls.rank) RF_TRY((launch_qrf_r<RR, uint32_t, false>(leaf_ids, ls.rank, ls.dict, skip, nrows, T, probs_dev, nprobs, \
-                                                                    out_q, ld_q, out_iqr, stream)));                   \
-        else RF_TRY((launch_qrf_r<RR, double, false>(leaf_ids, ls.sample, nullptr, skip, nrows, T, probs_dev, nprobs, out_q, \
-                                                     ld_q, out_iqr, stream)));                                         \
+        if (ls.direct) RF_TRY((launch_qrf_direct<RR>(leaf_ids, ls.dict, skip, nrows, T, probs_dev, nprobs, out_q, ld_q,   \
+                                                     out_iqr, stream)));                                               \
+        else if (ls.rank) RF_TRY((launch_qrf_r<RR, uint32_t>(leaf_ids, ls.rank, ls.dict, skip, nrows, T, probs_dev, nprobs, \
+                                                             out_q, ld_q, out_iqr, stream)));                          \
+        else RF_TRY((launch_qrf_r<RR, double>(leaf_ids, ls.sample, nullptr, skip, nrows, T, probs_dev, nprobs, out_q,   \
+                                              ld_q, out_iqr, stream)));                                                \
     } while (0)
     if (R <= 1) RFSI_QRF_CASE(1);
     else if (R <= 2) RFSI_QRF_CASE(2);
@@ -1189,22 +1276,23 @@ extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, i
     return rc;
 }
 
-extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix, const double* obs_x,
-                                 const double* obs_y, const double* obs_z, int32_t nobs, int32_t n_obs,
-                                 int32_t rm_dupl, double* out_dist, double* out_obs, int32_t* out_idx, int device)
+namespace {
+
+// near.obs with host buffers; column j of dist / obs / idx goes to dist_cols[j] / obs_cols[j] / idx_cols[j] (nullable array)
+int host_near_obs(const double* loc_x, const double* loc_y, int64_t npix, const double* obs_x, const double* obs_y,
+                  const double* obs_z, int32_t nobs, int32_t n_obs, int32_t rm_dupl, double* const* dist_cols,
+                  double* const* obs_cols, int32_t* const* idx_cols, int device)
 {
-    if (npix < 0 || nobs < 0 || n_obs < 1) return fail(RFSI_E_ARG, "near_obs: npix/nobs must be >= 0, n.obs >= 1");
-    if (npix > 0 && (!loc_x || !loc_y || !out_dist || !out_obs)) return fail(RFSI_E_ARG, "near_obs: NULL buffer");
-    if (nobs > 0 && (!obs_x || !obs_y || !obs_z)) return fail(RFSI_E_ARG, "near_obs: NULL observations");
     for (int32_t s = 0; s < nobs; ++s)
         if (obs_x[s] != obs_x[s] || obs_y[s] != obs_y[s])
             return fail(RFSI_E_NA_INPUT, "near_obs: observation %d has an NA coordinate", s + 1);
     RF_TRY(use_device(device));
     if (npix == 0) return RFSI_OK;
+    Trace tr;
 
     std::vector<double2> xy((size_t)std::max(nobs, 1));
     for (int32_t s = 0; s < nobs; ++s) xy[s] = make_double2(obs_x[s], obs_y[s]);
-    DevBuf d_xy, d_z, d_flags;
+    DevBuf d_xy, d_z, d_flags, d_cells;
     RF_TRY(d_xy.alloc(sizeof(double2) * xy.size()));
     RF_TRY(d_z.alloc(sizeof(double) * (size_t)std::max(nobs, 1)));
     RF_TRY(d_flags.alloc(2 * sizeof(int)));
@@ -1212,58 +1300,77 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
     if (nobs > 0) CU_TRY(cudaMemcpy(d_z.p, obs_z, sizeof(double) * nobs, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemset(d_flags.p, 0, 2 * sizeof(int)));
     const bool use_cells = nobs >= cells_min_S();
-    const int64_t chunk = std::min<int64_t>(npix, 1 << 20);
-    DevBuf d_cells, d_perm[2];
     CellsWs cells;
     if (use_cells) {
         RF_TRY(d_cells.alloc(cells_ws_bytes(nobs)));
         cells = carve_cells(d_cells.p, nobs);
         RF_TRY(build_cells(d_xy.as<double2>(), nobs, cells, nullptr));
-        for (int s = 0; s < (npix <= chunk ? 1 : 2); ++s) RF_TRY(d_perm[s].alloc(loc_perm_bytes(chunk)));
         CU_TRY(cudaStreamSynchronize(nullptr));
     }
-
-    DevBuf d_lx[2], d_ly[2], d_dist[2], d_obs[2], d_idx[2];
-    Stream st[2];
-    for (int s = 0; s < 2; ++s) {
-        RF_TRY(st[s].create());
-        RF_TRY(d_lx[s].alloc(sizeof(double) * chunk));
-        RF_TRY(d_ly[s].alloc(sizeof(double) * chunk));
-        RF_TRY(d_dist[s].alloc(sizeof(double) * chunk * n_obs));
-        RF_TRY(d_obs[s].alloc(sizeof(double) * chunk * n_obs));
-        if (out_idx) RF_TRY(d_idx[s].alloc(sizeof(int32_t) * chunk * n_obs));
-        if (npix <= chunk) break;
+    // chunks of ~32 k locations: worker w takes chunks w, w + W, ...; each worker has its own stream, device
+    // buffers and pinned slot, and scatters its finished chunk into the caller's columns itself
+    const int64_t chunk = std::min<int64_t>(npix, std::max<int64_t>(4096, env_int("RFSI_B200_NEAR_CHUNK", 32768)));
+    const int64_t nchunks = (npix + chunk - 1) / chunk;
+    const int W = host_workers(nchunks);
+    const size_t row_bytes = (size_t)n_obs * (2 * sizeof(double) + (idx_cols ? sizeof(int32_t) : 0));
+    struct Lane {
+        DevBuf lx, ly, dist, obs, idx, perm;
+        PinnedBuf stage;
+        Stream st;   // last: destroyed (synchronised) before the buffers above
+    };
+    std::vector<Lane> lane((size_t)W);
+    for (int w = 0; w < W; ++w) {
+        Lane& ln = lane[(size_t)w];
+        RF_TRY(ln.st.create());
+        RF_TRY(ln.lx.alloc(sizeof(double) * chunk));
+        RF_TRY(ln.ly.alloc(sizeof(double) * chunk));
+        RF_TRY(ln.dist.alloc(sizeof(double) * chunk * n_obs));
+        RF_TRY(ln.obs.alloc(sizeof(double) * chunk * n_obs));
+        if (idx_cols) RF_TRY(ln.idx.alloc(sizeof(int32_t) * chunk * n_obs));
+        if (use_cells) RF_TRY(ln.perm.alloc(loc_perm_bytes(chunk)));
+        RF_TRY(ln.stage.alloc(row_bytes * (size_t)chunk));
     }
     RF_TRY(pool_ready());
-    int slot = 0;
-    for (int64_t p0 = 0; p0 < npix; p0 += chunk, slot ^= 1) {
-        const int64_t cur = std::min(chunk, npix - p0);
-        cudaStream_t s = st[slot].s;
-        CU_TRY(cudaMemcpyAsync(d_lx[slot].p, loc_x + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(d_ly[slot].p, loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
-        LocSpec L{d_lx[slot].as<double>(), d_ly[slot].as<double>(), 0, 0, 0, 0, 1, 0};
-        const int32_t* perm = nullptr;
-        if (use_cells) RF_TRY(build_loc_perm(L, cur, d_perm[slot].p, &perm, s));
-        if (use_cells)
-            RF_TRY(launch_knn_cells<KNN_FINAL>(L, cur, cells, perm, n_obs + 1, d_z.as<double>(), rm_dupl,
-                                               d_dist[slot].as<double>(), d_obs[slot].as<double>(),
-                                               out_idx ? d_idx[slot].as<int32_t>() : nullptr, cur, d_flags.as<int>(),
-                                               d_flags.as<int>() + 1, s));
-        else
-            RF_TRY(launch_knn<KNN_FINAL>(L, cur, d_xy.as<double2>(), nobs, n_obs + 1, d_z.as<double>(), rm_dupl,
-                                         d_dist[slot].as<double>(), d_obs[slot].as<double>(),
-                                         out_idx ? d_idx[slot].as<int32_t>() : nullptr, cur, d_flags.as<int>(),
-                                         d_flags.as<int>() + 1, s));
-        CU_TRY(cudaMemcpy2DAsync(out_dist + p0, sizeof(double) * npix, d_dist[slot].p, sizeof(double) * cur,
-                                 sizeof(double) * cur, n_obs, cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaMemcpy2DAsync(out_obs + p0, sizeof(double) * npix, d_obs[slot].p, sizeof(double) * cur,
-                                 sizeof(double) * cur, n_obs, cudaMemcpyDeviceToHost, s));
-        if (out_idx)
-            CU_TRY(cudaMemcpy2DAsync(out_idx + p0, sizeof(int32_t) * npix, d_idx[slot].p, sizeof(int32_t) * cur,
-                                     sizeof(int32_t) * cur, n_obs, cudaMemcpyDeviceToHost, s));
-    }
-    for (int s = 0; s < 2; ++s)
-        if (st[s].s) CU_TRY(cudaStreamSynchronize(st[s].s));
+    tr.mark("near.obs setup");
+    const int rc = run_workers(W, device, [&](int w) -> int {
+        Lane& ln = lane[(size_t)w];
+        cudaStream_t s = ln.st.s;
+        for (int64_t c = w; c < nchunks; c += W) {
+            const int64_t p0 = c * chunk, cur = std::min(chunk, npix - p0);
+            CU_TRY(cudaMemcpyAsync(ln.lx.p, loc_x + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+            CU_TRY(cudaMemcpyAsync(ln.ly.p, loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+            LocSpec L{ln.lx.as<double>(), ln.ly.as<double>(), 0, 0, 0, 0, 1, 0};
+            const int32_t* perm = nullptr;
+            if (use_cells) {
+                RF_TRY(build_loc_perm(L, cur, ln.perm.p, &perm, s));
+                RF_TRY(launch_knn_cells<KNN_FINAL>(L, cur, cells, perm, n_obs + 1, d_z.as<double>(), rm_dupl,
+                                                   ln.dist.as<double>(), ln.obs.as<double>(),
+                                                   idx_cols ? ln.idx.as<int32_t>() : nullptr, cur, d_flags.as<int>(),
+                                                   d_flags.as<int>() + 1, s));
+            } else {
+                RF_TRY(launch_knn<KNN_FINAL>(L, cur, d_xy.as<double2>(), nobs, n_obs + 1, d_z.as<double>(), rm_dupl,
+                                             ln.dist.as<double>(), ln.obs.as<double>(),
+                                             idx_cols ? ln.idx.as<int32_t>() : nullptr, cur, d_flags.as<int>(),
+                                             d_flags.as<int>() + 1, s));
+            }
+            char* hs = ln.stage.as<char>();
+            double* h_dist = reinterpret_cast<double*>(hs);
+            double* h_obs = h_dist + (size_t)cur * n_obs;
+            int32_t* h_idx = reinterpret_cast<int32_t*>(h_obs + (size_t)cur * n_obs);
+            CU_TRY(cudaMemcpyAsync(h_dist, ln.dist.p, sizeof(double) * cur * n_obs, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaMemcpyAsync(h_obs, ln.obs.p, sizeof(double) * cur * n_obs, cudaMemcpyDeviceToHost, s));
+            if (idx_cols) CU_TRY(cudaMemcpyAsync(h_idx, ln.idx.p, sizeof(int32_t) * cur * n_obs, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));
+            for (int j = 0; j < n_obs; ++j) {   // the caller's (possibly never touched) pages: this thread takes the faults
+                memcpy(dist_cols[j] + p0, h_dist + (size_t)j * cur, sizeof(double) * cur);
+                memcpy(obs_cols[j] + p0, h_obs + (size_t)j * cur, sizeof(double) * cur);
+                if (idx_cols) memcpy(idx_cols[j] + p0, h_idx + (size_t)j * cur, sizeof(int32_t) * cur);
+            }
+        }
+        return RFSI_OK;
+    });
+    tr.mark("near.obs chunks (search + D2H + scatter)");
+    RF_TRY(rc);
     int flags[2] = {0, 0};
     CU_TRY(cudaMemcpy(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost));
     if (flags[1]) return fail(RFSI_E_NA_INPUT, "near_obs: a location has an NA coordinate");
@@ -1272,6 +1379,45 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
         return RFSI_W_TOO_FEW_OBS;
     }
     return RFSI_OK;
+}
+
+int check_near_obs_args(int64_t npix, int32_t nobs, int32_t n_obs, const void* loc_x, const void* loc_y, const void* a,
+                        const void* b, const void* ox, const void* oy, const void* oz) {
+    if (npix < 0 || nobs < 0 || n_obs < 1 || n_obs > kMaxNObs)
+        return fail(RFSI_E_ARG, "near_obs: npix/nobs must be >= 0, 1 <= n.obs <= %d", kMaxNObs);
+    if (npix > 0 && (!loc_x || !loc_y || !a || !b)) return fail(RFSI_E_ARG, "near_obs: NULL buffer");
+    if (nobs > 0 && (!ox || !oy || !oz)) return fail(RFSI_E_ARG, "near_obs: NULL observations");
+    return RFSI_OK;
+}
+
+}  // namespace
+
+extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64_t npix, const double* obs_x,
+                                 const double* obs_y, const double* obs_z, int32_t nobs, int32_t n_obs,
+                                 int32_t rm_dupl, double* out_dist, double* out_obs, int32_t* out_idx, int device)
+{
+    RF_TRY(check_near_obs_args(npix, nobs, n_obs, loc_x, loc_y, out_dist, out_obs, obs_x, obs_y, obs_z));
+    std::vector<double*> dc((size_t)n_obs), oc((size_t)n_obs);
+    std::vector<int32_t*> ic((size_t)n_obs);
+    for (int j = 0; j < n_obs; ++j) {
+        dc[(size_t)j] = out_dist + (size_t)j * npix;
+        oc[(size_t)j] = out_obs + (size_t)j * npix;
+        ic[(size_t)j] = out_idx ? out_idx + (size_t)j * npix : nullptr;
+    }
+    return host_near_obs(loc_x, loc_y, npix, obs_x, obs_y, obs_z, nobs, n_obs, rm_dupl, dc.data(), oc.data(),
+                         out_idx ? ic.data() : nullptr, device);
+}
+
+extern "C" int rfsi_near_obs_cols_f64(const double* loc_x, const double* loc_y, int64_t npix, const double* obs_x,
+                                      const double* obs_y, const double* obs_z, int32_t nobs, int32_t n_obs,
+                                      int32_t rm_dupl, double* const* dist_cols, double* const* obs_cols,
+                                      int32_t* const* idx_cols, int device)
+{
+    RF_TRY(check_near_obs_args(npix, nobs, n_obs, loc_x, loc_y, dist_cols, obs_cols, obs_x, obs_y, obs_z));
+    for (int j = 0; j < n_obs && npix > 0; ++j)
+        if (!dist_cols[j] || !obs_cols[j] || (idx_cols && !idx_cols[j]))
+            return fail(RFSI_E_ARG, "near_obs: column %d of the output is NULL", j + 1);
+    return host_near_obs(loc_x, loc_y, npix, obs_x, obs_y, obs_z, nobs, n_obs, rm_dupl, dist_cols, obs_cols, idx_cols, device);
 }
 
 // fp32 twin of near.obs: float buffers in and out; coordinates are widened to fp64 on the
@@ -1513,48 +1659,72 @@ int host_forest(const rfsi_forest_t* f, const double* X, int64_t npix, int64_t l
     rfsi_forest::Image im;
     RF_TRY(forest_image(f, device, &im));
     const int F = f->nfeat, T = f->ntrees;
-    // rows per chunk: bound the X tile (and the quantile scratch) to ~256 MB
-    int64_t chunk = std::max<int64_t>(4096, (int64_t(256) << 20) / (8 * (int64_t)F));
-    if (out_q) chunk = std::min(chunk, std::max<int64_t>(4096, (int64_t(512) << 20) / (8 * (int64_t)T)));
+    Trace tr;
+    // Chunks of rows, worker w of W takes chunks w, w + W, ...: it gathers its rows of the caller's (pageable) columns
+    // into a pinned slot, sends them in one copy, walks the forest on its own stream, brings the results back into the
+    // pinned slot and scatters them into the caller's (possibly never touched) arrays -- see "host staging" above.
+    int64_t chunk = std::max<int64_t>(4096, (int64_t(16) << 20) / (8 * (int64_t)F));          // ~16 MB of X per chunk
+    if (out_q) chunk = std::min(chunk, std::max<int64_t>(4096, (int64_t(256) << 20) / (4 * (int64_t)T)));
+    if (out_term) chunk = std::min(chunk, std::max<int64_t>(4096, (int64_t(64) << 20) / (4 * (int64_t)T)));
+    if (env_int("RFSI_B200_PREDICT_CHUNK", 0) > 0) chunk = std::max(256, env_int("RFSI_B200_PREDICT_CHUNK", 0));   // tests
     chunk = std::min<int64_t>(npix, chunk / 256 * 256);
+    const int64_t nchunks = (npix + chunk - 1) / chunk;
+    const int W = host_workers(nchunks);
     DevBuf d_flag;
     RF_TRY(d_flag.alloc(sizeof(int)));
     CU_TRY(cudaMemset(d_flag.p, 0, sizeof(int)));
-    DevBuf d_X[2], d_mean[2], d_q[2], d_term[2], d_scr[2];
-    Stream st[2];
-    for (int s = 0; s < 2; ++s) {
-        RF_TRY(st[s].create());
-        RF_TRY(d_X[s].alloc(sizeof(double) * chunk * F));
-        if (out_mean) RF_TRY(d_mean[s].alloc(sizeof(double) * chunk));
+    const size_t out_row = (out_mean ? sizeof(double) : 0) + (out_q ? sizeof(double) * nprobs : 0) + (out_term ? sizeof(int32_t) * T : 0);
+    struct Lane {
+        DevBuf X, mean, q, term, scr;
+        PinnedBuf in, out;
+        Stream st;   // last: destroyed (synchronised) before the buffers above
+    };
+    std::vector<Lane> lane((size_t)W);
+    for (int w = 0; w < W; ++w) {
+        Lane& ln = lane[(size_t)w];
+        RF_TRY(ln.st.create());
+        RF_TRY(ln.X.alloc(sizeof(double) * chunk * F));
+        if (out_mean) RF_TRY(ln.mean.alloc(sizeof(double) * chunk));
         if (out_q) {
-            RF_TRY(d_q[s].alloc(sizeof(double) * chunk * nprobs));
-            RF_TRY(d_scr[s].alloc(rfsi_dev_forest_scratch_bytes(f, chunk, nprobs)));
+            RF_TRY(ln.q.alloc(sizeof(double) * chunk * nprobs));
+            RF_TRY(ln.scr.alloc(rfsi_dev_forest_scratch_bytes(f, chunk, nprobs)));
         }
-        if (out_term) RF_TRY(d_term[s].alloc(sizeof(int32_t) * chunk * T));
-        if (npix <= chunk) break;
+        if (out_term) RF_TRY(ln.term.alloc(sizeof(int32_t) * chunk * T));
+        RF_TRY(ln.in.alloc(sizeof(double) * (size_t)chunk * F));
+        RF_TRY(ln.out.alloc(out_row * (size_t)chunk));
     }
     RF_TRY(pool_ready());
-    int slot = 0;
-    for (int64_t p0 = 0; p0 < npix; p0 += chunk, slot ^= 1) {
-        const int64_t cur = std::min(chunk, npix - p0);
-        cudaStream_t s = st[slot].s;
-        CU_TRY(cudaMemcpy2DAsync(d_X[slot].p, sizeof(double) * cur, X + p0, sizeof(double) * ldx,
-                                 sizeof(double) * cur, F, cudaMemcpyHostToDevice, s));
-        RF_TRY(rfsi_dev_forest_predict(f, d_X[slot].as<double>(), cur, cur, out_mean ? d_mean[slot].as<double>() : nullptr,
-                                       probs, nprobs, out_q ? d_q[slot].as<double>() : nullptr,
-                                       out_term ? d_term[slot].as<int32_t>() : nullptr, d_scr[slot].p, nullptr,
-                                       d_flag.as<int>(), device, s));
-        if (out_mean)
-            CU_TRY(cudaMemcpyAsync(out_mean + p0, d_mean[slot].p, sizeof(double) * cur, cudaMemcpyDeviceToHost, s));
-        if (out_q)
-            CU_TRY(cudaMemcpy2DAsync(out_q + p0, sizeof(double) * npix, d_q[slot].p, sizeof(double) * cur,
-                                     sizeof(double) * cur, nprobs, cudaMemcpyDeviceToHost, s));
-        if (out_term)
-            CU_TRY(cudaMemcpy2DAsync(out_term + p0, sizeof(int32_t) * npix, d_term[slot].p, sizeof(int32_t) * cur,
-                                     sizeof(int32_t) * cur, T, cudaMemcpyDeviceToHost, s));
-    }
-    for (int s = 0; s < 2; ++s)
-        if (st[s].s) CU_TRY(cudaStreamSynchronize(st[s].s));
+    tr.mark("predict setup");
+    const int rc = run_workers(W, device, [&](int w) -> int {
+        Lane& ln = lane[(size_t)w];
+        cudaStream_t s = ln.st.s;
+        for (int64_t c = w; c < nchunks; c += W) {
+            const int64_t p0 = c * chunk, cur = std::min(chunk, npix - p0);
+            double* hx = ln.in.as<double>();
+            for (int j = 0; j < F; ++j) memcpy(hx + (size_t)j * cur, X + (size_t)j * ldx + p0, sizeof(double) * cur);
+            CU_TRY(cudaMemcpyAsync(ln.X.p, hx, sizeof(double) * cur * F, cudaMemcpyHostToDevice, s));
+            RF_TRY(rfsi_dev_forest_predict(f, ln.X.as<double>(), cur, cur, out_mean ? ln.mean.as<double>() : nullptr,
+                                           probs, nprobs, out_q ? ln.q.as<double>() : nullptr,
+                                           out_term ? ln.term.as<int32_t>() : nullptr, ln.scr.p, nullptr,
+                                           d_flag.as<int>(), device, s));
+            char* ho = ln.out.as<char>();
+            double* h_mean = reinterpret_cast<double*>(ho);
+            double* h_q = h_mean + (out_mean ? cur : 0);
+            int32_t* h_term = reinterpret_cast<int32_t*>(h_q + (out_q ? (size_t)cur * nprobs : 0));
+            if (out_mean) CU_TRY(cudaMemcpyAsync(h_mean, ln.mean.p, sizeof(double) * cur, cudaMemcpyDeviceToHost, s));
+            if (out_q) CU_TRY(cudaMemcpyAsync(h_q, ln.q.p, sizeof(double) * cur * nprobs, cudaMemcpyDeviceToHost, s));
+            if (out_term) CU_TRY(cudaMemcpyAsync(h_term, ln.term.p, sizeof(int32_t) * cur * T, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));
+            if (out_mean) memcpy(out_mean + p0, h_mean, sizeof(double) * cur);
+            if (out_q)
+                for (int j = 0; j < nprobs; ++j) memcpy(out_q + (size_t)j * npix + p0, h_q + (size_t)j * cur, sizeof(double) * cur);
+            if (out_term)
+                for (int t = 0; t < T; ++t) memcpy(out_term + (size_t)t * npix + p0, h_term + (size_t)t * cur, sizeof(int32_t) * cur);
+        }
+        return RFSI_OK;
+    });
+    tr.mark("predict chunks (gather + H2D + walk + D2H + scatter)");
+    RF_TRY(rc);
     int flag = 0;
     CU_TRY(cudaMemcpy(&flag, d_flag.p, sizeof flag, cudaMemcpyDeviceToHost));
     if (flag) return fail(RFSI_E_NA_INPUT, "predict: missing data in a column the forest uses");

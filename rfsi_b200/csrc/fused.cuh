@@ -105,15 +105,16 @@ __host__ __device__ constexpr size_t fused_feature_bytes(int F) {
     return Q ? (((size_t)F * P * sizeof(uint32_t) + 15) & ~(size_t)15) : (size_t)(F + 1) * P * sizeof(double);
 }
 
-// Resident CTAs per SM the register budget is cut for (rank images): 4 x 256 threads at 64 registers with up to 8
-// trees in flight per thread; more trees in flight need more registers, so fewer, fatter CTAs (3 at J = 12, 2 at
-// J = 16: the same number of walks in flight per SM, less shared memory -> more L1 for the forest).
+// Resident CTAs per SM the register budget is cut for (rank images).  Measured on the bench forest (profiles/r02_b):
+// 3 x 256 threads at 80 registers 129.6 M pixel-days/s, 4 x 256 at 64 registers 127.5 M (register moves and the
+// re-materialised shared-memory base go away, 92 KB instead of 60 KB of L1), 2 x 256 at 96 registers 106.9 M; more
+// than 8 trees in flight per thread is slower at any occupancy (J = 12: 122.6 M, J = 16: 111.4 M).
 template <int P, int J>
 __host__ __device__ constexpr int fused_min_blocks_q() {
 #ifdef RFSI_FUSED_MINB   // experiment builds (tools/build_variant.sh)
     return (P * 64 * 4 <= 65536) ? (J >= 16 ? 2 : (J >= 12 ? (RFSI_FUSED_MINB < 3 ? RFSI_FUSED_MINB : 3) : RFSI_FUSED_MINB)) : 2;
 #else
-    return (P * 64 * 4 <= 65536) ? (J >= 16 ? 2 : (J >= 12 ? 3 : 4)) : 2;
+    return (P * 64 * 4 <= 65536) ? (J >= 16 ? 2 : 3) : 2;
 #endif
 }
 

@@ -340,13 +340,12 @@ __device__ __forceinline__ void qrf_cp_async16(void* smem_dst, const void* gsrc)
 
 // leaf_ids: [nrows][ld_ids] pixel-major leaf index per tree (written by the forest walk);
 // leaf_key: the forest's per-leaf table (samples, or their dictionary ranks with NA = 0xFFFFFFFF);
-// DIRECT (rank keys only): leaf_ids already holds the KEYS -- the sector image keeps each leaf's key in the leaf's own
-// block, so the walk stores it instead of the leaf number and nothing is left to gather: rows are read coalesced.
+// (When the walk can store the keys themselves -- sector image -- qrf_direct_kernel below is used instead.)
 // dict: the sorted distinct sample values (rank form only); skip (nullable): rows whose outputs
 // are NA (their ids were never written).
 // out_q[j*ld_q + row] for j < nprobs (nullable); out_iqr_i16[row] (nullable) =
 // round-half-even((q[nprobs-1]-q[0])/2*100), NA -> -32767.
-template <int R, class K, bool DIRECT>
+template <int R, class K>
 __global__ void __launch_bounds__(32 * kQrfWarps, qrf_min_blocks<R>())
 qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, const K* __restrict__ leaf_key,
                     const double* __restrict__ dict, const unsigned char* __restrict__ skip, long long nrows, int T,
@@ -390,8 +389,7 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int t = r * 32 + lane;
-            if constexpr (DIRECT) vn[r] = (rw < row_end && !skipped && t < T) ? (K)s.ids[t] : KT::na();
-            else vn[r] = (rw < row_end && !skipped && t < T) ? __ldg(leaf_key + s.ids[t]) : KT::na();
+            vn[r] = (rw < row_end && !skipped && t < T) ? __ldg(leaf_key + s.ids[t]) : KT::na();
         }
         __syncwarp();                          // every lane has read s.ids: it may be refilled
     };
@@ -422,6 +420,77 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
         qrf_row_finish<R, K>(s, valid, mn, mx, lane, row, probs, nprobs, dict, out_q, ld_q, out_iqr_i16);
         __syncwarp();   // the row's shared memory is free again
     }
+}
+
+
+// ---- DIRECT form: the scratch rows already hold the keys ------------------------------------------
+// With the sector forest image the walk stores each leaf's quantile key (the dictionary rank of ranger's
+// random.node.values entry) instead of the leaf number, so nothing is gathered here: a row of T keys is T
+// coalesced 4-byte words.  Each warp owns a ring of three row buffers in shared memory filled by cp.async two rows
+// ahead; the row being selected is used IN PLACE as qrf's sample array (no staging through registers, which is
+// what held the gather form at 121 registers and two CTAs per SM).
+template <int R>
+__host__ __device__ constexpr size_t qrf_direct_warp_smem() { return (size_t)3 * R * 32 * 4 + 256 * 4 + 256 * 4 + 32 * 4; }
+template <int R>
+__host__ __device__ constexpr size_t qrf_direct_smem_bytes() { return kQrfWarps * qrf_direct_warp_smem<R>(); }
+template <int R> constexpr int qrf_direct_min_blocks() { return R >= 32 ? 1 : (R >= 16 ? 3 : 4); }
+
+template <int R>
+__global__ void __launch_bounds__(32 * kQrfWarps, qrf_direct_min_blocks<R>())
+qrf_direct_kernel(const uint32_t* __restrict__ keys, long long ld_ids, const double* __restrict__ dict,
+                  const unsigned char* __restrict__ skip, long long nrows, int T, const double* __restrict__ probs, int nprobs,
+                  double* __restrict__ out_q, long long ld_q, int16_t* __restrict__ out_iqr_i16)
+{
+    extern __shared__ __align__(16) unsigned char qrf_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char* base = qrf_smem + (size_t)wib * qrf_direct_warp_smem<R>();
+    uint32_t* ring = reinterpret_cast<uint32_t*>(base);
+    QrfWarp<uint32_t> s;
+    s.hist0 = reinterpret_cast<int*>(base + (size_t)3 * R * 32 * 4);
+    s.hist1 = s.hist0 + 256;
+    s.mem = reinterpret_cast<uint32_t*>(s.hist1 + 256);
+    s.ids = nullptr;
+    s.sv = ring;
+    // this CTA's contiguous run of rows; its warps take them kQrfWarps at a time
+    const long long per_cta = ((nrows + gridDim.x - 1) / gridDim.x + kQrfWarps - 1) / kQrfWarps * kQrfWarps;
+    const long long row_end = min(nrows, (long long)(blockIdx.x + 1) * per_cta);
+    const long long stride = kQrfWarps;
+    long long row = (long long)blockIdx.x * per_cta + wib;
+    if (row >= row_end) return;   // whole warp
+    const int nchunk = (int)(ld_ids >> 2);   // 16-byte pieces of one key row
+    constexpr uint32_t NA = 0xFFFFFFFFu;
+
+    auto fetch = [&](long long rw, int slot) {      // keys of row rw -> ring slot (asynchronous); always commits a group
+        if (rw < row_end && !(skip && skip[rw])) {
+            const uint32_t* src = keys + rw * ld_ids;
+            uint32_t* dst = ring + slot * (R * 32);
+            for (int c = lane; c < nchunk; c += 32) qrf_cp_async16(dst + 4 * c, src + 4 * c);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(row, 0);
+    fetch(row + stride, 1);
+    int slot = 0;
+    for (; row < row_end; row += stride) {
+        int nslot = slot + 2; nslot -= nslot >= 3 ? 3 : 0;
+        fetch(row + 2 * stride, nslot);                            // its previous tenant (row - stride) is finished
+        asm volatile("cp.async.wait_group 2;" ::: "memory");       // this row's group has landed
+        __syncwarp();
+        s.sv = ring + slot * (R * 32);
+        const bool skipped = skip && skip[row];
+        unsigned valid = 0;
+        uint32_t mn = NA, mx = 0u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int t = r * 32 + lane;
+            const uint32_t x = (!skipped && t < T) ? s.sv[t] : NA;
+            if (x != NA) { valid |= 1u << r; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }   // na.rm = TRUE
+        }
+        qrf_row_finish<R, uint32_t>(s, valid, mn, mx, lane, row, probs, nprobs, dict, out_q, ld_q, out_iqr_i16);
+        __syncwarp();   // the row's shared memory is free again
+        slot = slot + 1 == 3 ? 0 : slot + 1;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");               // nothing may land after the warp is gone
 }
 
 }  // namespace rfsi

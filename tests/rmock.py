@@ -46,6 +46,8 @@ class MockR:
         L.mock_last_error.restype = C.c_char_p
         L.mock_last_warning.restype = C.c_char_p
         L.mock_finalize.argtypes = [P]
+        L.mock_class.restype = C.c_char_p; L.mock_class.argtypes = [P]
+        L.mock_rownames.restype = P; L.mock_rownames.argtypes = [P]
 
     # ---- Python -> SEXP ----
     def sexp(self, x):
@@ -85,6 +87,12 @@ class MockR:
             n = L.mock_length(s)
             vals = [self.value(L.mock_elt(s, i)) for i in range(n)]
             names = [L.mock_name(s, i).decode() for i in range(n)]
+            if L.mock_class(s) == b"data.frame":
+                import pandas as pd
+                rn = self.value(L.mock_rownames(s))       # compact form c(NA, -nrow)
+                df = pd.DataFrame(dict(zip(names, vals)))
+                assert rn[0] == np.iinfo(np.int32).min and -rn[1] == len(df), "row.names must be c(NA_integer_, -nrow)"
+                return df
             return dict(zip(names, vals)) if all(names) else vals
         n = L.mock_length(s)
         dt = np.int32 if t == INTSXP else np.float64

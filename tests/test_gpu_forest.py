@@ -188,8 +188,10 @@ def test_quantiles_heavy_ties_rebucketing(mode):
     np.testing.assert_array_equal(got, oracle.forest_quantiles(flat.as_dict(), X, probs, threads=8))
 
 
-def test_deep_skinny_tree_and_chunked_rows():
-    """A degenerate chain tree (depth 300) and > 1 row chunk through the host API."""
+def test_deep_skinny_tree_and_chunked_rows(monkeypatch):
+    """A degenerate chain tree (depth 300) and many row chunks through the host API (several staging threads,
+    each with its own stream: engine.cu "host staging")."""
+    monkeypatch.setenv("RFSI_B200_PREDICT_CHUNK", "65536")
     depth = 300
     left = np.zeros(2 * depth + 1, dtype=np.int32); right = left.copy()
     var = left.copy(); val = np.zeros(2 * depth + 1)

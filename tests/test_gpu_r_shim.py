@@ -46,6 +46,11 @@ def test_near_obs_through_the_call_entry(R, case_model):
     np.testing.assert_array_equal(res["dist"], d)
     np.testing.assert_array_equal(res["obs"], o)
     np.testing.assert_array_equal(res["idx"], i)
+    # the data.frame form near.obs() itself returns: dist1..distN, obs1..obsN, filled column by column
+    df = R.call("C_rfsi_near_obs_df", loc, case.obs_xy, case.obs_z[0], case.n_obs, True, 0)
+    n = case.n_obs
+    assert list(df.columns) == [f"dist{j + 1}" for j in range(n)] + [f"obs{j + 1}" for j in range(n)]
+    np.testing.assert_array_equal(df.to_numpy(), np.column_stack([d, o]))
     # too few stations: NA-filled columns and an R warning, not an error
     before = R.warning_count()
     res = R.call("C_rfsi_near_obs", loc[:50], case.obs_xy[:3], case.obs_z[0, :3], 5, True, 0)

@@ -26,17 +26,21 @@ struct SEXPREC {
     R_xlen_t length;
     int has_dim, nrow, ncol;   /* dim attribute */
     void* data;
-    SEXP names;
+    SEXP names, klass, rownames;
     void* extptr;
     R_CFinalizer_t finalizer;
     struct SEXPREC* next;
 };
 enum { NILSXP_ = 0, SYMSXP_ = 1, CHARSXP_ = 9, EXTPTRSXP_ = 22 };
 
-static struct SEXPREC nil_obj = {NILSXP_, 0, 0, 0, 0, NULL, NULL, NULL, NULL, NULL};
-static struct SEXPREC names_sym = {SYMSXP_, 0, 0, 0, 0, NULL, NULL, NULL, NULL, NULL};
+static struct SEXPREC nil_obj = {NILSXP_, 0, 0, 0, 0, NULL, NULL, NULL, NULL, NULL, NULL, NULL};
+static struct SEXPREC names_sym = {SYMSXP_, 0, 0, 0, 0, NULL, NULL, NULL, NULL, NULL, NULL, NULL};
+static struct SEXPREC class_sym = {SYMSXP_, 0, 0, 0, 0, NULL, NULL, NULL, NULL, NULL, NULL, NULL};
+static struct SEXPREC rownames_sym = {SYMSXP_, 0, 0, 0, 0, NULL, NULL, NULL, NULL, NULL, NULL, NULL};
 SEXP R_NilValue = &nil_obj;
 SEXP R_NamesSymbol = &names_sym;
+SEXP R_ClassSymbol = &class_sym;
+SEXP R_RowNamesSymbol = &rownames_sym;
 int R_NaInt = INT32_MIN;
 double R_NaN;
 
@@ -50,7 +54,7 @@ static int ralloc_n = 0;
 
 static SEXP new_obj(int type, R_xlen_t n, size_t elt) {
     SEXP s = (SEXP)calloc(1, sizeof(struct SEXPREC));
-    s->type = type; s->length = n; s->names = R_NilValue;
+    s->type = type; s->length = n; s->names = s->klass = s->rownames = R_NilValue;
     s->data = (elt && n > 0) ? calloc((size_t)n, elt) : NULL;
     s->next = all_objects; all_objects = s;
     return s;
@@ -104,7 +108,13 @@ void SET_STRING_ELT(SEXP v, R_xlen_t i, SEXP x) {
 }
 SEXP Rf_mkChar(const char* c) { SEXP s = new_obj(CHARSXP_, (R_xlen_t)strlen(c), 0); s->data = strdup(c); return s; }
 SEXP Rf_install(const char* c) { SEXP s = Rf_mkChar(c); s->type = SYMSXP_; return s; }
-SEXP Rf_setAttrib(SEXP x, SEXP what, SEXP v) { if (what == R_NamesSymbol) x->names = v; return v; }
+SEXP Rf_setAttrib(SEXP x, SEXP what, SEXP v) {
+    if (what == R_NamesSymbol) x->names = v;
+    else if (what == R_ClassSymbol) x->klass = v;
+    else if (what == R_RowNamesSymbol) x->rownames = v;
+    return v;
+}
+SEXP Rf_mkString(const char* c) { SEXP s = Rf_allocVector(STRSXP, 1); ((SEXP*)s->data)[0] = Rf_mkChar(c); return s; }
 char* R_alloc(size_t n, int size) {
     void* p = calloc(n ? n : 1, (size_t)size);
     if (ralloc_n < 4096) ralloc_list[ralloc_n++] = p;
@@ -177,6 +187,8 @@ const char* mock_name(SEXP s, int i) {
     if (s->names == R_NilValue || i >= s->names->length) return "";
     return (const char*)((SEXP*)s->names->data)[i]->data;
 }
+const char* mock_class(SEXP s) { return s->klass == R_NilValue ? "" : (const char*)((SEXP*)s->klass->data)[0]->data; }
+SEXP mock_rownames(SEXP s) { return s->rownames; }
 /* gc(): run the finalizers of external pointers, free everything */
 void mock_reset(void) {
     for (SEXP s = all_objects; s; s = s->next)

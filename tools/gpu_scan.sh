@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 FC=/tmp/rfsi_bench_forest.npz
 B="python bench.py --no-cpu --no-e2e --steps 4 --warmup 3 --forest-cache $FC"
-$B > gpurun_out/scan_base.json 2> gpurun_out/scan_base.err; echo "base rc=$?"
+$B --qrf > gpurun_out/scan_base.json 2> gpurun_out/scan_base.err; echo "base rc=$?"; python -m pytest tests/test_gpu_forest.py tests/test_gpu_fused.py tests/test_gpu_fuzz.py tests/test_gpu_maps.py -m gpu -x -q > gpurun_out/scan_suite.log 2>&1; echo "suite rc=$?"
 for v in $1; do
   lib=${v%%:*}; J=${v##*:}
   L=rfsi_b200/librfsi_b200.so; [ "$lib" != "-" ] && L=rfsi_b200/librfsi_b200_$lib.so
@@ -19,7 +19,7 @@ import json, glob
 for f in sorted(glob.glob("gpurun_out/scan_*.json")):
     try:
         j = json.loads(open(f).read().strip().splitlines()[-1]); r = j["roofline"]
-        print(f"{f[16:-5]:16s} value {j['value']/1e6:7.1f} M   fused launch {r['avg_launch_ms']:.2f} ms")
+        q = j.get('qrf') or {}; print(f"{f[16:-5]:16s} value {j['value']/1e6:7.1f} M   fused launch {r['avg_launch_ms']:.2f} ms   qrf {q.get('value', 0)/1e6:.1f} M q-kernel {q.get('quantile_kernel_ms_per_step', 0):.2f} ms")
     except Exception as ex:
         print(f, "unreadable:", ex)
 PY
