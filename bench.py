@@ -1,13 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- predicted pixel-days/s of the RFSI hot path (near.obs features + forest).
 
-Workload (BASELINE.json configs[4], the one the metric is quoted on): 10^4 stations,
-10^4 x 10^4 raster, n.obs = 20, 500 trees, F = 43 (3 daily covariates + 20 dist + 20 obs),
-2 % of stations missing per day.  One step = one band of raster rows x D days through
-rfsi_dev_predict_fused (geometry pass + fused near.obs->forest kernel), inputs resident in
-HBM.  `e2e` is the same band through rfsi_predict_fused with pinned HOST buffers (H2D of
-the covariates and D2H of the predictions inside the timed region).  Weak scaling: every
-rank owns its own band of rows; no collective on the compute path.
+Workload (BASELINE.json configs[4], the one the metric is quoted on): 10^4 stations, 10^4 x 10^4 raster,
+n.obs = 20, 500 trees, F = 43 (3 daily covariates + 20 dist + 20 obs), 2 % of stations missing per day.
+One step = ONE FIXED band of `--rows` raster rows (default 1600 rows = 1.6 x 10^7 pixels) x `--days` days for
+the whole job, cut into one band of rows per GPU by rfsi_b200.partition.partition() -- strong scaling: the
+work per step does not grow with N.  Every rank runs rfsi_dev_predict_fused (geometry pass + fused
+near.obs -> forest kernel) on its band with inputs resident in HBM; no collective on the compute path.
+`e2e` is the same band through rfsi_predict_fused with pinned HOST buffers (H2D of the covariates and D2H of
+the predictions inside the timed region).  Beside the headline the line carries: `qrf` (mean + 3 quantiles),
+`configs` (the reference's own configurations through the host API with the CPU port beside them),
+`in_process` (one process driving all GPUs through rfsi_predict_fused_multi), `parity_sample` (the timed
+kernel's output against the oracle) and a `roofline` whose every field is a physical quantity.
 
 python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 """
@@ -15,6 +19,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -44,13 +49,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=200, help="raster rows (of 10^4 cells) per step per GPU")
+    ap.add_argument("--rows", type=int, default=1600, help="raster rows (of 10^4 cells) per step for the WHOLE job")
     ap.add_argument("--days", type=int, default=8, help="days per step")
     ap.add_argument("--trees", type=int, default=N_TREES)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--qrf", action="store_true", help="also time mean + 3 quantiles (IQR maps) on 2 days of the band")
+    ap.add_argument("--no-qrf", action="store_true", help="skip the quantile-forest record (mean + 3 quantiles)")
+    ap.add_argument("--qrf", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the reference's own configurations (C1-C4)")
+    ap.add_argument("--no-inprocess", action="store_true", help="skip the one-process multi-GPU record")
     ap.add_argument("--forest-cache", default=None, help="npz file to keep the grown bench forest between runs (setup only)")
     return ap.parse_args()
 
@@ -145,7 +153,7 @@ def main_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, case, flat, cpu=True),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -157,9 +165,9 @@ def main_reference(args):
 
 def workload_config(args, case, flat, cpu=False):
     return {
-        "workload": "c5 scale-up: 10^4 stations, 10^4x10^4 raster (band of rows per step), n.obs=20, "
-                    f"{args.trees} trees, F=43 (3 daily covariates + 20 dist + 20 obs), 2% stations missing/day",
-        "pixels_per_step_per_gpu": args.rows * case.ncol,
+        "workload": "c5 scale-up: 10^4 stations, 10^4x10^4 raster (one fixed band of rows per step, cut across the GPUs), "
+                    f"n.obs=20, {args.trees} trees, F=43 (3 daily covariates + 20 dist + 20 obs), 2% stations missing/day",
+        "pixels_per_step": args.rows * case.ncol,
         "days_per_step": args.days,
         "forest_nodes": int(flat.node_offsets[-1]),
         "cpu_port": "kd-tree near.obs + threaded ranger-style descent (oracle/cpu_baseline.cpp); R/ranger not installable here",
@@ -219,21 +227,71 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def source_sha():
+    """Identity of the kernels the ncu-derived numbers in profiles/traffic.json belong to."""
+    h = hashlib.sha256()
+    for n in ("sector.cuh", "forest.cuh", "fused.cuh", "common.cuh"):
+        h.update((ROOT / "rfsi_b200" / "csrc" / n).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def warp_sector_model(flat, X, trees):
+    """Algorithmic traffic of the sector image for cache-served walks, counted on real paths: X holds the feature rows
+    of whole warps (32 consecutive rows = one 8 x 4 pixel patch).  For every tree the 32 lanes are walked level by
+    level; a block visit costs its 32-byte sector once per WARP (lanes standing on the same block share it), a leaf
+    its own sector.  Returns distinct sectors per warp and tree, block visits of the deepest lane per warp and tree
+    (the lock-step floor of load requests), and the mean internal nodes per lane and tree."""
+    npix = X.shape[0]
+    W = npix // 32
+    off = flat.node_offsets
+    rows = np.arange(npix)
+
+    def distinct(a):          # (W, 32) ints, -1 = none -> distinct values >= 0 per row
+        s = np.sort(a, axis=1)
+        return ((s[:, 1:] != s[:, :-1]) & (s[:, 1:] >= 0)).sum(1) + (s[:, 0] >= 0)
+
+    sectors = visits = depth_sum = 0
+    for t in range(trees):
+        o, e = int(off[t]), int(off[t + 1])
+        l, r, v, s = flat.left[o:e], flat.right[o:e], flat.split_var[o:e], flat.split_val[o:e]
+        node = np.zeros(npix, dtype=np.int64)
+        d = 0
+        deepest = np.zeros(W, dtype=np.int64)
+        while True:
+            internal = l[node] != 0
+            if d % 3 == 0:                       # block roots sit at depths 0, 3, 6, ...
+                roots = np.where(internal, node, -1).reshape(W, 32)
+                sectors += int(distinct(roots).sum())
+                deepest += (roots >= 0).any(axis=1)
+            if not internal.any():
+                break
+            depth_sum += int(internal.sum())
+            nxt = np.where(X[rows, v[node]] <= s[node], l[node], r[node])
+            node = np.where(internal, nxt, node)
+            d += 1
+        sectors += int(distinct(node.reshape(W, 32)).sum())     # the leaves' own blocks
+        visits += int(deepest.sum()) + W
+    n = W * trees
+    return sectors / n, visits / n, depth_sum / (npix * trees)
+
+
 def main_ours(args):
     import torch
     import rfsi_b200 as rb
     from rfsi_b200 import _lib
     from rfsi_b200._lib import FusedArgs
+    from rfsi_b200.partition import partition
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         log(f"[bench] WORLD_SIZE {world} != --gpus {args.gpus}; using WORLD_SIZE")
-    dist = None
+    dist = host_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")      # host-side waits that keep the GPUs free (in_process record)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load()
@@ -243,6 +301,7 @@ def main_ours(args):
     # ---- inputs ------------------------------------------------------------------
     case = build_case(args.days)
     D, S, n_obs = args.days, case.obs_xy.shape[0], case.n_obs
+    want_qrf = not args.no_qrf
 
     def gpu_near_obs(loc, obs, z, n):
         df = rb.near_obs(loc, np.column_stack([obs, z]), zcol=2, n_obs=n, device=local)
@@ -250,7 +309,7 @@ def main_ours(args):
         return a[:, :n], a[:, n:]
 
     if rank == 0:
-        flat = grow(case, gpu_near_obs, args.trees, quantreg=args.qrf and world == 1, cache=args.forest_cache)
+        flat = grow(case, gpu_near_obs, args.trees, quantreg=want_qrf, cache=args.forest_cache)
         parts = [flat.node_offsets, flat.left, flat.right, flat.split_var, flat.split_val]
     else:
         flat, parts = None, None
@@ -275,51 +334,58 @@ def main_ours(args):
     model.upload(local)
     info = model.info()
 
+    # ---- the step: one fixed band of rows for the whole job, cut by the product's partitioner -------
     ncol = case.ncol
-    P = args.rows * ncol
-    band_rows = case.nrow // world
-    row0 = rank * band_rows
-    nsteps_total = args.warmup + args.steps + 2
-    if args.rows * nsteps_total > band_rows:
-        log("[bench] band shorter than steps x rows; steps wrap inside the band")
+    units = partition(args.rows, ncol, D, world, mode="rows")
+    unit = units[rank]
+    P = unit.npix                                   # this rank's pixels per step
+    total_px = args.rows * ncol
+    row0 = unit.pix_begin // ncol
+    max_start = max(1, case.nrow - args.rows + 1)   # the band moves down the raster from step to step
 
     obs_x = torch.from_numpy(np.ascontiguousarray(case.obs_xy[:, 0])).to(dev)
     obs_y = torch.from_numpy(np.ascontiguousarray(case.obs_xy[:, 1])).to(dev)
     obs_z = torch.from_numpy(np.ascontiguousarray(case.obs_z[:D])).to(dev)
     # daily covariates of the band, generated on the device with synth.smooth_field's formula
     kk, ph = cov_params(case)
-    p = torch.arange(P, device=dev, dtype=torch.float64)
-    px = 0.5 + torch.remainder(p, ncol)
-    py = 0.5 + row0 + torch.div(p, ncol, rounding_mode="floor")
     cov = torch.empty((3, D, P), dtype=torch.float64, device=dev)
-    for c in range(3):
-        for d in range(D):
-            k = torch.from_numpy(kk[c, d]).to(dev); f = torch.from_numpy(ph[c, d]).to(dev)
-            cov[c, d] = np.sqrt(2.0 / 16) * torch.cos(px[:, None] * k[:, 0] + py[:, None] * k[:, 1] + f).sum(dim=1)
+    blk = 1 << 21
+    for a0 in range(0, P, blk):
+        p = torch.arange(a0, min(P, a0 + blk), device=dev, dtype=torch.float64)
+        px = 0.5 + torch.remainder(p, ncol)
+        py = 0.5 + row0 + torch.div(p, ncol, rounding_mode="floor")
+        for c in range(3):
+            for d in range(D):
+                k = torch.from_numpy(kk[c, d]).to(dev); f = torch.from_numpy(ph[c, d]).to(dev)
+                cov[c, d, a0:a0 + p.numel()] = np.sqrt(2.0 / 16) * torch.cos(px[:, None] * k[:, 0] + py[:, None] * k[:, 1] + f).sum(dim=1)
     del p, px, py
     out_mean = torch.empty((D, P), dtype=torch.float64, device=dev)
     fmap = rb.feature_map(case.feature_names, case.cov_names, n_obs)
-    probs = None
 
-    def make_args(step, device_side=True, host=None):
+    def pix_begin_of(step):
+        return ((step * args.rows) % max_start + row0) * ncol
+
+    def make_args(step, device_side=True, host=None, npix=None, ndays=None):
         a = FusedArgs()
         a.struct_size = C.sizeof(FusedArgs)
-        a.npix = P
+        a.npix = P if npix is None else npix
         a.grid_x0, a.grid_y0, a.grid_dx, a.grid_dy = case.grid[:4]
         a.grid_ncol = ncol
-        a.pix_begin = (row0 + (step * args.rows) % max(1, band_rows - args.rows + 1)) * ncol
-        a.nobs, a.ndays, a.n_obs, a.rm_dupl = S, D, n_obs, 1
+        a.pix_begin = pix_begin_of(step)
+        a.nobs, a.ndays, a.n_obs, a.rm_dupl = S, (D if ndays is None else ndays), n_obs, 1
         a.ncov = 3
         a.feat_map = fmap.ctypes.data_as(C.POINTER(C.c_int32))
         if device_side:
             a.obs_x, a.obs_y, a.obs_z = obs_x.data_ptr(), obs_y.data_ptr(), obs_z.data_ptr()
             ptrs = (C.c_void_p * 3)(*[cov[c].data_ptr() for c in range(3)])
             a.out_mean = out_mean.data_ptr()
+            stride = P
         else:
             a.obs_x, a.obs_y, a.obs_z = host["ox"].ctypes.data, host["oy"].ctypes.data, host["oz"].ctypes.data
             ptrs = (C.c_void_p * 3)(*[host["cov"][c].data_ptr() for c in range(3)])
             a.out_mean = host["out"].data_ptr()
-        strides = (C.c_int64 * 3)(P, P, P)
+            stride = host["cov"][0].shape[1]
+        strides = (C.c_int64 * 3)(stride, stride, stride)
         a.cov = C.cast(ptrs, C.POINTER(C.c_void_p))
         a.cov_day_stride = C.cast(strides, C.POINTER(C.c_int64))
         a._keep = (ptrs, strides)
@@ -349,7 +415,6 @@ def main_ours(args):
     visits_per_pd = float(cnt[0]) / max(1, int(cnt[1]))
     fallback_pd = int(cnt[2])
     assert int(cnt[1]) == P * D, f"counted {cnt[1]} pixel-days, expected {P * D}"
-    assert bool(torch.isfinite(out_mean).all()), "non-finite prediction"
 
     for i in range(args.warmup):
         step_dev(1 + i)
@@ -369,6 +434,7 @@ def main_ours(args):
     launches = rb.launch_count() - launches0
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
+    last_step = args.warmup + args.steps             # out_mean holds this step's band
     prof = {}
     for cls, name in ((0, "knn_geometry"), (2, "fused"), (3, "fallback")):
         tms, n = C.c_double(0), C.c_uint64(0)
@@ -378,50 +444,106 @@ def main_ours(args):
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
-    value = world * P * D * args.steps / (ms_max * 1e-3)
+    value = total_px * D * args.steps / (ms_max * 1e-3)
 
-    # ---- roofline of the dominant kernel (fused near.obs->forest) ---------------------
+    # ---- parity of the timed kernel's output: a sample of the last timed band against the oracle ----
+    parity = None
+    host_X = None
+    sel = sel_t = cv = None
+    if rank == 0 and not args.no_cpu:
+        import oracle
+        nwarp = 16                                   # whole 8 x 4 patches, so the sample also feeds the traffic model
+        sel = []
+        for wv in range(nwarp):
+            r0 = (wv * 97) % max(1, min(P // ncol, 200) - 4); c0 = (wv * 613) % (ncol - 8)   # within the first 2 x 10^6 pixels
+            sel += [(r0 + r) * ncol + c0 + c for r in range(4) for c in range(8)]
+        sel = np.array(sel)
+        gpix = pix_begin_of(last_step) + sel
+        loc = np.stack([case.grid[0] + (gpix % ncol) * case.grid[2], case.grid[1] + (gpix // ncol) * case.grid[3]], axis=1)
+        sel_t = torch.from_numpy(sel).to(dev)
+        cv = {n: cov[c][:2].index_select(1, sel_t).cpu().numpy() for c, n in enumerate(case.cov_names)}
+        ref = oracle.predict_fused(flat.as_dict(), case.feature_names, loc_xy=loc, obs_xy=case.obs_xy, obs_z=case.obs_z[:2],
+                                   n_obs=n_obs, covariates=cv, kdtree=True, threads=oracle.hardware_threads())
+        got = out_mean[:2].index_select(1, sel_t).cpu().numpy()
+        rel = np.abs(got - ref["mean"]) / np.maximum(1.0, np.abs(ref["mean"]))
+        parity = {"n": int(got.size), "what": "512 pixels x 2 days of the last timed band, all trees, vs oracle.predict_fused",
+                  "max_rel_err": float(np.nanmax(rel)), "bit_equal": bool(np.array_equal(got, ref["mean"])),
+                  "tolerance": 1e-12}
+        assert parity["max_rel_err"] <= 1e-12, f"timed kernel disagrees with the oracle: {parity}"
+        # feature rows of those patches on day 0 (host side), for the traffic model below
+        ok = ~np.isnan(case.obs_z[0])
+        dd, oo, _, _ = oracle.near_obs(loc, case.obs_xy[ok], case.obs_z[0][ok], n_obs, kdtree=True, nthreads=oracle.hardware_threads())
+        cols = []
+        for n in case.feature_names:
+            cols.append(dd[:, int(n[4:]) - 1] if n.startswith("dist") else oo[:, int(n[3:]) - 1] if n.startswith("obs") else cv[n][0])
+        host_X = np.stack(cols, axis=1)
+    else:
+        assert bool(torch.isfinite(out_mean).all()), "non-finite prediction"
+
+    # ---- roofline of the dominant kernel (fused near.obs -> forest) ------------------------------------
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
         peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    f_ext = 3
-    b_rf = 8 * f_ext + 16 * (visits_per_pd + args.trees) + 8          # SURVEY.md 8(d), fused form
-    # DRAM traffic of the same kernel from the committed ncu --set full capture (per pixel-day)
-    traffic = None
-    tpath = ROOT / "profiles" / "traffic.json"
-    if tpath.exists():
-        try:
-            traffic = float(json.loads(tpath.read_text())["fused_kernel"]["dram_bytes_per_pixel_day"])
-        except Exception:
-            traffic = None
     fused_ms, fused_n = prof["fused"]
     units_per_launch = P * D * args.steps / max(1, fused_n)
-    achieved = b_rf * units_per_launch / (fused_ms / max(1, fused_n) * 1e-3) / 1e9 if fused_ms > 0 else None
+    launch_s = fused_ms / max(1, fused_n) * 1e-3
     image = {0: "wide 16-byte fp64 nodes", 1: "compact 8-byte rank nodes", 2: "blocked 4-byte rank nodes, 4 levels per 128-byte line",
              3: "sector image: 4-byte rank nodes, 3 levels + implicit children per 32-byte sector, leaf payload in the leaf's block"}
     image_code = int(info.get("image", 3))
+    f_ext = 3
+    b_survey = 8 * f_ext + 16 * (visits_per_pd + args.trees) + 8          # a private 16-B gather per visit
+    model_rec = None
+    b_alg = None
+    if host_X is not None and image_code == 3:
+        sect, vis, dmean = warp_sector_model(flat, host_X, args.trees)
+        b_alg = 32.0 * sect * args.trees / 32.0 + 8 * f_ext + 8
+        model_rec = {"sectors_per_warp_tree": sect, "block_visits_per_warp_tree_lockstep_floor": vis,
+                     "mean_internal_nodes_per_tree_in_sample": dmean,
+                     "sample": f"{host_X.shape[0] // 32} warps (8x4 patches) x {args.trees} trees"}
+    ncu = {}
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        try:
+            ncu = json.loads(tpath.read_text()).get("fused_kernel", {})
+        except Exception:
+            ncu = {}
+    sha = source_sha()
+    stale = bool(ncu) and ncu.get("source_sha") != sha
+    traffic = ncu.get("dram_bytes_per_pixel_day")
+    achieved = (b_alg * units_per_launch / launch_s / 1e9) if (b_alg and launch_s > 0) else None
     roofline = {
-        "bound": "hbm", "kernel": f"fused_kernel<256,J> on the {image[image_code]} "
-                                  "(per-day candidate compaction + forest traversal)",
+        "bound": "hbm",
+        "kernel": f"fused_kernel<256,J> on the {image[image_code]} (per-day candidate compaction + forest traversal)",
+        "model": "warp-unique sectors: every 32-byte forest sector a warp of 32 adjacent pixels touches counts once per warp and tree "
+                 "(what has to reach the SM when nothing is reused between trees), + 8 B per covariate and 8 B out per pixel-day; "
+                 "counted on real paths of a sample of the timed band (bench.py: warp_sector_model)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+        "algorithmic_bytes_per_pixel_day": b_alg, "model_detail": model_rec,
         "traffic": (traffic * units_per_launch) if traffic else None,
-        "traffic_source": "profiles/traffic.json (ncu --set full dram__bytes_read+write, bench shape), bytes per launch",
+        "dram_frac": (traffic * units_per_launch / launch_s / 1e9 / peak) if (traffic and launch_s > 0) else None,
+        "issue_frac": ncu.get("issue_active_frac"), "l1_hit": ncu.get("l1_sector_hit_frac"),
+        "l1_data_pipe_frac": ncu.get("l1tex_data_pipe_frac"),
+        "loads_per_warp_tree": {"measured": ncu.get("global_load_requests_per_warp_tree"),
+                                "path_minimum": (3.0 * (model_rec["block_visits_per_warp_tree_lockstep_floor"] - 1) + 2.0) if model_rec else None},
+        "ncu_source": ncu.get("captured"), "ncu_source_sha": ncu.get("source_sha"), "kernel_source_sha": sha, "ncu_stale": stale,
         "peak_source": peak_src,
-        "algorithmic_bytes_per_pixel_day": b_rf, "mean_internal_nodes_per_tree": visits_per_pd / args.trees,
+        "survey_model": {"bytes_per_pixel_day": b_survey, "frac": (b_survey * units_per_launch / launch_s / 1e9 / peak) if launch_s > 0 else None,
+                         "note": "SURVEY.md 8(d) charges every node visit of every pixel a private 16-byte gather; adjacent pixels share "
+                                 "4-byte nodes, so this is not a bound for this design -- kept only for continuity with round 1"},
+        "mean_internal_nodes_per_tree": visits_per_pd / args.trees,
         "pixel_days_per_launch": units_per_launch, "avg_launch_ms": fused_ms / max(1, fused_n),
         "kernel_share_of_step": fused_ms / ms if ms > 0 else None,
         "geometry_pass_ms_per_step": prof["knn_geometry"][0] / max(1, args.steps),
         "forest_bytes": info["device_bytes"],
-        "note": "achieved counts every node visit as a 16-B gather (SURVEY.md 8d: algorithmic bytes); a warp's 32 "
-                "adjacent pixels share tree paths and the rank-quantised images move 4 or 8 B per node, so L1/L2 serve most "
-                "visits: frac > 1 of the HBM roof, DRAM traffic ~14x below the algorithmic figure; the kernel is "
-                "L1-data-path bound (profiles/r01_e_*)",
+        "note": "the walk is bound by the L1 data stage (one wavefront per distinct 128-byte line a warp-level load touches, "
+                "plus the shared-memory rank loads), not by HBM: dram_frac and frac are both far below 1 (profiles/r02_*)",
     }
 
     # ---- e2e through the host-buffer C ABI -------------------------------------------
     e2e = None
+    host = None
     if not args.no_e2e:
         host = {
             "ox": np.ascontiguousarray(case.obs_xy[:, 0]), "oy": np.ascontiguousarray(case.obs_xy[:, 1]),
@@ -448,24 +570,61 @@ def main_ours(args):
         t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * P * D * args.steps / float(t_e.item()), "unit": UNIT,
-               "h2d_bytes_per_step": 3 * D * P * 8 + D * S * 8 + 2 * S * 8, "d2h_bytes_per_step": D * P * 8,
+        e2e = {"value": total_px * D * args.steps / float(t_e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": 3 * D * total_px * 8 + world * (D * S * 8 + 2 * S * 8), "d2h_bytes_per_step": D * total_px * 8,
                "ms_per_step": 1e3 * float(t_e.item()) / args.steps,
-               "api": "rfsi_predict_fused (pinned host buffers in, pinned host buffer out)"}
+               "api": "rfsi_predict_fused (pinned host buffers in, pinned host buffer out), one call per rank and step"}
 
-    # ---- quantile forest (IQR maps), reported separately -------------------
+    # ---- one process, all GPUs: rfsi_predict_fused_multi on the same fixed grid --------------------------
+    in_process = None
+    if not args.no_inprocess and not args.no_e2e and world > 1:
+        # rank 0 drives devices 0..N-1 itself; the other ranks wait on the HOST (gloo), their GPUs idle
+        if rank == 0:
+            reps = world
+            big = {"ox": host["ox"], "oy": host["oy"], "oz": host["oz"],
+                   "cov": [torch.cat([host["cov"][c]] * reps, dim=1).pin_memory() for c in range(3)],
+                   "out": torch.empty((D, P * reps), dtype=torch.float64).pin_memory()}
+            devs = (C.c_int * world)(*range(world))
+
+            def step_multi(i, ndev):
+                a = make_args(i, device_side=False, host=big, npix=P * reps)
+                _lib.check(lib.rfsi_predict_fused_multi(model.handle, C.byref(a), devs, ndev))
+
+            step_multi(0, world); step_multi(1, world)          # warm-up: images and staging on every device
+            step_multi(0, world)
+            first = big["out"].clone()
+            nst = max(2, min(args.steps, 5))
+            t0 = time.perf_counter()
+            for i in range(nst):
+                step_multi(2 + i, world)
+            dtm = time.perf_counter() - t0
+            step_multi(0, 1)                                     # the same call on ONE device: bit-equal?
+            same = bool(torch.equal(big["out"], first))
+            t0 = time.perf_counter()
+            for i in range(2):
+                step_multi(2 + i, 1)
+            dt1 = (time.perf_counter() - t0) / 2
+            in_process = {"api": "rfsi_predict_fused_multi: one process, one host thread and one band of rows per GPU, pinned host buffers",
+                          "devices": world, "pixels_per_call": P * reps, "days": D,
+                          "value": P * reps * D * nst / dtm, "unit": UNIT, "ms_per_call": 1e3 * dtm / nst,
+                          "one_device_ms_per_call": 1e3 * dt1, "speedup_vs_one_device": dt1 / (dtm / nst),
+                          "bit_equal_to_one_device": same}
+            del big, first
+        dist.barrier(group=host_group)
+
+    # ---- quantile forest (IQR maps): mean + quantiles (.25,.5,.75) + the Int16 IQR product ----------------
     qrf = None
-    if args.qrf and world == 1:
-        Pq, Dq = P, min(D, 2)   # the whole band: 4 bytes of leaf-id scratch per (pixel-day, tree)
+    if want_qrf and world == 1:
+        Pq, Dq = min(P, 2_000_000), min(D, 2)   # 4 bytes of key scratch per (pixel-day, tree): 2 x 10^6 pixels x 2 days = 8 GB
         out_q = torch.empty((3, Dq, Pq), dtype=torch.float64, device=dev)
         out_m = torch.empty((Dq, Pq), dtype=torch.float64, device=dev)
+        out_i = torch.empty((Dq, Pq), dtype=torch.int16, device=dev)
         probs_c = (C.c_double * 3)(0.25, 0.5, 0.75)
 
         def qargs(step):
-            a = make_args(step)
-            a.npix, a.ndays = Pq, Dq
+            a = make_args(step, npix=Pq, ndays=Dq)
             a.probs = C.cast(probs_c, C.POINTER(C.c_double)); a.nprobs = 3
-            a.out_mean, a.out_q = out_m.data_ptr(), out_q.data_ptr()
+            a.out_mean, a.out_q, a.out_iqr_i16 = out_m.data_ptr(), out_q.data_ptr(), out_i.data_ptr()
             return a
         aq = qargs(0)
         wsq = torch.empty(lib.rfsi_dev_fused_workspace_bytes(model.handle, C.byref(aq)), dtype=torch.uint8, device=dev)
@@ -485,10 +644,30 @@ def main_ours(args):
         lib.rfsi_profile_read(4, C.byref(tq), C.byref(nq))
         tf, nf = C.c_double(0), C.c_uint64(0)
         lib.rfsi_profile_read(2, C.byref(tf), C.byref(nf))
-        qrf = {"value": Pq * Dq * args.steps / (qms * 1e-3), "unit": UNIT, "what": "mean + quantiles (.25,.5,.75)",
+        qrf = {"value": Pq * Dq * args.steps / (qms * 1e-3), "unit": UNIT,
+               "what": "mean + quantiles (.25,.5,.75) + Int16 IQR product (temp_croatia/2_predictions.R:174-178), device-resident",
                "pixels": Pq, "days": Dq, "quantile_kernel_ms_per_step": tq.value / args.steps,
                "fused_kernel_ms_per_step": tf.value / args.steps}
-        del out_q, out_m, wsq
+        if host_X is not None and int(sel.max()) < Pq:
+            import oracle
+            # parity of the quantile path on the same patches as above (the last qrf step's band)
+            qs = 2 + args.steps - 1
+            gp = pix_begin_of(qs) + sel
+            loc_q = np.stack([case.grid[0] + (gp % ncol) * case.grid[2], case.grid[1] + (gp // ncol) * case.grid[3]], axis=1)
+            refq = oracle.predict_fused(flat.as_dict(), case.feature_names, loc_xy=loc_q, obs_xy=case.obs_xy, obs_z=case.obs_z[:Dq],
+                                        n_obs=n_obs, covariates={n: v[:Dq] for n, v in cv.items()}, quantiles=[0.25, 0.5, 0.75],
+                                        kdtree=True, threads=oracle.hardware_threads())
+            gq = out_q.index_select(2, sel_t).cpu().numpy()
+            qrf["parity_sample"] = {"n": int(gq.size), "bit_equal": bool(np.array_equal(gq, refq["quantiles"]))}
+            assert qrf["parity_sample"]["bit_equal"], "quantile path disagrees with the oracle"
+        del out_q, out_m, out_i, wsq
+
+    # ---- the reference's own configurations through the host API, CPU port beside them ----------------------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs and not args.no_cpu:
+        del cov, ws
+        torch.cuda.empty_cache()
+        configs = reference_configs(local)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------
     cpu = None
@@ -501,23 +680,105 @@ def main_ours(args):
     if rank == 0:
         cfg = workload_config(args, case, flat)
         cfg.update({"cache": "inputs larger than L2 every step (forest %.0f MB, covariates %.0f MB, candidate lists "
-                             "%.0f MB; a different band of rows each step)" %
+                             "%.0f MB per GPU; the band moves down the raster from step to step)" %
                              (info["device_bytes"] / 1e6, 3 * D * P * 8 / 1e6, 32 * 12 * P / 1e6),
-                    "parallelism": f"{world} x row bands, forest + stations replicated, no collective",
+                    "parallelism": f"{world} x bands of rows of the fixed grid (rfsi_b200.partition.partition), forest + stations "
+                                   "replicated, no collective",
+                    "pixels_per_step_per_gpu": P,
                     "fallback_pixel_days_per_step": fallback_pd})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "parity_sample": parity,
         }
         if qrf is not None:
             line["qrf"] = qrf
+        if configs is not None:
+            line["configs"] = configs
+        if in_process is not None:
+            line["in_process"] = in_process
         emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def reference_configs(device):
+    """The reference's own configurations (BASELINE.json configs[0..3]) through the R-call-shaped host API -- host
+    buffers in, freshly allocated host buffers out, exactly what simulation.R:190-215 times as DT (near.obs) and
+    PT (predict) -- with the CPU port (oracle/cpu_baseline.cpp, all host threads) timed on the same inputs."""
+    import oracle
+    import rfsi_b200 as rb
+    from rfsi_b200 import grow as grower, synth
+    threads = oracle.hardware_threads()
+
+    def best(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    def once(fn):
+        t0 = time.perf_counter(); fn(); return time.perf_counter() - t0
+
+    out = {"cpu_threads": threads, "timing": "GPU: best of 3 after one warm-up call; CPU port: one call",
+           "c1_simulation_R": [], "note": "DT = near.obs(250 000 grid cells, stations, n.obs = 25), PT = predict(250-tree forest, 250 000 x 50 "
+                                          "data frame): simulation/simulation.R:190-215; published reference timings in BASELINE.md"}
+    rng = np.random.default_rng(42)
+    loc = synth.lattice(500, 500)
+    for S in (100, 200, 500, 1000, 2000, 5000):
+        obs = loc[rng.choice(250000, S, replace=False)]
+        z = 20 + np.sqrt(10) * synth.smooth_field(obs, 1) + rng.normal(0, np.sqrt(2.5), S)
+        odf = np.column_stack([obs, z])
+        tr = rb.near_obs(obs, odf, zcol=2, n_obs=25, device=device)
+        flat = grower.grow_forest(tr.to_numpy(), z, list(tr.columns), num_trees=250)
+        model = rb.RangerForest(flat)
+        X = rb.near_obs(loc, odf, zcol=2, n_obs=25, device=device).to_numpy()
+        dt = best(lambda: rb.near_obs(loc, odf, zcol=2, n_obs=25, device=device))
+        pt = best(lambda: rb.predict(model, X, device=device))
+        cdt = once(lambda: oracle.near_obs(loc, obs, z, 25, kdtree=True, nthreads=threads))
+        cpt = once(lambda: oracle.forest_predict(flat.as_dict(), X, threads=threads))
+        out["c1_simulation_R"].append({"stations": S, "DT_ms": 1e3 * dt, "PT_ms": 1e3 * pt, "pixels_per_s": 250000 / (dt + pt),
+                                       "cpu_DT_ms": 1e3 * cdt, "cpu_PT_ms": 1e3 * cpt, "cpu_pixels_per_s": 250000 / (cdt + cpt)})
+        model.close()
+    case = synth.make_case("c2")
+    odf = np.column_stack([case.obs_xy, case.obs_z[0]])
+    l2 = case.locations()
+    out["c2_sim_500_R"] = {"what": "near.obs(250 000 cells, 500 stations, n.obs = 40) once (sim_500.R:131-139)",
+                           "DT_ms": 1e3 * best(lambda: rb.near_obs(l2, odf, zcol=2, n_obs=40, device=device)),
+                           "cpu_DT_ms": 1e3 * once(lambda: oracle.near_obs(l2, case.obs_xy, case.obs_z[0], 40, kdtree=True, nthreads=threads))}
+
+    def gpu_no(l, o, z, n):
+        a = rb.near_obs(l, np.column_stack([o, z]), zcol=2, n_obs=n, device=device).to_numpy()
+        return a[:, :n], a[:, n:]
+
+    for name, key, train_days, days in (("c3", "c3_temp_croatia", 366, 4), ("c4", "c4_prcp_catalonia", 1095, 4)):
+        case = synth.make_case(name, ndays=train_days)
+        Xt, yt = synth.training_table(case, gpu_no)
+        flat = grower.grow_forest(Xt, yt, case.feature_names, num_trees=250, min_node_size=6, quantreg=True)
+        model = rb.RangerForest(flat)
+        locs = case.locations()
+        cv = case.covariates(locs, ndays=days)
+        kw = dict(obs_xy=case.obs_xy, obs_z=case.obs_z[:days], n_obs=case.n_obs, grid=case.grid, npix=case.npix, covariates=cv,
+                  device=device)
+        tm = best(lambda: rb.predict_fused(model, **kw))
+        tq = best(lambda: rb.predict_fused(model, quantiles=[.25, .5, .75], centi_int16=True, **kw))
+        okw = dict(loc_xy=locs, obs_xy=case.obs_xy, obs_z=case.obs_z[:days], n_obs=case.n_obs, covariates=cv, kdtree=True, threads=threads)
+        cm = once(lambda: oracle.predict_fused(flat.as_dict(), case.feature_names, **okw))
+        cq = once(lambda: oracle.predict_fused(flat.as_dict(), case.feature_names, quantiles=[.25, .5, .75], **okw))
+        pd_ = case.npix * days
+        out[key] = {"what": f"map loop: {case.ncol}x{case.nrow} cells x {days} days, {case.obs_xy.shape[0]} stations, n.obs={case.n_obs}, "
+                            f"F={len(case.feature_names)}, 250 trees ({int(flat.node_offsets[-1])} nodes); mean, then mean + quantiles "
+                            "(.25,.5,.75) + Int16 products, host buffers in and out (rfsi_predict_fused)",
+                    "mean_ms": 1e3 * tm, "mean_quantiles_ms": 1e3 * tq, "pixel_days_per_s": pd_ / tm, "pixel_days_per_s_quantiles": pd_ / tq,
+                    "cpu_mean_ms": 1e3 * cm, "cpu_mean_quantiles_ms": 1e3 * cq, "cpu_pixel_days_per_s": pd_ / cm,
+                    "cpu_pixel_days_per_s_quantiles": pd_ / cq}
+        model.close()
+    return out
 
 
 def emit(line: dict):
