@@ -105,6 +105,16 @@ __host__ __device__ constexpr size_t fused_feature_bytes(int F) {
     return Q ? (((size_t)F * P * sizeof(uint32_t) + 15) & ~(size_t)15) : (size_t)(F + 1) * P * sizeof(double);
 }
 
+// shared memory of a CTA: feature tile | neighbour lists of the fallback scan | reorder window of the sector walk
+template <int P, bool Q>
+__host__ __device__ constexpr size_t fused_rob_offset(int F, int k, bool fallback) {
+    return fused_feature_bytes<P, Q>(F) + (fallback ? (size_t)k * P * (sizeof(double) + sizeof(int32_t)) : 0);
+}
+template <int P, bool Q>
+__host__ __device__ constexpr size_t fused_smem_bytes(int F, int k, bool fallback) {
+    return fused_rob_offset<P, Q>(F, k, fallback) + (Q ? (size_t)kSRob * P * sizeof(uint32_t) : 0);
+}
+
 // Resident CTAs per SM the register budget is cut for (rank images).  Measured on the bench forest (profiles/r02_b):
 // 3 x 256 threads at 80 registers 129.6 M pixel-days/s, 4 x 256 at 64 registers 127.5 M (register moves and the
 // re-materialised shared-memory base go away, 92 KB instead of 60 KB of L1), 2 x 256 at 96 registers 106.9 M; more
@@ -260,7 +270,9 @@ fused_kernel(const __grid_constant__ FusedParams a)
         double sum = a.t_begin > 0 ? a.acc[row] : 0.0;
         if (Q && a.q.sect)
             sum = traverse_sect<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
-                                             reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
+                                             reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x,
+                                             reinterpret_cast<uint32_t*>(smem_raw + fused_rob_offset<P, Q>(a.F, a.n_obs + 1, FALLBACK)) + threadIdx.x,
+                                             o, row, nvisit);
         else if (Q && a.q.blocks)
             sum = traverse_b<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
                                           reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
@@ -288,9 +300,5 @@ fused_kernel(const __grid_constant__ FusedParams a)
     }
 }
 
-template <int P, bool Q>
-__host__ __device__ constexpr size_t fused_smem_bytes(int F, int k, bool fallback) {
-    return fused_feature_bytes<P, Q>(F) + (fallback ? (size_t)k * P * (sizeof(double) + sizeof(int32_t)) : 0);
-}
 
 }  // namespace rfsi
