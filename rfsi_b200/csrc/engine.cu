@@ -303,7 +303,7 @@ struct rfsi_forest {
         bool blocked = false;
         bool sector = false;
         bool direct_keys = false;          // sector image whose leaf blocks carry the quantile keys (no leaf table on the device)
-        QForest q{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 32u, 0u, 1};
+        QForest q{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 32u, 0u};
     };
     mutable std::mutex mu;
     mutable std::map<int, Image> images;
@@ -1053,7 +1053,6 @@ int launch_forest_xq_pj(const rfsi_forest* f, const QForest& q_in, const double*
     const int T = f->ntrees, F = f->nfeat;
     QForest q = q_in;
     q.sect_tile_stride = (uint32_t)(P * sizeof(uint32_t));
-    q.sect_refill = env_int("RFSI_B200_REFILL", 1);
     const size_t smem = forest_q_smem_bytes<P>(F);
     const unsigned grid = (unsigned)((npix + P - 1) / P);
     const std::vector<int> cb = tree_chunks(f);
@@ -1945,7 +1944,6 @@ template <int P, int J, bool FALLBACK, bool Q>
 int launch_fused_pj(const FusedParams& fp_in, unsigned grid, int k, bool count, cudaStream_t st) {
     FusedParams fp = fp_in;
     fp.q.sect_tile_stride = (uint32_t)(P * sizeof(uint32_t));
-    fp.q.sect_refill = FALLBACK ? 0 : env_int("RFSI_B200_REFILL", 1);
     const size_t smem = fused_smem_bytes<P, Q>(fp.F, k, FALLBACK);
     ProfScope ps(FALLBACK ? PROF_FALLBACK : PROF_FUSED, st);
     const int carve = env_int("RFSI_B200_CARVEOUT", -1);   // experiment knob: shared-memory carveout in percent

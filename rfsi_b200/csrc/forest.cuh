@@ -37,8 +37,6 @@ struct QForest {
     const uint32_t* sroot;    // [T] root block of each tree
     uint32_t sect_block_bytes;  // 32, and the byte stride between features of the rank tile (4 * pixels per CTA):
     uint32_t sect_tile_stride;  // run-time values on purpose, see SectorView
-    int sect_refill;            // sector walk: 0 = lock-step groups of J trees, 1 = slot refill when only the mean is wanted,
-                                // 2 = slot refill always (leaf ids / terminal nodes are then written tree by tree)
 };
 
 // number of thresholds of feature f strictly below x (x is never NaN here).  The bucket
@@ -255,20 +253,12 @@ __device__ __forceinline__ double traverse_b(const QForest& q, int t_begin, int 
 }
 
 // Sector-format walk (sector.cuh): the leaf's value, number and quantile key sit in the leaf's own block.
-// rob: this thread's column of the reorder window in shared memory (kSRob entries, P apart), for the refill form.
 template <int P, int J, bool COUNT>
 __device__ __forceinline__ double traverse_sect(const QForest& q, int t_begin, int t_end, int T, double sum,
-                                                const uint32_t* __restrict__ rs, uint32_t* rob, const ForestOut& o, long long row,
+                                                const uint32_t* __restrict__ rs, const ForestOut& o, long long row,
                                                 unsigned& nvisit)
 {
     const SectorView v{q.sect, q.sroot, q.sect_block_bytes, q.sect_tile_stride};
-    if (q.sect_refill >= 2 || (q.sect_refill == 1 && !o.leaf_ids && !o.terminal)) {
-        auto sink_r = [&](int t, uint32_t lb) {
-            if (o.terminal) o.terminal[(long long)t * o.ld_term + row] = o.leaf_rid[__ldg(q.sect + (size_t)lb * 8u + kSWordLeafNo)];
-            if (o.leaf_ids) o.leaf_ids[row * o.ld_ids + t] = __ldg(q.sect + (size_t)lb * 8u + o.ids_word);
-        };
-        return traverse_r<P, J, COUNT>(v, t_begin, t_end, sum, rs, rob, sink_r, nvisit);
-    }
     auto sink = [&](int t0, int remaining, const uint32_t (&lb)[J]) {
         if (o.terminal) {
 #pragma unroll
@@ -298,7 +288,7 @@ __device__ __forceinline__ void forest_na_row(const ForestOut& o, long long p, i
 
 template <int P>
 __host__ __device__ constexpr size_t forest_q_smem_bytes(int F) {
-    return (size_t)F * P * sizeof(uint32_t) + (size_t)kSRob * P * sizeof(uint32_t);   // rank tile + reorder window (sector walk)
+    return (size_t)F * P * sizeof(uint32_t);
 }
 
 template <int P, int J, bool COUNT>
@@ -325,7 +315,7 @@ forest_xq_kernel(QForest q, int t_begin, int t_end, int T, int F, const double* 
             forest_na_row(o, p, t_begin, t_end, na_flag);
         } else {
             double sum = (t_begin > 0 && o.mean) ? o.mean[p] : 0.0;
-            if (q.sect) sum = traverse_sect<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, rs + (size_t)F * P, o, p, nvisit);
+            if (q.sect) sum = traverse_sect<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
             else if (q.blocks) sum = traverse_b<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
             else sum = traverse_q<P, J, COUNT>(q, t_begin, t_end, T, sum, rs, o, p, nvisit);
             if (o.mean) o.mean[p] = (t_end == T) ? sum / (double)T : sum;

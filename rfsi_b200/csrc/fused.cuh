@@ -105,14 +105,10 @@ __host__ __device__ constexpr size_t fused_feature_bytes(int F) {
     return Q ? (((size_t)F * P * sizeof(uint32_t) + 15) & ~(size_t)15) : (size_t)(F + 1) * P * sizeof(double);
 }
 
-// shared memory of a CTA: feature tile | neighbour lists of the fallback scan | reorder window of the sector walk
-template <int P, bool Q>
-__host__ __device__ constexpr size_t fused_rob_offset(int F, int k, bool fallback) {
-    return fused_feature_bytes<P, Q>(F) + (fallback ? (size_t)k * P * (sizeof(double) + sizeof(int32_t)) : 0);
-}
+// shared memory of a CTA: feature tile | neighbour lists of the fallback scan
 template <int P, bool Q>
 __host__ __device__ constexpr size_t fused_smem_bytes(int F, int k, bool fallback) {
-    return fused_rob_offset<P, Q>(F, k, fallback) + (Q ? (size_t)kSRob * P * sizeof(uint32_t) : 0);
+    return fused_feature_bytes<P, Q>(F) + (fallback ? (size_t)k * P * (sizeof(double) + sizeof(int32_t)) : 0);
 }
 
 // Resident CTAs per SM the register budget is cut for (rank images).  Measured on the bench forest (profiles/r02_b):
@@ -270,9 +266,7 @@ fused_kernel(const __grid_constant__ FusedParams a)
         double sum = a.t_begin > 0 ? a.acc[row] : 0.0;
         if (Q && a.q.sect)
             sum = traverse_sect<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
-                                             reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x,
-                                             reinterpret_cast<uint32_t*>(smem_raw + fused_rob_offset<P, Q>(a.F, a.n_obs + 1, FALLBACK)) + threadIdx.x,
-                                             o, row, nvisit);
+                                             reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);
         else if (Q && a.q.blocks)
             sum = traverse_b<P, J, COUNT>(a.q, a.t_begin, a.t_end, a.T, sum,
                                           reinterpret_cast<const uint32_t*>(smem_raw) + threadIdx.x, o, row, nvisit);

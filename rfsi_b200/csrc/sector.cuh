@@ -226,113 +226,6 @@ RFSI_SECT_DEV double traverse_s(const SectorView& q, int t_begin, int t_end, dou
 }
 
 
-// ---- the same walk with slot refill --------------------------------------------------------------------
-// traverse_s starts J trees together and waits for the deepest of them (and of the warp's 32 lanes): on the bench
-// forest a group costs 10.0 block visits where the trees of a warp need 8.2 on average (profiles/r02_c_refill_model.txt).
-// Here a slot takes the NEXT tree as soon as its own is finished in every lane of the warp.  Leaf values must still be
-// added in tree order (the mean is bit-equal to ranger's sequential sum), so a finished tree parks its leaf block in a
-// reorder window of kSRob entries per thread in shared memory (rob[(t mod kSRob) * P], this thread's column) and the
-// sum takes them in order; a tree may only start while it is less than kSRob trees ahead of the oldest unfinished one.
-// All decisions are warp-uniform (votes), so the branches below do not diverge; a lane whose chain is done idles on
-// block 0 exactly as in traverse_s.  sink(tree, leaf_block) is called once per tree, in retirement order.
-constexpr int kSRob = 16;
-
-#if defined(RFSI_SECTOR_HOST_CHECK)
-inline bool sector_warp_all(bool x) { return x; }
-inline uint32_t sector_warp_and(uint32_t x) { return x; }
-#else
-RFSI_SECT_DEV bool sector_warp_all(bool x) { return __all_sync(0xffffffffu, x) != 0; }
-RFSI_SECT_DEV uint32_t sector_warp_and(uint32_t x) { return __reduce_and_sync(0xffffffffu, x); }
-#endif
-
-template <int P, int J, bool COUNT, class Sink>
-RFSI_SECT_DEV double traverse_r(const SectorView& q, int t_begin, int t_end, double sum, const uint32_t* rs, uint32_t* rob,
-                                Sink&& sink, unsigned& nvisit)
-{
-    static_assert(J <= kSRob && (kSRob & (kSRob - 1)) == 0, "reorder window: a power of two, at least J");
-    const char* rsb = reinterpret_cast<const char*>(rs);
-    const uint32_t* words = sector_base(q);
-    int next = t_begin, commit = t_begin;
-    uint32_t done = 0u;                       // bit (t mod kSRob): tree t is finished, its leaf block waits in rob
-    uint32_t bb[J];
-    int tr[J];
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const bool go = next < t_end;
-        tr[j] = go ? next : -1;
-        bb[j] = go ? __ldg(q.root + next) : kSLeafFlag;
-        next += go ? 1 : 0;
-    }
-    while (commit < t_end) {
-        // ---- one block visit of every slot (as in traverse_s) ----
-        uint2 w01[J];
-        const uint32_t* blk[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            blk[j] = sector_block(q, words, bb[j]);
-            w01[j] = __ldg(reinterpret_cast<const uint2*>(blk[j]));
-        }
-        uint32_t h[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w01[j].y & 0xFFu) * q.tile_stride);
-            h[j] = sector_step(1u, w01[j].y, xs);
-            if (COUNT) nvisit += (w01[j].y != kSPassWord) ? 1u : 0u;
-        }
-#pragma unroll
-        for (int lev = 1; lev < 3; ++lev) {
-            uint32_t w[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) w[j] = __ldg(blk[j] + h[j]);
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w[j] & 0xFFu) * q.tile_stride);
-                h[j] = sector_step(h[j], w[j], xs);
-                if (COUNT) nvisit += (w[j] != kSPassWord) ? 1u : 0u;
-            }
-        }
-        uint32_t any = 0u;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            bb[j] = sector_umax(bb[j], w01[j].x + (h[j] - 8u));
-            any |= bb[j];
-        }
-        // ---- retire / commit / restart (rare: about once per tree) ----
-        // a slot can only be finished in every lane if every lane has some finished slot: one vote rejects most visits
-        if (!sector_warp_all((int32_t)any < 0)) continue;
-        uint32_t m = 0u;
-#pragma unroll
-        for (int j = 0; j < J; ++j) m |= (bb[j] >> 31) << j;
-        m = sector_warp_and(m);                                       // slots finished in every lane
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            if (((m >> j) & 1u) && tr[j] >= 0) {
-                const uint32_t lb = bb[j] & ~kSLeafFlag;
-                const int slot = tr[j] & (kSRob - 1);
-                rob[slot * P] = lb;
-                sink(tr[j], lb);
-                done |= 1u << slot;
-                tr[j] = -1;                                           // empty until restarted below
-            }
-        }
-        while (done & (1u << (commit & (kSRob - 1)))) {               // the sum takes the leaves in tree order
-            const uint32_t lb = rob[(commit & (kSRob - 1)) * P];
-            sum += __ldg(reinterpret_cast<const double*>(words + (size_t)lb * 8u + kSWordValue));
-            done &= ~(1u << (commit & (kSRob - 1)));
-            ++commit;
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            if (tr[j] < 0 && next < t_end && next - commit < kSRob) {
-                tr[j] = next;
-                bb[j] = __ldg(q.root + next);
-                ++next;
-            }
-        }
-    }
-    return sum;
-}
-
 // ---- host: build the image ---------------------------------------------------------------------
 // node(i) -> {is_leaf, feature, left child index (right = left + 1), complemented node word, leaf number, value}
 // for the wide device layout of engine.cu (tree t's root is node t).  Blocks of a tree are contiguous, in BFS order

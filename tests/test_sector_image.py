@@ -30,7 +30,6 @@ def lib(request, tmp_path_factory):
     L.sh_free.argtypes = [C.c_void_p]
     L.sh_set_keys.argtypes = [C.c_void_p, C.c_void_p]
     L.sh_walk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
-    L.sh_walk_refill.argtypes = L.sh_walk.argtypes
     return L
 
 
@@ -46,15 +45,14 @@ def _build(lib, flat, nfeat):
     return h
 
 
-def _walk(lib, h, Q, T, J, t_begin=0, t_end=None, total=None, refill=False):
+def _walk(lib, h, Q, T, J, t_begin=0, t_end=None, total=None):
     Xt = np.ascontiguousarray(Q.T)
     node = np.full((len(Q), T), -1, dtype=np.int32)
     key = np.zeros((len(Q), T), dtype=np.uint32)
     total = np.zeros(len(Q)) if total is None else total
     visits = C.c_uint64(0)
-    fn = lib.sh_walk_refill if refill else lib.sh_walk
-    assert fn(h, _p(Xt), len(Q), len(Q), J, t_begin, T if t_end is None else t_end, _p(total), _p(node), _p(key),
-              C.byref(visits)) == 0
+    assert lib.sh_walk(h, _p(Xt), len(Q), len(Q), J, t_begin, T if t_end is None else t_end, _p(total), _p(node), _p(key),
+                       C.byref(visits)) == 0
     return total, node, key, visits.value
 
 
@@ -87,17 +85,15 @@ def test_sector_walk_equals_the_oracle(lib):
     dep = _depths(flat)
     d = np.stack([dep[t][want_node[:, t]] for t in range(flat.ntrees)], axis=1)
     for J in (1, 2, 4, 8, 12, 16):                  # 60 trees: J = 8 leaves a tail of 4, J = 16 a tail of 12
-        for refill in (False, True):                # lock-step groups / slot refill with the in-order reorder window
-            total, node, _, visits = _walk(lib, h, Q, flat.ntrees, J, refill=refill)
-            np.testing.assert_array_equal(node, want_node, err_msg=f"J={J} refill={refill}")
-            np.testing.assert_array_equal(total / flat.ntrees, want_mean, err_msg=f"J={J} refill={refill}")   # tree order: bit-equal
-            assert visits == d.sum(), f"J={J} refill={refill}: internal nodes counted"
+        total, node, _, visits = _walk(lib, h, Q, flat.ntrees, J)
+        np.testing.assert_array_equal(node, want_node, err_msg=f"J={J}")
+        np.testing.assert_array_equal(total / flat.ntrees, want_mean, err_msg=f"J={J}")        # tree order: bit-equal
+        assert visits == d.sum(), f"J={J}: internal nodes counted"
     # tree ranges (one launch per forest chunk): the running sum is carried through
-    for refill in (False, True):
-        total, node, _, _ = _walk(lib, h, Q, flat.ntrees, 8, 0, 13, refill=refill)
-        total, node2, _, _ = _walk(lib, h, Q, flat.ntrees, 8, 13, 60, total, refill=refill)
-        np.testing.assert_array_equal(total / flat.ntrees, want_mean)
-        np.testing.assert_array_equal(np.where(node2 >= 0, node2, node), want_node)
+    total, node, _, _ = _walk(lib, h, Q, flat.ntrees, 8, 0, 13)
+    total, node2, _, _ = _walk(lib, h, Q, flat.ntrees, 8, 13, 60, total)
+    np.testing.assert_array_equal(total / flat.ntrees, want_mean)
+    np.testing.assert_array_equal(np.where(node2 >= 0, node2, node), want_node)
     blocks, leaves, unused = lib.sh_stats(h, 0), lib.sh_stats(h, 1), lib.sh_stats(h, 2)
     nodes = int(flat.node_offsets[-1])
     assert leaves == sum(int((flat.left[flat.node_offsets[t]:flat.node_offsets[t + 1]] == 0).sum()) for t in range(flat.ntrees))
@@ -152,8 +148,7 @@ def test_degenerate_forests(lib):
     Q = np.array([(a, b) for a in g for b in g])
     fo = flat.as_dict()
     for J in (1, 2, 4, 8):
-        for refill in (False, True):
-            total, node, _, _ = _walk(lib, h, Q, 3, J, refill=refill)
-            np.testing.assert_array_equal(node, oracle.forest_terminal_nodes(fo, Q))
-            np.testing.assert_array_equal(total / 3, oracle.forest_predict(fo, Q))
+        total, node, _, _ = _walk(lib, h, Q, 3, J)
+        np.testing.assert_array_equal(node, oracle.forest_terminal_nodes(fo, Q))
+        np.testing.assert_array_equal(total / 3, oracle.forest_predict(fo, Q))
     lib.sh_free(h)

@@ -107,29 +107,6 @@ extern "C" void sh_set_keys(void* h, const uint32_t* key_of_leaf) {
 }
 
 template <int J>
-static void walk_refill(const Image* im, const double* X, int64_t npix, int64_t ldx, int t_begin, int t_end, double* sum,
-                        int32_t* node, uint32_t* key, uint64_t* visits)
-{
-    rfsi::SectorView q{im->words.data(), im->root.data(), 32u, 4u};
-    std::vector<uint32_t> rk((size_t)im->F);
-    uint32_t rob[rfsi::kSRob];
-    for (int64_t p = 0; p < npix; ++p) {
-        for (int f = 0; f < im->F; ++f) {
-            const auto& u = im->u[(size_t)f];
-            rk[(size_t)f] = (uint32_t)(std::lower_bound(u.begin(), u.end(), X[(int64_t)f * ldx + p]) - u.begin()) << 8;
-        }
-        unsigned nv = 0;
-        auto sink = [&](int t, uint32_t lb) {
-            const uint32_t* blk = im->words.data() + (size_t)lb * 8;
-            if (node) node[p * im->T + t] = im->leaf_rid[blk[rfsi::kSWordLeafNo]];
-            if (key) key[p * im->T + t] = blk[rfsi::kSWordKey];
-        };
-        sum[p] = rfsi::traverse_r<1, J, true>(q, t_begin, t_end, sum[p], rk.data(), rob, sink, nv);
-        if (visits) *visits += nv;
-    }
-}
-
-template <int J>
 static void walk(const Image* im, const double* X, int64_t npix, int64_t ldx, int t_begin, int t_end, double* sum,
                  int32_t* node, uint32_t* key, uint64_t* visits)
 {
@@ -150,21 +127,6 @@ static void walk(const Image* im, const double* X, int64_t npix, int64_t ldx, in
         };
         sum[p] = rfsi::traverse_s<1, J, true>(q, t_begin, t_end, sum[p], rk.data(), sink, nv);
         if (visits) *visits += nv;
-    }
-}
-
-extern "C" int sh_walk_refill(const void* h, const double* X, int64_t npix, int64_t ldx, int J, int t_begin, int t_end, double* sum,
-                              int32_t* node, uint32_t* key, uint64_t* visits)
-{
-    const Image* im = static_cast<const Image*>(h);
-    switch (J) {
-        case 1: walk_refill<1>(im, X, npix, ldx, t_begin, t_end, sum, node, key, visits); return 0;
-        case 2: walk_refill<2>(im, X, npix, ldx, t_begin, t_end, sum, node, key, visits); return 0;
-        case 4: walk_refill<4>(im, X, npix, ldx, t_begin, t_end, sum, node, key, visits); return 0;
-        case 8: walk_refill<8>(im, X, npix, ldx, t_begin, t_end, sum, node, key, visits); return 0;
-        case 12: walk_refill<12>(im, X, npix, ldx, t_begin, t_end, sum, node, key, visits); return 0;
-        case 16: walk_refill<16>(im, X, npix, ldx, t_begin, t_end, sum, node, key, visits); return 0;
-        default: return -1;
     }
 }
 
