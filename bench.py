@@ -633,11 +633,16 @@ def main_ours(args):
         torch.cuda.synchronize(dev)
         lib.rfsi_profile_enable(1)
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prof_range = os.environ.get("RFSI_BENCH_PROFILE_QRF") == "1"   # ncu --profile-from-start off: capture this phase only
+        if prof_range:
+            torch.cuda.profiler.start()
         q0.record(stream)
         for i in range(args.steps):
             _lib.check(lib.rfsi_dev_predict_fused(model.handle, C.byref(qargs(2 + i)), wsq.data_ptr(), None, local, None))
         q1.record(stream)
         torch.cuda.synchronize(dev)
+        if prof_range:
+            torch.cuda.profiler.stop()
         lib.rfsi_profile_enable(0)
         qms = q0.elapsed_time(q1)
         tq, nq = C.c_double(0), C.c_uint64(0)

@@ -61,13 +61,16 @@ def _column(obj, col) -> np.ndarray:
 
 def near_obs(locations, observations, zcol=2, n_obs: int = 10, locations_x_y=(0, 1), observations_x_y=(0, 1),
              rm_dupl: bool = True, avg: bool = False, direct: bool = False, idw: bool = False,
-             return_idx: bool = False, device: int = 0):
+             return_idx: bool = False, device: int = 0, precision: str = "fp64"):
     """meteo::near.obs: for every location the n_obs nearest observations.
 
     Returns a data frame with columns dist1..distN then obs1..obsN (the order
     sim_500.R:146 relies on; names relied on at temp_croatia/1_models.R:978,1053).
     Column indices are 0-based here (R's c(1,2) default becomes (0, 1), zcol=3 -> 2).
     With return_idx also returns the 1-based neighbour indices (npix x n_obs).
+    precision="fp32": fp32 mode (rfsi_near_obs_f32) -- coordinates and values are rounded to float first, float
+    buffers cross PCIe, fp32 distances prefilter the search and the survivors are re-ranked in fp64: neighbours are
+    those of the fp64 call on the rounded coordinates, dist/obs come back as float32 columns.
     """
     if avg or direct or idw:
         # the reference passes only locations, observations, zcol, n.obs (all 20 call sites)
@@ -79,18 +82,31 @@ def near_obs(locations, observations, zcol=2, n_obs: int = 10, locations_x_y=(0,
     obs = _coords(observations, observations_x_y)
     z = _column(observations, zcol)
     npix, nobs = loc.shape[0], obs.shape[0]
+    if precision not in ("fp64", "fp32"):
+        raise ValueError("precision must be 'fp64' or 'fp32'")
+    names = [f"dist{j + 1}" for j in range(n_obs)] + [f"obs{j + 1}" for j in range(n_obs)]
+    idx = np.empty((n_obs, npix), dtype=np.int32) if return_idx else None
+    if precision == "fp32":
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        lx, ly, ox, oy, oz = f32(loc[:, 0]), f32(loc[:, 1]), f32(obs[:, 0]), f32(obs[:, 1]), f32(z)
+        both = np.empty((2, n_obs, npix), dtype=np.float32)
+        rc = _lib.load().rfsi_near_obs_f32(_ptr(lx), _ptr(ly), npix, _ptr(ox), _ptr(oy), _ptr(oz), nobs, n_obs,
+                                          1 if rm_dupl else 0, _ptr(both[0]), _ptr(both[1]), _ptr(idx), device)
+        if _lib.check(rc) == _lib.RFSI_W_TOO_FEW_OBS:
+            warnings.warn(_lib.last_error())
+        cols = [both[0, j] for j in range(n_obs)] + [both[1, j] for j in range(n_obs)]
+        out = pd.DataFrame(dict(zip(names, cols)), copy=False) if pd is not None else dict(zip(names, cols))
+        return (out, idx.T) if return_idx else out
     lx, ly = _f64(loc[:, 0]), _f64(loc[:, 1])
     ox, oy, oz = _f64(obs[:, 0]), _f64(obs[:, 1]), _f64(z)
     # one array per column, filled in place by the engine (rfsi_near_obs_cols_f64): the frame below wraps them
     cols = [np.empty(npix, dtype=np.float64) for _ in range(2 * n_obs)]
-    idx = np.empty((n_obs, npix), dtype=np.int32) if return_idx else None
     cptr = (C.c_void_p * (2 * n_obs))(*[c.ctypes.data for c in cols])
     iptr = (C.c_void_p * n_obs)(*[idx[j].ctypes.data for j in range(n_obs)]) if return_idx else None
     rc = _lib.load().rfsi_near_obs_cols_f64(_ptr(lx), _ptr(ly), npix, _ptr(ox), _ptr(oy), _ptr(oz), nobs, n_obs,
                                            1 if rm_dupl else 0, cptr, C.byref(cptr, n_obs * C.sizeof(C.c_void_p)), iptr, device)
     if _lib.check(rc) == _lib.RFSI_W_TOO_FEW_OBS:
         warnings.warn(_lib.last_error())
-    names = [f"dist{j + 1}" for j in range(n_obs)] + [f"obs{j + 1}" for j in range(n_obs)]
     out = pd.DataFrame(dict(zip(names, cols)), copy=False) if pd is not None else dict(zip(names, cols))
     return (out, idx.T) if return_idx else out
 

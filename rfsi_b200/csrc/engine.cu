@@ -15,6 +15,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include <sys/mman.h>
@@ -947,6 +948,7 @@ struct CellsWs {
     int32_t* cursor = nullptr;
     double2* sxy = nullptr;
     int32_t* sid = nullptr;
+    float2* sxyf = nullptr;   // the sorted coordinates as floats (read by the fp32-mode prefilter only)
 };
 
 // Morton-order permutation of unordered explicit locations (knn_cells.cuh)
@@ -988,7 +990,7 @@ int cells_G(int S) { return std::max(1, std::min(1024, (int)std::ceil(std::sqrt(
 size_t cells_ws_bytes(int S) {
     const size_t G2 = (size_t)cells_G(S) * cells_G(S);
     return 256 + align_up((G2 + 1) * 4, 256) + align_up(G2 * 4, 256) + align_up((size_t)std::max(S, 1) * 16, 256) +
-           align_up((size_t)std::max(S, 1) * 4, 256);
+           align_up((size_t)std::max(S, 1) * 4, 256) + align_up((size_t)std::max(S, 1) * 8, 256);
 }
 CellsWs carve_cells(void* ws, int S) {
     const size_t G2 = (size_t)cells_G(S) * cells_G(S);
@@ -998,27 +1000,29 @@ CellsWs carve_cells(void* ws, int S) {
     c.cell_start = reinterpret_cast<int32_t*>(p); p += align_up((G2 + 1) * 4, 256);
     c.cursor = reinterpret_cast<int32_t*>(p); p += align_up(G2 * 4, 256);
     c.sxy = reinterpret_cast<double2*>(p); p += align_up((size_t)std::max(S, 1) * 16, 256);
-    c.sid = reinterpret_cast<int32_t*>(p);
+    c.sid = reinterpret_cast<int32_t*>(p); p += align_up((size_t)std::max(S, 1) * 4, 256);
+    c.sxyf = reinterpret_cast<float2*>(p);
     return c;
 }
 int cells_min_S() { return env_int("RFSI_B200_CELLS_MIN", 128); }  // measured: the cell-grid search wins from ~100 stations up
 int build_cells(const double2* xy, int S, const CellsWs& c, cudaStream_t st) {
-    build_cells_kernel<<<1, 1024, 0, st>>>(xy, S, cells_G(S), c.hdr, c.cell_start, c.cursor, c.sxy, c.sid);
+    build_cells_kernel<<<1, 1024, 0, st>>>(xy, S, cells_G(S), c.hdr, c.cell_start, c.cursor, c.sxy, c.sid, c.sxyf);
     count_launch();
     CU_TRY(cudaGetLastError());
     return RFSI_OK;
 }
 
 // perm: Morton permutation for unordered explicit locations (build_loc_perm), or nullptr
+// f32_mode: every coordinate is a float (rfsi_near_obs_f32): fp32 prefilter, exact fp64 re-rank (knn_cells.cuh)
 template <int MODE>
 int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, const int32_t* perm, int k, const double* st_z,
                      int rm_dupl, double* out_a, double* out_b, int32_t* out_i, int64_t ld, int* warn, int* na_flag,
-                     cudaStream_t stream)
+                     cudaStream_t stream, bool f32_mode = false)
 {
     if (npix == 0) return RFSI_OK;
     const size_t smem = knn_cells_smem_bytes<kKnnP>(k);
     if (smem > 227 * 1024) return fail(RFSI_E_ARG, "n.obs = %d needs %zu B of shared memory (> 227 KB)", k - 1, smem);
-    auto kern = knn_cells_kernel<kKnnP, MODE>;
+    auto kern = f32_mode ? knn_cells_kernel<kKnnP, MODE, true> : knn_cells_kernel<kKnnP, MODE, false>;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // 2-D tiles need rows of L.ncol locations: the raster form, or explicit coordinates stored row by row
     const int tile2d = loc_rows(L, npix) ? 1 : 0;
@@ -1033,7 +1037,7 @@ int launch_knn_cells(const LocSpec& L, int64_t npix, const CellsWs& c, const int
     }
     {
         ProfScope ps(MODE == KNN_RAW ? PROF_KNN_RAW : PROF_KNN_FINAL, stream);
-        kern<<<(unsigned)ntiles, kKnnP, smem, stream>>>(L, npix, c.hdr, c.cell_start, c.sxy, c.sid, k, st_z, rm_dupl,
+        kern<<<(unsigned)ntiles, kKnnP, smem, stream>>>(L, npix, c.hdr, c.cell_start, c.sxy, c.sxyf, c.sid, k, st_z, rm_dupl,
                                                          out_a, out_b, out_i, ld, warn, na_flag, tile2d, tiles_per_row,
                                                          perm);
     }
@@ -1190,7 +1194,9 @@ int launch_qrf_direct(const uint32_t* keys, const double* dict, const unsigned c
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kQrfWarps, smem));
     const int64_t want = (nrows + kQrfWarps - 1) / kQrfWarps;   // persistent warps: one resident wave, a contiguous run of rows per CTA
     const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * std::max(per_sm, 1));
-    kern<<<grid, 32 * kQrfWarps, smem, stream>>>(keys, leaf_ids_ld(T), dict, skip, nrows, T, probs_dev, nprobs, out_q, ld_q, out_iqr);
+    static const int fast = env_int("RFSI_B200_QRF_FAST", 1);   // 0: the re-bucketing selection for every row (A/B switch, tests)
+    kern<<<grid, 32 * kQrfWarps, smem, stream>>>(keys, leaf_ids_ld(T), dict, skip, nrows, T, probs_dev, nprobs, out_q, ld_q, out_iqr,
+                                                 fast);
     return RFSI_OK;
 }
 
@@ -1297,11 +1303,26 @@ extern "C" int rfsi_dev_near_obs_f64(const double* loc_x, const double* loc_y, i
 
 namespace {
 
-// near.obs with host buffers; column j of dist / obs / idx goes to dist_cols[j] / obs_cols[j] / idx_cols[j] (nullable array)
-int host_near_obs(const double* loc_x, const double* loc_y, int64_t npix, const double* obs_x, const double* obs_y,
-                  const double* obs_z, int32_t nobs, int32_t n_obs, int32_t rm_dupl, double* const* dist_cols,
-                  double* const* obs_cols, int32_t* const* idx_cols, int device)
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];   // NA_real_ stays a NaN
+}
+
+// near.obs with host buffers; column j of dist / obs / idx goes to dist_cols[j] / obs_cols[j] / idx_cols[j] (nullable array).
+// T = double: the R call.  T = float: fp32 mode -- float buffers cross PCIe in both directions (half the bytes of the
+// host-bound part of the call), coordinates are widened on the device (exactly), the search runs with the fp32 prefilter
+// and the exact fp64 re-rank, results are rounded to float on the device.
+template <class T>
+int host_near_obs(const T* loc_x, const T* loc_y, int64_t npix, const T* obs_x, const T* obs_y,
+                  const T* obs_z, int32_t nobs, int32_t n_obs, int32_t rm_dupl, T* const* dist_cols,
+                  T* const* obs_cols, int32_t* const* idx_cols, int device)
 {
+    constexpr bool F32 = std::is_same<T, float>::value;
+    static const bool prefilter = env_int("RFSI_B200_KNN_F32_PREFILTER", 1) != 0;   // A/B switch (profiles/r02_i)
     for (int32_t s = 0; s < nobs; ++s)
         if (obs_x[s] != obs_x[s] || obs_y[s] != obs_y[s])
             return fail(RFSI_E_NA_INPUT, "near_obs: observation %d has an NA coordinate", s + 1);
@@ -1310,13 +1331,14 @@ int host_near_obs(const double* loc_x, const double* loc_y, int64_t npix, const 
     Trace tr;
 
     std::vector<double2> xy((size_t)std::max(nobs, 1));
-    for (int32_t s = 0; s < nobs; ++s) xy[s] = make_double2(obs_x[s], obs_y[s]);
+    std::vector<double> zz((size_t)std::max(nobs, 1));
+    for (int32_t s = 0; s < nobs; ++s) { xy[s] = make_double2((double)obs_x[s], (double)obs_y[s]); zz[s] = (double)obs_z[s]; }
     DevBuf d_xy, d_z, d_flags, d_cells;
     RF_TRY(d_xy.alloc(sizeof(double2) * xy.size()));
     RF_TRY(d_z.alloc(sizeof(double) * (size_t)std::max(nobs, 1)));
     RF_TRY(d_flags.alloc(2 * sizeof(int)));
     CU_TRY(cudaMemcpy(d_xy.p, xy.data(), sizeof(double2) * xy.size(), cudaMemcpyHostToDevice));
-    if (nobs > 0) CU_TRY(cudaMemcpy(d_z.p, obs_z, sizeof(double) * nobs, cudaMemcpyHostToDevice));
+    if (nobs > 0) CU_TRY(cudaMemcpy(d_z.p, zz.data(), sizeof(double) * nobs, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemset(d_flags.p, 0, 2 * sizeof(int)));
     const bool use_cells = nobs >= cells_min_S();
     CellsWs cells;
@@ -1331,9 +1353,9 @@ int host_near_obs(const double* loc_x, const double* loc_y, int64_t npix, const 
     const int64_t chunk = std::min<int64_t>(npix, std::max<int64_t>(4096, env_int("RFSI_B200_NEAR_CHUNK", 32768)));
     const int64_t nchunks = (npix + chunk - 1) / chunk;
     const int W = host_workers(nchunks);
-    const size_t row_bytes = (size_t)n_obs * (2 * sizeof(double) + (idx_cols ? sizeof(int32_t) : 0));
+    const size_t row_bytes = (size_t)n_obs * (2 * sizeof(T) + (idx_cols ? sizeof(int32_t) : 0));
     struct Lane {
-        DevBuf lx, ly, dist, obs, idx, perm;
+        DevBuf lx, ly, dist, obs, idx, perm, fin, fout;   // fin / fout: the float side of fp32 mode
         PinnedBuf stage;
         Stream st;   // last: destroyed (synchronised) before the buffers above
     };
@@ -1347,6 +1369,7 @@ int host_near_obs(const double* loc_x, const double* loc_y, int64_t npix, const 
         RF_TRY(ln.obs.alloc(sizeof(double) * chunk * n_obs));
         if (idx_cols) RF_TRY(ln.idx.alloc(sizeof(int32_t) * chunk * n_obs));
         if (use_cells) RF_TRY(ln.perm.alloc(loc_perm_bytes(chunk)));
+        if (F32) { RF_TRY(ln.fin.alloc(sizeof(float) * 2 * chunk)); RF_TRY(ln.fout.alloc(sizeof(float) * 2 * chunk * n_obs)); }
         RF_TRY(ln.stage.alloc(row_bytes * (size_t)chunk));
     }
     RF_TRY(pool_ready());
@@ -1356,8 +1379,16 @@ int host_near_obs(const double* loc_x, const double* loc_y, int64_t npix, const 
         cudaStream_t s = ln.st.s;
         for (int64_t c = w; c < nchunks; c += W) {
             const int64_t p0 = c * chunk, cur = std::min(chunk, npix - p0);
-            CU_TRY(cudaMemcpyAsync(ln.lx.p, loc_x + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
-            CU_TRY(cudaMemcpyAsync(ln.ly.p, loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+            if (F32) {
+                CU_TRY(cudaMemcpyAsync(ln.fin.p, loc_x + p0, sizeof(float) * cur, cudaMemcpyHostToDevice, s));
+                CU_TRY(cudaMemcpyAsync(ln.fin.as<float>() + cur, loc_y + p0, sizeof(float) * cur, cudaMemcpyHostToDevice, s));
+                f32_to_f64_kernel<<<(unsigned)((cur + 255) / 256), 256, 0, s>>>(ln.fin.as<float>(), ln.lx.as<double>(), cur);
+                f32_to_f64_kernel<<<(unsigned)((cur + 255) / 256), 256, 0, s>>>(ln.fin.as<float>() + cur, ln.ly.as<double>(), cur);
+                count_launch(); count_launch();
+            } else {
+                CU_TRY(cudaMemcpyAsync(ln.lx.p, loc_x + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+                CU_TRY(cudaMemcpyAsync(ln.ly.p, loc_y + p0, sizeof(double) * cur, cudaMemcpyHostToDevice, s));
+            }
             LocSpec L{ln.lx.as<double>(), ln.ly.as<double>(), 0, 0, 0, 0, 1, 0};
             const int32_t* perm = nullptr;
             if (use_cells) {
@@ -1365,7 +1396,7 @@ int host_near_obs(const double* loc_x, const double* loc_y, int64_t npix, const 
                 RF_TRY(launch_knn_cells<KNN_FINAL>(L, cur, cells, perm, n_obs + 1, d_z.as<double>(), rm_dupl,
                                                    ln.dist.as<double>(), ln.obs.as<double>(),
                                                    idx_cols ? ln.idx.as<int32_t>() : nullptr, cur, d_flags.as<int>(),
-                                                   d_flags.as<int>() + 1, s));
+                                                   d_flags.as<int>() + 1, s, F32 && prefilter));
             } else {
                 RF_TRY(launch_knn<KNN_FINAL>(L, cur, d_xy.as<double2>(), nobs, n_obs + 1, d_z.as<double>(), rm_dupl,
                                              ln.dist.as<double>(), ln.obs.as<double>(),
@@ -1373,18 +1404,28 @@ int host_near_obs(const double* loc_x, const double* loc_y, int64_t npix, const 
                                              d_flags.as<int>() + 1, s));
             }
             char* hs = ln.stage.as<char>();
-            double* h_dist = reinterpret_cast<double*>(hs);
-            double* h_obs = h_dist + (size_t)cur * n_obs;
+            T* h_dist = reinterpret_cast<T*>(hs);
+            T* h_obs = h_dist + (size_t)cur * n_obs;
             int32_t* h_idx = reinterpret_cast<int32_t*>(h_obs + (size_t)cur * n_obs);
-            CU_TRY(cudaMemcpyAsync(h_dist, ln.dist.p, sizeof(double) * cur * n_obs, cudaMemcpyDeviceToHost, s));
-            CU_TRY(cudaMemcpyAsync(h_obs, ln.obs.p, sizeof(double) * cur * n_obs, cudaMemcpyDeviceToHost, s));
+            const void* src_dist = ln.dist.p;
+            const void* src_obs = ln.obs.p;
+            if (F32) {
+                const long long ne = (long long)cur * n_obs;
+                f64_to_f32_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(ln.dist.as<double>(), ln.fout.as<float>(), ne);
+                f64_to_f32_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(ln.obs.as<double>(), ln.fout.as<float>() + ne, ne);
+                count_launch(); count_launch();
+                src_dist = ln.fout.p;
+                src_obs = ln.fout.as<float>() + ne;
+            }
+            CU_TRY(cudaMemcpyAsync(h_dist, src_dist, sizeof(T) * cur * n_obs, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaMemcpyAsync(h_obs, src_obs, sizeof(T) * cur * n_obs, cudaMemcpyDeviceToHost, s));
             if (idx_cols) CU_TRY(cudaMemcpyAsync(h_idx, ln.idx.p, sizeof(int32_t) * cur * n_obs, cudaMemcpyDeviceToHost, s));
             CU_TRY(cudaStreamSynchronize(s));
             for (int j = 0; j < n_obs; ++j) {   // the caller's (possibly never touched) pages: this thread maps and fills them
-                prefault_for_write(dist_cols[j] + p0, sizeof(double) * cur);
-                prefault_for_write(obs_cols[j] + p0, sizeof(double) * cur);
-                memcpy(dist_cols[j] + p0, h_dist + (size_t)j * cur, sizeof(double) * cur);
-                memcpy(obs_cols[j] + p0, h_obs + (size_t)j * cur, sizeof(double) * cur);
+                prefault_for_write(dist_cols[j] + p0, sizeof(T) * cur);
+                prefault_for_write(obs_cols[j] + p0, sizeof(T) * cur);
+                memcpy(dist_cols[j] + p0, h_dist + (size_t)j * cur, sizeof(T) * cur);
+                memcpy(obs_cols[j] + p0, h_obs + (size_t)j * cur, sizeof(T) * cur);
                 if (idx_cols) memcpy(idx_cols[j] + p0, h_idx + (size_t)j * cur, sizeof(int32_t) * cur);
             }
         }
@@ -1425,8 +1466,8 @@ extern "C" int rfsi_near_obs_f64(const double* loc_x, const double* loc_y, int64
         oc[(size_t)j] = out_obs + (size_t)j * npix;
         ic[(size_t)j] = out_idx ? out_idx + (size_t)j * npix : nullptr;
     }
-    return host_near_obs(loc_x, loc_y, npix, obs_x, obs_y, obs_z, nobs, n_obs, rm_dupl, dc.data(), oc.data(),
-                         out_idx ? ic.data() : nullptr, device);
+    return host_near_obs<double>(loc_x, loc_y, npix, obs_x, obs_y, obs_z, nobs, n_obs, rm_dupl, dc.data(), oc.data(),
+                                 out_idx ? ic.data() : nullptr, device);
 }
 
 extern "C" int rfsi_near_obs_cols_f64(const double* loc_x, const double* loc_y, int64_t npix, const double* obs_x,
@@ -1438,84 +1479,28 @@ extern "C" int rfsi_near_obs_cols_f64(const double* loc_x, const double* loc_y, 
     for (int j = 0; j < n_obs && npix > 0; ++j)
         if (!dist_cols[j] || !obs_cols[j] || (idx_cols && !idx_cols[j]))
             return fail(RFSI_E_ARG, "near_obs: column %d of the output is NULL", j + 1);
-    return host_near_obs(loc_x, loc_y, npix, obs_x, obs_y, obs_z, nobs, n_obs, rm_dupl, dist_cols, obs_cols, idx_cols, device);
+    return host_near_obs<double>(loc_x, loc_y, npix, obs_x, obs_y, obs_z, nobs, n_obs, rm_dupl, dist_cols, obs_cols, idx_cols, device);
 }
 
-// fp32 twin of near.obs: float buffers in and out; coordinates are widened to fp64 on the
-// device and the search itself is the fp64 one, so neighbour indices are those of the fp64
-// call on the same (float-representable) coordinates and dist/obs are its results rounded to
-// float (north_star: 1e-5 relative in fp32 mode).
-namespace {
-__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (double)in[i];
-}
-__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (float)in[i];   // NA_real_ stays a NaN
-}
-}  // namespace
-
+// fp32 mode of near.obs (north_star: "1e-5 in fp32 mode"): float buffers in and out through the same pinned, chunked
+// pipeline as the fp64 call -- half the bytes over PCIe and through the host copies, which is where the call's time goes
+// (profiles/r02_i_fp32_mode.txt) -- and fp32 distance arithmetic as a prefilter in the cell-grid search, every survivor
+// re-ranked by its exact fp64 distance (knn_cells.cuh).  Neighbour indices are therefore bit-identical to the fp64 call on
+// the same (float-representable) coordinates; dist/obs are its results rounded to float (6e-8 relative).
 extern "C" int rfsi_near_obs_f32(const float* loc_x, const float* loc_y, int64_t npix, const float* obs_x,
                                  const float* obs_y, const float* obs_z, int32_t nobs, int32_t n_obs, int32_t rm_dupl,
                                  float* out_dist, float* out_obs, int32_t* out_idx, int device)
 {
-    if (npix < 0 || nobs < 0 || n_obs < 1) return fail(RFSI_E_ARG, "near_obs_f32: npix/nobs must be >= 0, n.obs >= 1");
-    if (npix > 0 && (!loc_x || !loc_y || !out_dist || !out_obs)) return fail(RFSI_E_ARG, "near_obs_f32: NULL buffer");
-    if (nobs > 0 && (!obs_x || !obs_y || !obs_z)) return fail(RFSI_E_ARG, "near_obs_f32: NULL observations");
-    for (int32_t s = 0; s < nobs; ++s)
-        if (obs_x[s] != obs_x[s] || obs_y[s] != obs_y[s])
-            return fail(RFSI_E_NA_INPUT, "near_obs_f32: observation %d has an NA coordinate", s + 1);
-    RF_TRY(use_device(device));
-    if (npix == 0) return RFSI_OK;
-    const int64_t chunk = std::min<int64_t>(npix, 1 << 20);
-    const int64_t nmax = std::max<int64_t>(chunk * n_obs, std::max<int64_t>(nobs, 1));
-    DevBuf f_in, d_lx, d_ly, d_ox, d_oy, d_oz, d_dist, d_obs, d_idx, f_out, d_warn;
-    RF_TRY(f_in.alloc(sizeof(float) * std::max<int64_t>(chunk, std::max<int64_t>(nobs, 1))));
-    RF_TRY(d_lx.alloc(sizeof(double) * chunk)); RF_TRY(d_ly.alloc(sizeof(double) * chunk));
-    RF_TRY(d_ox.alloc(sizeof(double) * std::max(nobs, 1))); RF_TRY(d_oy.alloc(sizeof(double) * std::max(nobs, 1)));
-    RF_TRY(d_oz.alloc(sizeof(double) * std::max(nobs, 1)));
-    RF_TRY(d_dist.alloc(sizeof(double) * chunk * n_obs)); RF_TRY(d_obs.alloc(sizeof(double) * chunk * n_obs));
-    if (out_idx) RF_TRY(d_idx.alloc(sizeof(int32_t) * chunk * n_obs));
-    RF_TRY(f_out.alloc(sizeof(float) * nmax));
-    RF_TRY(d_warn.alloc(sizeof(int)));
-    CU_TRY(cudaMemset(d_warn.p, 0, sizeof(int)));
-    auto widen = [&](const float* host, double* dev, int64_t n) -> int {
-        if (n == 0) return RFSI_OK;
-        CU_TRY(cudaMemcpy(f_in.p, host, sizeof(float) * n, cudaMemcpyHostToDevice));
-        f32_to_f64_kernel<<<(unsigned)((n + 255) / 256), 256>>>(f_in.as<float>(), dev, n);
-        count_launch();
-        CU_TRY(cudaGetLastError());
-        return RFSI_OK;
-    };
-    auto narrow = [&](const double* dev, float* host, int64_t cur, int64_t p0) -> int {
-        f64_to_f32_kernel<<<(unsigned)((cur * n_obs + 255) / 256), 256>>>(dev, f_out.as<float>(), cur * n_obs);
-        count_launch();
-        CU_TRY(cudaMemcpy2D(host + p0, sizeof(float) * npix, f_out.p, sizeof(float) * cur, sizeof(float) * cur, n_obs,
-                            cudaMemcpyDeviceToHost));
-        return RFSI_OK;
-    };
-    RF_TRY(widen(obs_x, d_ox.as<double>(), nobs)); RF_TRY(widen(obs_y, d_oy.as<double>(), nobs));
-    RF_TRY(widen(obs_z, d_oz.as<double>(), nobs));
-    for (int64_t p0 = 0; p0 < npix; p0 += chunk) {
-        const int64_t cur = std::min(chunk, npix - p0);
-        RF_TRY(widen(loc_x + p0, d_lx.as<double>(), cur)); RF_TRY(widen(loc_y + p0, d_ly.as<double>(), cur));
-        RF_TRY(rfsi_dev_near_obs_f64(d_lx.as<double>(), d_ly.as<double>(), cur, d_ox.as<double>(), d_oy.as<double>(),
-                                     d_oz.as<double>(), nobs, n_obs, rm_dupl, d_dist.as<double>(), d_obs.as<double>(),
-                                     out_idx ? d_idx.as<int32_t>() : nullptr, d_warn.as<int>(), device, nullptr));
-        RF_TRY(narrow(d_dist.as<double>(), out_dist, cur, p0));
-        RF_TRY(narrow(d_obs.as<double>(), out_obs, cur, p0));
-        if (out_idx)
-            CU_TRY(cudaMemcpy2D(out_idx + p0, sizeof(int32_t) * npix, d_idx.p, sizeof(int32_t) * cur,
-                                sizeof(int32_t) * cur, n_obs, cudaMemcpyDeviceToHost));
+    RF_TRY(check_near_obs_args(npix, nobs, n_obs, loc_x, loc_y, out_dist, out_obs, obs_x, obs_y, obs_z));
+    std::vector<float*> dc((size_t)n_obs), oc((size_t)n_obs);
+    std::vector<int32_t*> ic((size_t)n_obs);
+    for (int j = 0; j < n_obs; ++j) {
+        dc[(size_t)j] = out_dist + (size_t)j * npix;
+        oc[(size_t)j] = out_obs + (size_t)j * npix;
+        ic[(size_t)j] = out_idx ? out_idx + (size_t)j * npix : nullptr;
     }
-    int warn = 0;
-    CU_TRY(cudaMemcpy(&warn, d_warn.p, sizeof warn, cudaMemcpyDeviceToHost));
-    if (warn) {
-        g_err = "near_obs_f32: fewer observations than n.obs(+1); missing neighbours are NA";
-        return RFSI_W_TOO_FEW_OBS;
-    }
-    return RFSI_OK;
+    return host_near_obs<float>(loc_x, loc_y, npix, obs_x, obs_y, obs_z, nobs, n_obs, rm_dupl, dc.data(), oc.data(),
+                                out_idx ? ic.data() : nullptr, device);
 }
 
 // near.obs for all days of a station table (the per-day feature / training table)

@@ -33,7 +33,7 @@ __device__ __forceinline__ int cell_coord(double v, double v0, double inv_cs, in
 __global__ void __launch_bounds__(1024)
 build_cells_kernel(const double2* __restrict__ xy, int S, int Gmax, CellHeader* __restrict__ hdr,
                    int32_t* __restrict__ cell_start, int32_t* __restrict__ cursor,
-                   double2* __restrict__ sxy, int32_t* __restrict__ sid)
+                   double2* __restrict__ sxy, int32_t* __restrict__ sid, float2* __restrict__ sxyf)
 {
     __shared__ double red[4][32];
     __shared__ CellHeader h;
@@ -107,6 +107,7 @@ build_cells_kernel(const double2* __restrict__ xy, int S, int Gmax, CellHeader* 
         const int slot = atomicAdd(&cursor[c], 1);
         sxy[slot] = p;
         sid[slot] = i;
+        if (sxyf) sxyf[slot] = make_float2((float)p.x, (float)p.y);   // fp32 mode: the coordinates ARE floats (exact)
     }
 }
 
@@ -201,10 +202,22 @@ __device__ __forceinline__ long long knn_pixel_of_thread(const LocSpec& L, long 
     return row * L.ncol + col - L.pix_begin;
 }
 
-template <int P, int MODE>
+// fp32 mode (PREF, rfsi_near_obs_f32; north_star's "1e-5 in fp32 mode"): every location and station coordinate is a
+// float, so d2 is first formed in fp32 -- two subtractions, two products, one sum, each rounded once:
+// d2f = d2 (1 + e), |e| < 2^-22 (+ 2^-148 when a product underflows) -- and a station is dropped on that value alone
+// when d2f > lim = k-th best d2, rounded up to float, times (1 + 2^-20): then d2 >= d2f / (1 + 2^-22) > k-th best, the
+// station can neither enter the list nor tie with its last entry.  Everything that survives is re-ranked by the exact
+// fp64 d2 of the same coordinates, so neighbours and their order are bit-identical to the fp64 search; the distances
+// that come out are the fp64 ones (rounded to float by the caller: 6e-8 relative).
+__device__ __forceinline__ float knn_f32_limit(double thr) {
+    return __fadd_ru(__fmul_ru(__double2float_ru(thr), 1.000001f), 1.0e-37f);
+}
+
+template <int P, int MODE, bool PREF = false>
 __global__ void __launch_bounds__(P)
 knn_cells_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
                  const int32_t* __restrict__ cell_start, const double2* __restrict__ sxy,
+                 const float2* __restrict__ sxyf,
                  const int32_t* __restrict__ sid, int k, const double* __restrict__ st_z, int rm_dupl,
                  double* __restrict__ out_a, double* __restrict__ out_b, int32_t* __restrict__ out_i,
                  long long ld, int* __restrict__ warn, int* __restrict__ na_flag, int tile2d,
@@ -230,6 +243,8 @@ knn_cells_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
     for (int j = 0; j < k; ++j) { ld2[j * P] = inf; lid[j * P] = kIdxNone; }
     double thr = inf;
     int32_t thr_id = kIdxNone;
+    const float pxf = (float)px, pyf = (float)py;      // PREF: exact, the caller's coordinates are floats
+    float lim = __int_as_float(0x7f800000);            // +inf: nothing is dropped before the list is full
 
     if (threadIdx.x == 0) { s_box[0] = G; s_box[1] = -1; s_box[2] = G; s_box[3] = -1; }
     __syncthreads();
@@ -253,6 +268,22 @@ knn_cells_kernel(LocSpec L, long long npix, const CellHeader* __restrict__ hdr,
                 const int c = y * G + x;
                 const int s_begin = __ldg(cell_start + c), s_end = __ldg(cell_start + c + 1);
                 for (int s = s_begin; s < s_end; ++s) {
+                    if (PREF) {
+                        const float2 qf = __ldg(sxyf + s);
+                        const float dxf = __fsub_rn(pxf, qf.x), dyf = __fsub_rn(pyf, qf.y);
+                        const float d2f = __fadd_rn(__fmul_rn(dxf, dxf), __fmul_rn(dyf, dyf));
+                        if (!act || d2f > lim) continue;                      // cannot enter the list, cannot tie
+                        const double2 q = __ldg(sxy + s);
+                        const int32_t id = __ldg(sid + s);
+                        const double d2 = dist2_rn(px, py, q.x, q.y);         // exact re-rank of the survivors
+                        if (d2 < thr || (d2 == thr && id < thr_id)) {
+                            list_insert<P>(ld2, lid, k, d2, id);
+                            thr = ld2[(k - 1) * P];
+                            thr_id = lid[(k - 1) * P];
+                            lim = knn_f32_limit(thr);
+                        }
+                        continue;
+                    }
                     const double2 q = __ldg(sxy + s);
                     const int32_t id = __ldg(sid + s);
                     if (act) {

@@ -423,6 +423,236 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
 }
 
 
+// ---- one row of integer keys, all quantiles in one pass over the row (direct form) ---------------------------------
+// Same selection idea as qrf_row_finish (monotone buckets between the row's min and max, exact ranking inside the few
+// buckets that matter), restated for 4-byte keys so that a row costs about half the instructions (profiles/r02_h):
+//   * NA keys (0xFFFFFFFF) are simply the largest keys: ranks below the number of valid samples never reach them, so
+//     there is no validity mask; the row's tail beyond T is filled with NA by the caller;
+//   * bucket(x) = min(255, umulhi(x - min, mult)), mult <= (2^40 - 1) / (max - min + 1): two integer instructions, monotone;
+//   * one histogram, one warp scan; the table is rewritten in place as tab[b] = first rank of bucket b | (one past its last
+//     rank) << 16, so every element learns the rank interval of its own bucket with one shared-memory load;
+//   * per quantile the WINDOW = the elements whose bucket's rank interval meets [k, k+1] (k = floor(index) - 1): the bucket
+//     holding rank k and, when k is that bucket's last rank, the next non-empty bucket.  The three windows of a group of
+//     three quantiles are marked in ONE pass over the 16 elements of a lane (no per-quantile bucket search, no bucket
+//     matching); a window's members (a handful) are compacted into shared memory with the first rank of their bucket
+//     and ranked against each other: global rank = smallest first rank in the window + local rank;
+//   * lanes 0..2 finish the three quantiles side by side (R's (1-h)*x[lo] + h*x[hi], two dictionary look-ups each).
+// Returns false -- nothing written -- when a window has more than 32 members that are not all equal (heavy ties next to
+// other values): the caller then runs qrf_row_finish, which re-buckets.
+constexpr int kQrfGroup = 3;   // quantiles marked per pass over the row
+
+// window bit of element r for rank k: bucket interval [first, end) meets {k, k+1}  <=>  first <= k+1 && end > k.
+// iv = first | end << 16, iv_lo = iv << 16 = first << 16, kk = (k+1) << 16: end > k <=> iv >= kk; first <= k+1 <=> iv_lo <= kk.
+// Three instructions: written in PTX because the compiler otherwise collects all 48 predicates of a row first and
+// spills them (profiles/r02_h_sass_qrf_fast.txt).
+__device__ __forceinline__ void qrf_mark(unsigned& w, uint32_t iv, uint32_t iv_lo, uint32_t kk, uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %1, %3;\n\tsetp.le.and.u32 p, %2, %3, p;\n\t@p or.b32 %0, %0, %4;\n\t}"
+        : "+r"(w) : "r"(iv), "r"(iv_lo), "r"(kk), "r"(bit));
+}
+
+template <int R>
+__device__ __forceinline__ bool qrf_row_fast(const uint32_t* sv, int* tab, uint2* mem, int lane, long long row,
+                                             const double* __restrict__ probs, int nprobs, const double* __restrict__ dict,
+                                             double* __restrict__ out_q, long long ld_q, int16_t* __restrict__ out_iqr_i16)
+{
+    static_assert(R % 2 == 0 || R == 1, "rows are read two elements at a time");
+    constexpr uint32_t NA = 0xFFFFFFFFu;
+    const double nan = na_real();
+    uint32_t x[R];
+    uint32_t mn = NA, mxp = 0u;
+    unsigned nval = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) x[r] = sv[r * 32 + lane];
+#pragma unroll
+    for (int r = 0; r + 1 < R; r += 2) {
+        const uint32_t y0 = x[r] + 1u, y1 = x[r + 1] + 1u;       // NA + 1 wraps to 0: the maximum of the valid keys, plus one
+        mn = __vimin3_u32(mn, x[r], x[r + 1]);
+        mxp = __vimax3_u32(mxp, y0, y1);
+        nval += min(y0, 1u) + min(y1, 1u);
+    }
+    if (R & 1) {
+        const uint32_t y0 = x[R - 1] + 1u;
+        mn = min(mn, x[R - 1]); mxp = max(mxp, y0); nval += min(y0, 1u);
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mxp = __reduce_max_sync(0xffffffffu, mxp);
+    const int m = (int)__reduce_add_sync(0xffffffffu, nval);                          // na.rm = TRUE
+    const uint32_t mx = mxp - 1u;
+
+    double qfirst = nan, qlast = nan;
+    if (m == 0 || mn == mx) {                       // no sample at all, or every sample equal
+        const double q = (m == 0) ? nan : __ldg(dict + mn);
+        if (out_q) for (int j = lane; j < nprobs; j += 32) out_q[(long long)j * ld_q + row] = q;
+        qfirst = qlast = q;
+    } else {
+        // ---- histogram of 256 monotone buckets, scanned into rank intervals ------------------------
+        const float fr = __uint2float_ru(mx - mn + 1u);                              // >= 2
+        const uint32_t mult = __float2uint_rz(__fdividef(1099507433472.0f, fr));     // 2^40 (1 - 2^-18) / (range + 1), saturating
+        reinterpret_cast<int4*>(tab)[lane * 2] = make_int4(0, 0, 0, 0);
+        reinterpret_cast<int4*>(tab)[lane * 2 + 1] = make_int4(0, 0, 0, 0);
+        __syncwarp();
+        const int* slot[R];                                                           // &tab[bucket of element r]
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            slot[r] = tab + min(__umulhi(x[r] - mn, mult), 255u);                    // the clamp only ever acts on NA keys
+            atomicAdd(const_cast<int*>(slot[r]), 1);
+        }
+        __syncwarp();
+        {
+            const int4 h0 = reinterpret_cast<const int4*>(tab)[lane * 2];
+            const int4 h1 = reinterpret_cast<const int4*>(tab)[lane * 2 + 1];
+            const int s1 = h0.x, s2 = s1 + h0.y, s3 = s2 + h0.z, s4 = s3 + h0.w;
+            const int s5 = s4 + h1.x, s6 = s5 + h1.y, s7 = s6 + h1.z, s8 = s7 + h1.w;
+            int incl = s8;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int e = incl - s8;                                                  // elements in the buckets of lower lanes
+            const int4 p0 = make_int4(e | ((e + s1) << 16), (e + s1) | ((e + s2) << 16), (e + s2) | ((e + s3) << 16),
+                                      (e + s3) | ((e + s4) << 16));
+            const int4 p1 = make_int4((e + s4) | ((e + s5) << 16), (e + s5) | ((e + s6) << 16), (e + s6) | ((e + s7) << 16),
+                                      (e + s7) | ((e + s8) << 16));
+            __syncwarp();
+            reinterpret_cast<int4*>(tab)[lane * 2] = p0;
+            reinterpret_cast<int4*>(tab)[lane * 2 + 1] = p1;
+        }
+        __syncwarp();
+
+        const unsigned lt = (1u << lane) - 1u;
+        for (int j0 = 0; j0 < nprobs; j0 += kQrfGroup) {
+            // ---- lane j < 3: quantile j0 + j.  R: index = 1 + (n-1)*p in two roundings, lo = floor, hi = ceil --
+            const int jq = min(j0 + min(lane, kQrfGroup - 1), nprobs - 1);
+            const double index = __dadd_rn(1.0, __dmul_rn((double)(m - 1), probs[jq]));
+            const double lo = floor(index);
+            const int k_mine = (int)lo - 1;                                           // 0-based rank of x[lo]
+            const int k0 = __shfl_sync(0xffffffffu, k_mine, 0);
+            const int k1 = __shfl_sync(0xffffffffu, k_mine, 1);
+            const int k2 = __shfl_sync(0xffffffffu, k_mine, 2);
+            // ---- mark the three windows in one pass over this lane's elements --------------------
+            const uint32_t kk0 = (uint32_t)(k0 + 1) << 16, kk1 = (uint32_t)(k1 + 1) << 16, kk2 = (uint32_t)(k2 + 1) << 16;
+            unsigned w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t iv = (uint32_t)*slot[r];
+                const uint32_t iv_lo = iv << 16;
+                qrf_mark(w0, iv, iv_lo, kk0, 1u << r);
+                qrf_mark(w1, iv, iv_lo, kk1, 1u << r);
+                qrf_mark(w2, iv, iv_lo, kk2, 1u << r);
+            }
+            uint32_t klo_mine = 0, khi_mine = 0;
+#pragma unroll
+            for (int g = 0; g < kQrfGroup; ++g) {
+                unsigned wm = g == 0 ? w0 : (g == 1 ? w1 : w2);
+                const int k = g == 0 ? k0 : (g == 1 ? k1 : k2);
+                if (g > 0 && j0 + g >= nprobs) break;                                 // uniform
+                const int cnt = (int)__reduce_add_sync(0xffffffffu, (unsigned)__popc(wm));
+                uint32_t klo, khi;
+                if (cnt > 32) {
+                    // heavy window: more members than lanes means ties (many trees returning the same training sample,
+                    // zero-inflated data).  The same peeling on the uncompacted members: the smallest remaining value,
+                    // its multiplicity, drop it; a handful of distinct values at most before the rank is covered.
+                    uint32_t base = 0xFFFFu;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (wm & (1u << r)) base = min(base, (uint32_t)*slot[r] & 0xFFFFu);
+                    int a = k - (int)__reduce_min_sync(0xffffffffu, base);           // rank k inside the window
+                    bool found = false;
+#pragma unroll 1
+                    for (int it = 0; it < 8 && !found; ++it) {
+                        uint32_t v = NA;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) v = (wm & (1u << r)) ? min(v, sv[r * 32 + lane]) : v;
+                        v = __reduce_min_sync(0xffffffffu, v);
+                        unsigned eqm = 0;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) eqm |= (sv[r * 32 + lane] == v) ? (1u << r) : 0u;
+                        eqm &= wm;
+                        const int n_eq = (int)__reduce_add_sync(0xffffffffu, (unsigned)__popc(eqm));
+                        wm &= ~eqm;
+                        if (a < n_eq || n_eq == 0) {                                  // n_eq == 0 cannot happen (a < cnt): no endless loop
+                            klo = khi = v;
+                            if (a + 1 >= n_eq) {                                      // rank k+1 is the next distinct value
+                                uint32_t nx = NA;
+#pragma unroll
+                                for (int r = 0; r < R; ++r) nx = (wm & (1u << r)) ? min(nx, sv[r * 32 + lane]) : nx;
+                                khi = __reduce_min_sync(0xffffffffu, nx);
+                            }
+                            found = true;
+                        }
+                        a -= n_eq;
+                    }
+                    if (!found) return false;        // uniform: the caller re-buckets with qrf_row_finish
+                } else {
+                    // compact the members, one per lane and round, each with the first rank of its bucket
+                    int pos = 0;
+#pragma unroll 1
+                    while (__any_sync(0xffffffffu, wm != 0u)) {
+                        const bool is = wm != 0u;
+                        const unsigned bal = __ballot_sync(0xffffffffu, is);
+                        if (is) {
+                            const int r = __ffs(wm) - 1;
+                            wm &= wm - 1u;
+                            const uint32_t xv = sv[r * 32 + lane];
+                            const uint32_t iv = (uint32_t)tab[min(__umulhi(xv - mn, mult), 255u)];
+                            mem[pos + __popc(bal & lt)] = make_uint2(xv, iv & 0xFFFFu);
+                        }
+                        pos += __popc(bal);
+                    }
+                    __syncwarp();
+                    const uint2 mine = (lane < cnt) ? mem[lane] : make_uint2(NA, 0xFFFFu);
+                    int a = k - (int)__reduce_min_sync(0xffffffffu, mine.y);          // rank k inside the window
+                    // peel the window's distinct values from below (a tie group at a time) until the group that covers
+                    // rank a is reached: about |bucket| / 2 warp reductions, all results warp-uniform
+                    uint32_t cur = mine.x;
+#pragma unroll 1
+                    for (;;) {
+                        const uint32_t v = __reduce_min_sync(0xffffffffu, cur);
+                        const bool eq = cur == v;
+                        const int n_eq = __popc(__ballot_sync(0xffffffffu, eq));      // v == NA: all 32 lanes, ends the loop
+                        cur = eq ? NA : cur;
+                        if (a < n_eq) {
+                            klo = v;
+                            khi = (a + 1 < n_eq) ? v : __reduce_min_sync(0xffffffffu, cur);   // NA when rank k+1 does not exist
+                            break;
+                        }
+                        a -= n_eq;
+                    }
+                    __syncwarp();                                                     // mem is free again
+                }
+                if (lane == g) { klo_mine = klo; khi_mine = khi; }
+            }
+            // ---- lanes 0..2: interpolate and store ---------------------------------------------------
+            double q = nan;
+            if (lane < kQrfGroup && j0 + lane < nprobs) {
+                const double xlo = __ldg(dict + klo_mine);
+                // rank k+1 only exists as a sample when index > lo (otherwise it may be an NA key: no look-up)
+                const double xhi = (khi_mine == klo_mine || !(index > lo)) ? xlo : __ldg(dict + khi_mine);
+                q = xlo;
+                if (index > lo && xhi != xlo) {       // R: i <- which(index > lo & x[hi] != qs)
+                    const double h = index - lo;
+                    q = __dadd_rn(__dmul_rn(1.0 - h, xlo), __dmul_rn(h, xhi));
+                }
+                if (out_q) out_q[(long long)(j0 + lane) * ld_q + row] = q;
+            }
+            if (j0 == 0) qfirst = __shfl_sync(0xffffffffu, q, 0);
+            if (j0 + kQrfGroup >= nprobs) qlast = __shfl_sync(0xffffffffu, q, nprobs - 1 - j0);
+        }
+    }
+    if (lane == 0 && out_iqr_i16) {
+        const double c = __dmul_rn(__dmul_rn(__dsub_rn(qlast, qfirst), 0.5), 100.0);
+        int16_t r16 = -32767;
+        if (c == c) {
+            double rr = rint(c);
+            rr = fmin(fmax(rr, -32767.0), 32767.0);
+            r16 = (int16_t)rr;
+        }
+        out_iqr_i16[row] = r16;
+    }
+    return true;
+}
+
 // ---- DIRECT form: the scratch rows already hold the keys ------------------------------------------
 // With the sector forest image the walk stores each leaf's quantile key (the dictionary rank of ranger's
 // random.node.values entry) instead of the leaf number, so nothing is gathered here: a row of T keys is T
@@ -430,7 +660,7 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
 // ahead; the row being selected is used IN PLACE as qrf's sample array (no staging through registers, which is
 // what held the gather form at 121 registers and two CTAs per SM).
 template <int R>
-__host__ __device__ constexpr size_t qrf_direct_warp_smem() { return (size_t)3 * R * 32 * 4 + 256 * 4 + 256 * 4 + 32 * 4; }
+__host__ __device__ constexpr size_t qrf_direct_warp_smem() { return (size_t)3 * R * 32 * 4 + 256 * 4 + 256 * 4 + 32 * 8; }
 template <int R>
 __host__ __device__ constexpr size_t qrf_direct_smem_bytes() { return kQrfWarps * qrf_direct_warp_smem<R>(); }
 template <int R> constexpr int qrf_direct_min_blocks() { return R >= 32 ? 1 : (R >= 16 ? 3 : 4); }
@@ -439,7 +669,7 @@ template <int R>
 __global__ void __launch_bounds__(32 * kQrfWarps, qrf_direct_min_blocks<R>())
 qrf_direct_kernel(const uint32_t* __restrict__ keys, long long ld_ids, const double* __restrict__ dict,
                   const unsigned char* __restrict__ skip, long long nrows, int T, const double* __restrict__ probs, int nprobs,
-                  double* __restrict__ out_q, long long ld_q, int16_t* __restrict__ out_iqr_i16)
+                  double* __restrict__ out_q, long long ld_q, int16_t* __restrict__ out_iqr_i16, int fast)
 {
     extern __shared__ __align__(16) unsigned char qrf_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -462,9 +692,11 @@ qrf_direct_kernel(const uint32_t* __restrict__ keys, long long ld_ids, const dou
 
     auto fetch = [&](long long rw, int slot) {      // keys of row rw -> ring slot (asynchronous); always commits a group
         if (rw < row_end && !(skip && skip[rw])) {
-            const uint32_t* src = keys + rw * ld_ids;
-            uint32_t* dst = ring + slot * (R * 32);
-            for (int c = lane; c < nchunk; c += 32) qrf_cp_async16(dst + 4 * c, src + 4 * c);
+            const uint32_t* src = keys + rw * ld_ids + 4 * lane;
+            uint32_t* dst = ring + slot * (R * 32) + 4 * lane;
+#pragma unroll
+            for (int i = 0; i < (R + 3) / 4; ++i)     // R * 8 pieces of 16 bytes at most, 32 per round
+                if (lane + 32 * i < nchunk) qrf_cp_async16(dst + 128 * i, src + 128 * i);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -478,15 +710,29 @@ qrf_direct_kernel(const uint32_t* __restrict__ keys, long long ld_ids, const dou
         __syncwarp();
         s.sv = ring + slot * (R * 32);
         const bool skipped = skip && skip[row];
-        unsigned valid = 0;
-        uint32_t mn = NA, mx = 0u;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int t = r * 32 + lane;
-            const uint32_t x = (!skipped && t < T) ? s.sv[t] : NA;
-            if (x != NA) { valid |= 1u << r; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }   // na.rm = TRUE
+        bool done = false;
+        if (skipped) {                                             // NA row (masked pixel, NA covariate, too few stations)
+            if (out_q) for (int j = lane; j < nprobs; j += 32) out_q[(long long)j * ld_q + row] = na_real();
+            if (lane == 0 && out_iqr_i16) out_iqr_i16[row] = (int16_t)-32767;
+            done = true;
+        } else if (fast) {
+            for (int t = T + lane; t < R * 32; t += 32) s.sv[t] = NA;   // the tail beyond the last tree: NA keys sort last
+            __syncwarp();
+            done = qrf_row_fast<R>(s.sv, s.hist0, reinterpret_cast<uint2*>(s.mem), lane, row, probs, nprobs, dict, out_q, ld_q,
+                                   out_iqr_i16);
+            __syncwarp();
         }
-        qrf_row_finish<R, uint32_t>(s, valid, mn, mx, lane, row, probs, nprobs, dict, out_q, ld_q, out_iqr_i16);
+        if (!done) {                                               // heavy ties next to other values: re-bucketing selection
+            unsigned valid = 0;
+            uint32_t mn = NA, mx = 0u;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int t = r * 32 + lane;
+                const uint32_t x = (t < T) ? s.sv[t] : NA;
+                if (x != NA) { valid |= 1u << r; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }   // na.rm = TRUE
+            }
+            qrf_row_finish<R, uint32_t>(s, valid, mn, mx, lane, row, probs, nprobs, dict, out_q, ld_q, out_iqr_i16);
+        }
         __syncwarp();   // the row's shared memory is free again
         slot = slot + 1 == 3 ? 0 : slot + 1;
     }

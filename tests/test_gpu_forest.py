@@ -164,7 +164,7 @@ def test_quantiles_more_than_1024_trees_is_an_error():
     assert rb.predict(model, rng.normal(size=(10, 2))).predictions.shape == (10,)   # the mean still works
 
 
-@pytest.mark.parametrize("mode", ["coarse", "two_values", "one_outlier", "all_equal"])
+@pytest.mark.parametrize("mode", ["coarse", "two_values", "one_outlier", "all_equal", "zero_inflated", "zero_inflated_close", "top_heavy"])
 def test_quantiles_heavy_ties_rebucketing(mode):
     """More than 32 equal / near-equal samples in one histogram bucket: the re-bucketing loop
     and its all-equal exit (qrf.cuh) against the oracle's sort."""
@@ -178,6 +178,14 @@ def test_quantiles_heavy_ties_rebucketing(mode):
     elif mode == "one_outlier":
         rnv[ok] = 3.5 + 1e-9 * rng.integers(0, 3, size=int(ok.sum()))   # three values 1e-9 apart ...
         rnv[flat.rnv_offsets[0]:flat.rnv_offsets[1]] = 1.0e6             # ... and tree 0 far away
+    elif mode == "zero_inflated":                            # daily precipitation: mostly exact zeros, a continuous tail
+        rnv[ok] = np.where(rng.random(int(ok.sum())) < 0.6, 0.0, np.abs(rnv[ok]))
+    elif mode == "zero_inflated_close":                      # ... whose smallest values share the zeros' bucket
+        u = rng.random(int(ok.sum()))
+        rnv[ok] = np.where(u < 0.5, 0.0, np.where(u < 0.6, 1e-7 * rng.integers(1, 40, size=int(ok.sum())), 50.0 * np.abs(rnv[ok])))
+    elif mode == "top_heavy":                                # the heavy value is the window's largest: falls back to re-bucketing
+        u = rng.random(int(ok.sum()))
+        rnv[ok] = np.where(u < 0.5, 9.0, np.where(u < 0.6, 9.0 - 1e-7 * rng.integers(1, 40, size=int(ok.sum())), -50.0 * np.abs(rnv[ok])))
     else:
         rnv[ok] = -7.25
     flat.random_node_values = rnv

@@ -237,3 +237,63 @@ def test_near_obs_f32_twin():
     np.testing.assert_array_equal(idx.T, ei)
     np.testing.assert_allclose(dist.T, ed, rtol=1e-5)
     np.testing.assert_array_equal(val.T, eo.astype(np.float32))
+
+
+@pytest.mark.parametrize("case", ["lattice_ties", "utm_1km", "clustered", "few_stations_brute", "n40"])
+def test_fp32_mode_neighbours_are_bit_exact(case):
+    """fp32 mode (rfsi_near_obs_f32 / precision="fp32"): fp32 distances only PREFILTER the cell-grid search, every
+    survivor is re-ranked by its exact fp64 distance, so the neighbour indices -- tie order included -- are those of
+    the fp64 search on the same float-representable coordinates; distances within north_star's 1e-5 (in fact they are
+    the fp64 distances rounded to float)."""
+    rng = np.random.default_rng(11)
+    n = 8
+    if case == "lattice_ties":                   # every distance class is shared by several stations
+        g = np.stack(np.meshgrid(np.arange(40.0), np.arange(40.0)), -1).reshape(-1, 2)
+        obs = g[rng.choice(len(g), 700, replace=False)]
+        loc = g
+    elif case == "utm_1km":                      # UTM-sized coordinates: 24-bit floats resolve 0.5 m at 5e6
+        obs = np.column_stack([rng.uniform(4.0e5, 8.0e5, 900), rng.uniform(4.7e6, 5.2e6, 900)])
+        loc = np.column_stack([rng.uniform(4.0e5, 8.0e5, 20000), rng.uniform(4.7e6, 5.2e6, 20000)])
+    elif case == "clustered":                    # dense clusters: many candidates within one float ulp of the k-th best
+        c = rng.uniform(0, 1000, size=(12, 2))
+        obs = (c[rng.integers(0, 12, 1500)] + rng.normal(scale=0.01, size=(1500, 2)))
+        loc = (c[rng.integers(0, 12, 6000)] + rng.normal(scale=0.02, size=(6000, 2)))
+    elif case == "few_stations_brute":           # below the cell-grid threshold: the brute-force kernel, float I/O only
+        obs = rng.uniform(0, 100, size=(87, 2)); loc = rng.uniform(0, 100, size=(5000, 2))
+    else:
+        n = 40
+        obs = rng.uniform(0, 200, size=(500, 2)); loc = synth.lattice(200, 200).astype(np.float64)
+    obs = obs.astype(np.float32).astype(np.float64); loc = loc.astype(np.float32).astype(np.float64)
+    z = rng.normal(size=len(obs)).astype(np.float32).astype(np.float64)
+    df, idx = rb.near_obs(loc, np.column_stack([obs, z]), zcol=2, n_obs=n, return_idx=True, precision="fp32")
+    ed, eo, ei, _ = oracle.near_obs(loc, obs, z, n)
+    np.testing.assert_array_equal(idx, ei)
+    got_d = np.column_stack([df[f"dist{j + 1}"] for j in range(n)]); got_o = np.column_stack([df[f"obs{j + 1}"] for j in range(n)])
+    assert got_d.dtype == np.float32
+    np.testing.assert_array_equal(got_d, ed.astype(np.float32))        # the fp64 distance, rounded once
+    np.testing.assert_allclose(got_d, ed, rtol=1e-5)                    # north_star's fp32 tolerance
+    np.testing.assert_array_equal(got_o, eo.astype(np.float32))
+
+
+def test_fp32_mode_na_and_too_few():
+    """The fp32 entry keeps the fp64 entry's contract: NA coordinates are RFSI_E_NA_INPUT, short lists are NA-filled
+    with a warning, chunked calls equal one call."""
+    import ctypes as C
+    from rfsi_b200 import _lib
+    rng = np.random.default_rng(5)
+    obs = rng.uniform(0, 10, size=(5, 2)).astype(np.float32); z = rng.normal(size=5).astype(np.float32)
+    loc = rng.uniform(0, 10, size=(300, 2)).astype(np.float32)
+    with pytest.warns(UserWarning):
+        df = rb.near_obs(loc, np.column_stack([obs, z]), zcol=2, n_obs=7, precision="fp32")
+    assert np.isnan(df["dist6"]).all() and np.isnan(df["obs7"]).all() and not np.isnan(df["dist4"]).any()
+    bad = loc.copy(); bad[17, 0] = np.nan
+    with pytest.raises(rb.RfsiError) as e:
+        rb.near_obs(bad, np.column_stack([obs, z]), zcol=2, n_obs=2, precision="fp32")
+    assert e.value.code == _lib.RFSI_E_NA_INPUT
+    # many chunks, several staging threads
+    obs = rng.uniform(0, 1000, size=(400, 2)).astype(np.float32); z = rng.normal(size=400).astype(np.float32)
+    loc = rng.uniform(0, 1000, size=(150_000, 2)).astype(np.float32)
+    df, idx = rb.near_obs(loc, np.column_stack([obs, z]), zcol=2, n_obs=5, return_idx=True, precision="fp32")
+    ed, eo, ei, _ = oracle.near_obs(loc.astype(np.float64), obs.astype(np.float64), z.astype(np.float64), 5, kdtree=True, nthreads=8)
+    np.testing.assert_array_equal(idx, ei)
+    np.testing.assert_array_equal(np.column_stack([df[f"dist{j + 1}"] for j in range(5)]), ed.astype(np.float32))
