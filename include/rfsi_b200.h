@@ -88,9 +88,14 @@ int rfsi_near_obs_cols_f64(const double* loc_x, const double* loc_y, int64_t npi
                            int32_t nobs, int32_t n_obs, int32_t rm_dupl,
                            double* const* dist_cols, double* const* obs_cols, int32_t* const* idx_cols, int device);
 
-/* fp32 twin (float buffers): coordinates are widened to fp64 on the device and searched with
- * the fp64 kernels, so indices equal those of the fp64 call on the same coordinates and
- * dist/obs are its results rounded to float (1e-5 relative, north_star's fp32 mode). */
+/* fp32 mode (north_star: "1e-5 in fp32 mode"): float buffers in both directions through the same pinned, chunked
+ * pipeline as the fp64 call (half the PCIe bytes and host copies: the call is 1.3-1.5x faster at simulation.R's
+ * sizes, profiles/r02_i_fp32_mode.txt).  On the device the coordinates are widened exactly; with 128 stations or
+ * more the cell-grid search forms d2 in fp32 first and drops on that value every station that provably cannot enter
+ * or tie with the current list (|d2f - d2| < 2^-22 d2, bound applied with a 2^-20 margin); the survivors are
+ * re-ranked by their exact fp64 d2.  Neighbour indices and their order are therefore bit-identical to the fp64 call
+ * on the same float-representable coordinates; dist/obs are the fp64 results rounded to float (6e-8 relative).
+ * Same status codes as rfsi_near_obs_f64 (RFSI_E_NA_INPUT for NA coordinates, RFSI_W_TOO_FEW_OBS + NA fill). */
 int rfsi_near_obs_f32(const float* loc_x, const float* loc_y, int64_t npix,
                       const float* obs_x, const float* obs_y, const float* obs_z,
                       int32_t nobs, int32_t n_obs, int32_t rm_dupl,

@@ -136,3 +136,36 @@ def test_multi_chunk_multi_daybatch_host_pipeline():
     ref = oracle.predict_fused(flat.as_dict(), case.feature_names, loc_xy=loc, obs_xy=case.obs_xy,
                                obs_z=case.obs_z, n_obs=case.n_obs, kdtree=True, threads=8)
     same_mean(got["mean"][:, sel], ref["mean"])
+
+
+@pytest.mark.parametrize("T", [129, 200, 256, 257, 300, 512])
+def test_quantiles_selected_inside_the_walk(T):
+    """129..512 trees: the main fused kernel selects the quantiles of its own rows after the walk (fused.cuh,
+    8 or 16 keys per lane) and the quantile kernel only finishes what is left -- here the rows of the fallback list
+    (60 % of the stations missing on day 1), masked pixels and a day with too few stations.  Seven
+    quantile levels = three passes of three; the Int16 products come from the same selection."""
+    case = synth.make_case("c4", ndays=4)
+    rng = np.random.default_rng(T)
+    case.obs_z[1, rng.choice(case.obs_z.shape[1], int(0.6 * case.obs_z.shape[1]), replace=False)] = np.nan
+    case.obs_z[3, case.n_obs - 1:] = np.nan                          # fewer valid stations than n.obs: the whole day is NA
+    flat = _forest_for(case, T=T, max_rows=1500)
+    if T == 300:                                                     # heavy ties: a handful of distinct leaf samples
+        rnv = flat.random_node_values.copy(); ok = ~np.isnan(rnv); rnv[ok] = np.round(rnv[ok], 0); flat.random_node_values = rnv
+    model = rb.RangerForest(flat)
+    begin, npix = 120 * case.ncol, 40 * case.ncol
+    loc = case.locations(begin, npix)
+    cov = {k: np.array(v, copy=True) for k, v in case.covariates(loc).items()}
+    mask = (rng.uniform(size=npix) < 0.7).astype(np.uint8)
+    probs = [0.0, 0.1, 0.25, 0.5, 0.75, 0.9, 1.0]
+    with pytest.warns(UserWarning):
+        got = rb.predict_fused(model, obs_xy=case.obs_xy, obs_z=case.obs_z, n_obs=case.n_obs, grid=case.grid, pix_begin=begin,
+                               npix=npix, covariates=cov, quantiles=probs, pix_mask=mask, centi_int16=True)
+    ref = oracle.predict_fused(flat.as_dict(), case.feature_names, loc_xy=loc, obs_xy=case.obs_xy, obs_z=case.obs_z,
+                               n_obs=case.n_obs, covariates=cov, quantiles=probs, kdtree=True, threads=8)
+    ref["mean"][:, mask == 0] = np.nan
+    ref["quantiles"][:, :, mask == 0] = np.nan
+    assert np.isnan(ref["mean"][3]).all() and not np.isnan(ref["mean"][1][mask == 1]).any()
+    same_mean(got["mean"], ref["mean"])
+    np.testing.assert_array_equal(got["quantiles"], ref["quantiles"])            # NaN == NaN here
+    iqr = (ref["quantiles"][-1] - ref["quantiles"][0]) / 2
+    np.testing.assert_array_equal(got["iqr_i16"].ravel(), oracle.centi_int16(iqr.ravel()))
