@@ -1952,21 +1952,6 @@ int kc_extra_default() {
     return v;
 }
 
-// the main walk with the quantile selection inside (fused.cuh): J = 8, no visit counting
-template <int P, int SELR>
-int launch_fused_sel(const FusedParams& fp_in, unsigned grid, int k, cudaStream_t st) {
-    FusedParams fp = fp_in;
-    fp.q.sect_tile_stride = (uint32_t)(P * sizeof(uint32_t));
-    const size_t smem = std::max(fused_smem_bytes<P, true>(fp.F, k, false), fused_sel_bytes<P, SELR>());
-    ProfScope ps(PROF_FUSED, st);
-    auto kern = fused_kernel<P, 8, false, false, true, SELR>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, P, smem, st>>>(fp);
-    count_launch();
-    CU_TRY(cudaGetLastError());
-    return RFSI_OK;
-}
-
 template <int P, int J, bool FALLBACK, bool Q>
 int launch_fused_pj(const FusedParams& fp_in, unsigned grid, int k, bool count, cudaStream_t st) {
     FusedParams fp = fp_in;
@@ -2101,13 +2086,6 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
     // The too-few / fallback counters (counters[2..3]) are kept whenever `counters` is given.
     const bool count = counters != nullptr && count_visits;
     const std::vector<int> cb = tree_chunks(f);
-    // quantiles selected inside the main walk (fused.cuh) when the walk stores the keys themselves and runs as one launch
-    // of the 256-pixel, 8-trees-in-flight kernel; the quantile kernel then only sees the rows left over (fallback list, NA
-    // rows, heavy ties).  RFSI_B200_QRF_FUSED=0: selection stays a kernel of its own (A/B switch, tests).
-    int selr = 0;
-    if (pl.want_q && Q && im.direct_keys && main256 && !count && cb.size() == 2 && forest_J() == 8 &&
-        env_int("RFSI_B200_QRF_FUSED", 1) != 0 && env_int("RFSI_B200_QRF_FAST", 1) != 0)
-        selr = f->ntrees > 512 ? 0 : (f->ntrees > 256 ? 16 : (f->ntrees > 128 ? 8 : 0));
 
     for (int d0 = 0; d0 < a->ndays; d0 += pl.db) {
         const int nd = std::min(pl.db, a->ndays - d0);
@@ -2118,19 +2096,12 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         fp.out_mean_i16 = a->out_mean_i16 ? a->out_mean_i16 + obase : nullptr;
         fp.leaf_ids = leaf_ids; fp.ld_ids = leaf_ids_ld(f->ntrees); fp.row_skip = skip;
         fp.ids_word = leaf_ids_word(im);
-        if (selr) {
-            fp.sel_probs = probs_dev; fp.sel_nprobs = a->nprobs; fp.sel_dict = im.sample_dict;
-            fp.out_q = a->out_q ? a->out_q + obase : nullptr; fp.ld_q = (int64_t)a->ndays * a->npix;
-            fp.out_iqr_i16 = a->out_iqr_i16 ? a->out_iqr_i16 + obase : nullptr;
-        }
         CU_TRY(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int), st));
         const unsigned grid = (unsigned)(ntiles * nd);
         for (size_t c = 0; c + 1 < cb.size(); ++c) {  // one sweep of all tiles per L2-sized forest chunk
             fp.t_begin = cb[c]; fp.t_end = cb[c + 1];
             const int k = a->n_obs + 1;
-            if (selr == 16) RF_TRY((launch_fused_sel<kFusedP, 16>(fp, grid, k, st)));
-            else if (selr == 8) RF_TRY((launch_fused_sel<kFusedP, 8>(fp, grid, k, st)));
-            else if (Q) {
+            if (Q) {
                 if (main256) RF_TRY((launch_fused_p<kFusedP, false, true>(fp, grid, k, count, st)));
                 else RF_TRY((launch_fused_p<kFallbackP, false, true>(fp, grid, k, count, st)));
             } else {

@@ -17,7 +17,6 @@
 #include "common.cuh"
 #include "forest.cuh"
 #include "knn.cuh"
-#include "qrf.cuh"
 
 namespace rfsi {
 
@@ -60,15 +59,7 @@ struct FusedParams {
     uint32_t* leaf_ids;          // [ndays*npix][ld_ids] leaf index per tree (quantile pass; nullable)
     long long ld_ids;
     int ids_word;                // sector image: word of the leaf block stored into leaf_ids (forest.cuh)
-    unsigned char* row_skip;     // [ndays*npix] 0 = the quantile kernel selects this row, 1 = its outputs are NA, 2 = done here
-    // in-kernel quantile selection (SELR > 0): after its walk a warp selects the quantiles of its own 32 rows from the key
-    // rows it has just written, while the other CTAs of the SM are still walking
-    const double* sel_probs;     // device; nullptr = selection stays with the quantile kernel
-    int sel_nprobs;
-    const double* sel_dict;
-    double* out_q;               // [nprobs][ld_q], row index as for out_mean
-    long long ld_q;
-    int16_t* out_iqr_i16;
+    unsigned char* row_skip;     // [ndays*npix]
     // fallback list
     int2* fb_list;
     unsigned int* fb_count;
@@ -120,70 +111,6 @@ __host__ __device__ constexpr size_t fused_smem_bytes(int F, int k, bool fallbac
     return fused_feature_bytes<P, Q>(F) + (fallback ? (size_t)k * P * (sizeof(double) + sizeof(int32_t)) : 0);
 }
 
-// ---- in-kernel quantile selection ---------------------------------------------------------------------------------
-// The walk is bound by the L1 data stage with half of the issue slots idle (profiles/r02_e), the quantile selection is
-// bound by issue slots (profiles/r02_i): run in the same kernel, a CTA that has finished its trees selects while the
-// other resident CTAs walk, and the selection disappears into the walk's idle issue slots instead of being a second
-// kernel that owns the machine.  After the walk the rank tile is dead: each warp takes a slice of it for two key-row
-// buffers (the next row arrives by cp.async while this one is selected), the histogram table and the member buffer,
-// and goes through the (up to) 32 rows its lanes have just written -- each a contiguous run of T keys, read back from L2.
-// A row whose windows are too heavy for qrf_row_fast is left to the quantile kernel (row_skip = 0), which runs after
-// this kernel anyway for the rows of the fallback list.
-template <int SELR>
-__host__ __device__ constexpr size_t fused_sel_warp_bytes() { return (size_t)2 * SELR * 32 * 4 + 256 * 4 + 32 * 8; }
-template <int P, int SELR>
-__host__ __device__ constexpr size_t fused_sel_bytes() { return SELR > 0 ? (P / 32) * fused_sel_warp_bytes<SELR>() : 0; }
-
-template <int SELR>
-__device__ __forceinline__ void fused_select_rows(const FusedParams& a, unsigned char* smem_raw, long long row, bool walked)
-{
-    constexpr uint32_t NA = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char* base = smem_raw + (size_t)wib * fused_sel_warp_bytes<SELR>();
-    uint32_t* ring = reinterpret_cast<uint32_t*>(base);
-    int* tab = reinterpret_cast<int*>(base + (size_t)2 * SELR * 32 * 4);
-    uint2* mem = reinterpret_cast<uint2*>(tab + 256);
-    unsigned todo = __ballot_sync(0xffffffffu, walked);
-    if (!todo) return;
-    const int nchunk = (int)(a.ld_ids >> 2);                         // 16-byte pieces of one key row
-    const unsigned rlo = (unsigned)row, rhi = (unsigned)((unsigned long long)row >> 32);
-    auto row_of = [&](int src) {
-        return (long long)(((unsigned long long)__shfl_sync(0xffffffffu, rhi, src) << 32) | __shfl_sync(0xffffffffu, rlo, src));
-    };
-    auto fetch = [&](long long rw, int slot) {
-        const uint32_t* src = a.leaf_ids + rw * a.ld_ids + 4 * lane;
-        uint32_t* dst = ring + slot * (SELR * 32) + 4 * lane;
-#pragma unroll
-        for (int i = 0; i < (SELR + 3) / 4; ++i)
-            if (lane + 32 * i < nchunk) qrf_cp_async16(dst + 128 * i, src + 128 * i);
-    };
-    int cur = __ffs(todo) - 1;
-    todo &= todo - 1u;
-    long long rcur = row_of(cur);
-    fetch(rcur, 0);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    int slot = 0;
-    for (;;) {
-        const int nxt = todo ? __ffs(todo) - 1 : -1;
-        todo &= todo - 1u;
-        long long rnxt = 0;
-        if (nxt >= 0) { rnxt = row_of(nxt); fetch(rnxt, slot ^ 1); }
-        asm volatile("cp.async.commit_group;" ::: "memory");          // always: the wait below counts groups
-        asm volatile("cp.async.wait_group 1;" ::: "memory");          // this row's keys have landed
-        __syncwarp();
-        uint32_t* sv = ring + slot * (SELR * 32);
-        for (int t = a.T + lane; t < SELR * 32; t += 32) sv[t] = NA;  // the tail beyond the last tree: NA keys sort last
-        __syncwarp();
-        const bool done = qrf_row_fast<SELR>(sv, tab, mem, lane, rcur, a.sel_probs, a.sel_nprobs, a.sel_dict, a.out_q, a.ld_q,
-                                             a.out_iqr_i16);
-        if (lane == 0) a.row_skip[rcur] = done ? 2 : 0;
-        __syncwarp();
-        if (nxt < 0) break;
-        cur = nxt; rcur = rnxt; slot ^= 1;
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-}
-
 // Resident CTAs per SM the register budget is cut for (rank images).  Measured on the bench forest (profiles/r02_b):
 // 3 x 256 threads at 80 registers 129.6 M pixel-days/s, 4 x 256 at 64 registers 127.5 M (register moves and the
 // re-materialised shared-memory base go away, 92 KB instead of 60 KB of L1), 2 x 256 at 96 registers 106.9 M; more
@@ -197,7 +124,7 @@ __host__ __device__ constexpr int fused_min_blocks_q() {
 #endif
 }
 
-template <int P, int J, bool COUNT, bool FALLBACK, bool Q, int SELR = 0>
+template <int P, int J, bool COUNT, bool FALLBACK, bool Q>
 __global__ void __launch_bounds__(P, Q ? fused_min_blocks_q<P, J>() : ((P * (20 + 6 * J) <= 32768) ? 2 : 1))
 fused_kernel(const __grid_constant__ FusedParams a)
 {
@@ -325,7 +252,6 @@ fused_kernel(const __grid_constant__ FusedParams a)
     }
 
     unsigned nvisit = 0;
-    bool walked = false;         // SELR: this thread's key row is complete and waits for its quantiles
     if (ok) {
         ForestOut o;
         o.mean = nullptr;
@@ -353,15 +279,10 @@ fused_kernel(const __grid_constant__ FusedParams a)
             const double mean = sum / (double)a.T;
             if (a.out_mean) a.out_mean[row] = mean;
             if (a.out_mean_i16) a.out_mean_i16[row] = centi_i16(mean);
-            if (SELR > 0) walked = true;
-            else if (a.row_skip) a.row_skip[row] = 0;
+            if (a.row_skip) a.row_skip[row] = 0;
         } else {
             a.acc[row] = sum;
         }
-    }
-    if constexpr (SELR > 0) {
-        __syncthreads();         // every warp of the CTA is done with the rank tile; the key rows are visible to the CTA
-        fused_select_rows<SELR>(a, smem_raw, row, walked);
     }
     if (COUNT && a.counters) {
         const unsigned long long w = warp_sum_u64(nvisit);

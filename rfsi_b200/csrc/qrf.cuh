@@ -709,12 +709,9 @@ qrf_direct_kernel(const uint32_t* __restrict__ keys, long long ld_ids, const dou
         asm volatile("cp.async.wait_group 2;" ::: "memory");       // this row's group has landed
         __syncwarp();
         s.sv = ring + slot * (R * 32);
-        const unsigned char sk = skip ? skip[row] : (unsigned char)0;
-        const bool skipped = sk != 0;
+        const bool skipped = skip && skip[row];
         bool done = false;
-        if (sk == 2) {                                             // selected inside the fused kernel already (fused.cuh)
-            done = true;
-        } else if (skipped) {                                      // NA row (masked pixel, NA covariate, too few stations)
+        if (skipped) {                                             // NA row (masked pixel, NA covariate, too few stations)
             if (out_q) for (int j = lane; j < nprobs; j += 32) out_q[(long long)j * ld_q + row] = na_real();
             if (lane == 0 && out_iqr_i16) out_iqr_i16[row] = (int16_t)-32767;
             done = true;

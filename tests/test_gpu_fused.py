@@ -139,11 +139,10 @@ def test_multi_chunk_multi_daybatch_host_pipeline():
 
 
 @pytest.mark.parametrize("T", [129, 200, 256, 257, 300, 512])
-def test_quantiles_selected_inside_the_walk(T):
-    """129..512 trees: the main fused kernel selects the quantiles of its own rows after the walk (fused.cuh,
-    8 or 16 keys per lane) and the quantile kernel only finishes what is left -- here the rows of the fallback list
-    (60 % of the stations missing on day 1), masked pixels and a day with too few stations.  Seven
-    quantile levels = three passes of three; the Int16 products come from the same selection."""
+def test_quantile_products_for_129_to_512_trees(T):
+    """129..512 trees (8 or 16 keys per lane in the quantile kernel, both sides of the 256 boundary) through the fused call:
+    rows of the fallback list (60 % of the stations missing on day 1), masked pixels and a day with too few stations.
+    Seven quantile levels = three passes of three in the one-pass selection; the Int16 products come from the same selection."""
     case = synth.make_case("c4", ndays=4)
     rng = np.random.default_rng(T)
     case.obs_z[1, rng.choice(case.obs_z.shape[1], int(0.6 * case.obs_z.shape[1]), replace=False)] = np.nan
