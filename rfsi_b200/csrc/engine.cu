@@ -1913,6 +1913,13 @@ int validate_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a) {
     return RFSI_OK;
 }
 
+// bytes of quantile key scratch one fused launch may use (RFSI_B200_QRF_SCRATCH_MB; read once: the plan must not change
+// between rfsi_dev_fused_workspace_bytes and the call)
+int64_t qrf_scratch_budget() {
+    static const int64_t mb = std::max(64, env_int("RFSI_B200_QRF_SCRATCH_MB", 8192));
+    return mb << 20;
+}
+
 FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_extra) {
     FusedPlan pl;
     const int k = a->n_obs + 1;
@@ -1920,9 +1927,9 @@ FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_
     pl.want_q = a->out_q || a->out_iqr_i16;
     const int64_t npix = std::max<int64_t>(a->npix, 1);
     int db = std::min(a->ndays, 16);
-    if (pl.want_q) {
+    if (pl.want_q) {   // key scratch: 4 bytes per (pixel-day, tree); days per launch within the scratch budget
         const int64_t per_day = npix * leaf_ids_ld(f->ntrees) * 4;
-        db = (int)std::max<int64_t>(1, std::min<int64_t>(db, (int64_t(1) << 30) / per_day));
+        db = (int)std::max<int64_t>(1, std::min<int64_t>(db, qrf_scratch_budget() / per_day));
     }
     // keep the 1-D grid below 2^31 CTAs
     while (db > 1 && ((npix + kFusedP - 1) / kFusedP + 64) * db > (int64_t)0x7fffffff) --db;
@@ -2197,7 +2204,7 @@ int host_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int device, i
     // pixel chunking: bound per-chunk device memory
     const bool want_q = a->out_q || a->out_iqr_i16;
     int64_t chunk = std::max<int64_t>(4096, env_int("RFSI_B200_FUSED_CHUNK", 1 << 20));
-    if (want_q) chunk = std::max<int64_t>(4096, std::min<int64_t>(chunk, (int64_t(1) << 30) / (8 * (int64_t)f->ntrees)));
+    if (want_q) chunk = std::max<int64_t>(4096, std::min<int64_t>(chunk, qrf_scratch_budget() / (8 * (int64_t)f->ntrees)));
     chunk = std::min(chunk, band);
     // whole raster rows per chunk keep the 2-D tiles, whole tile rows (16 raster rows) keep every tile full: a chunk of
     // 104 rows would leave the lower half of its seventh tile row idle
