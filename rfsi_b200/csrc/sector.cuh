@@ -46,11 +46,6 @@
 #ifndef RFSI_SECT_WIDE
 #define RFSI_SECT_WIDE 0
 #endif
-// experiment (tools/build_variant.sh pred1 -DRFSI_SECT_PRED=1): a finished chain issues no loads at all instead of idling on
-// block 0 -- 1: the three global loads of a block visit are predicated, 2: the three shared-memory loads as well
-#ifndef RFSI_SECT_PRED
-#define RFSI_SECT_PRED 0
-#endif
 
 #if defined(RFSI_SECTOR_HOST_CHECK)
 // tests/tools/sector_host.cpp compiles the very same loop for the host (no CUDA headers)
@@ -121,39 +116,6 @@ RFSI_SECT_DEV const uint32_t* sector_block(const SectorView& q, const uint32_t* 
 #endif
 }
 
-// ---- RFSI_SECT_PRED: loads of a chain that is still walking (bb >= 0); a finished chain keeps what its registers held after its
-// last real visit -- the visit of its leaf block: w0 = flag | own index, every node word it read a pass-through word -- so the
-// arithmetic of the visit reproduces bb unchanged and nothing is loaded.  One setp per load (a thread has 7 predicate registers
-// for 8 chains: they cannot stay live across the visit).
-RFSI_SECT_DEV void sector_ld2_alive(uint32_t bb, const uint32_t* p, uint2& v) {
-#if defined(RFSI_SECTOR_HOST_CHECK)
-    if ((int32_t)bb >= 0) { v.x = p[0]; v.y = p[1]; }
-#else
-    asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %2, 0;\n\t@q ld.global.nc.v2.u32 {%0, %1}, [%3];\n\t}" : "+r"(v.x), "+r"(v.y) : "r"(bb), "l"(p));
-#endif
-}
-RFSI_SECT_DEV void sector_ld1_alive(uint32_t bb, const uint32_t* p, uint32_t& v) {
-#if defined(RFSI_SECTOR_HOST_CHECK)
-    if ((int32_t)bb >= 0) v = *p;
-#else
-    asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %1, 0;\n\t@q ld.global.nc.u32 %0, [%2];\n\t}" : "+r"(v) : "r"(bb), "l"(p));
-#endif
-}
-// rank of the pixel's feature `w & 0xFF`: rsb = this thread's column of the tile
-RFSI_SECT_DEV void sector_rank_alive(uint32_t bb, const char* rsb, uint32_t off, uint32_t& xs) {
-#if defined(RFSI_SECTOR_HOST_CHECK)
-    if ((int32_t)bb >= 0) xs = *reinterpret_cast<const uint32_t*>(rsb + off);
-#elif RFSI_SECT_PRED >= 2
-    asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %1, 0;\n\t@q ld.shared.u32 %0, [%2];\n\t}"
-        : "+r"(xs) : "r"(bb), "r"((uint32_t)__cvta_generic_to_shared(rsb) + off));
-#else
-    xs = *reinterpret_cast<const uint32_t*>(rsb + off);
-#endif
-}
-RFSI_SECT_DEV const uint32_t* sector_block_raw(const SectorView& q, const uint32_t* words, uint32_t bb) {   // no clamp: never dereferenced when finished
-    return reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(words) + (size_t)bb * q.block_bytes);
-}
-
 // Walk trees [t_begin, t_end) for the pixel whose pre-shifted ranks are rs[f * P] (feature-major tile in shared
 // memory), J trees in lock step.  `sum` carries the tree-order partial sum of the trees before; the updated sum is
 // returned.  After each group of J trees `sink(t0, remaining, leaf_block[J])` sees the leaf blocks the trees
@@ -168,56 +130,6 @@ RFSI_SECT_DEV double traverse_s(const SectorView& q, int t_begin, int t_end, dou
         uint32_t bb[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) bb[j] = (t0 + j < t_end) ? __ldg(q.root + t0 + j) : kSLeafFlag;   // no tree: finished, idles on block 0
-#if RFSI_SECT_PRED
-        uint2 w01[J];
-        uint32_t w2[J], w3[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) { w01[j].x = kSLeafFlag; w01[j].y = kSPassWord; w2[j] = w3[j] = kSPassWord; }
-        for (;;) {
-            const uint32_t* blk[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                blk[j] = sector_block_raw(q, words, bb[j]);
-                sector_ld2_alive(bb[j], blk[j], w01[j]);                     // w0 and the level-1 node: one request
-            }
-            uint32_t fin = kSLeafFlag;
-#pragma unroll
-            for (int j = 0; j < J; ++j) fin &= bb[j] | w01[j].x;
-            if (fin) {                                                        // every chain finished or on its leaf
-#pragma unroll
-                for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w01[j].x);
-                break;
-            }
-            uint32_t h[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                uint32_t xs = 0u;                                            // a pass-through word never carries, whatever xs
-                sector_rank_alive(bb[j], rsb, (w01[j].y & 0xFFu) * q.tile_stride, xs);
-                h[j] = sector_step(1u, w01[j].y, xs);
-                if (COUNT) nvisit += ((int32_t)bb[j] >= 0 && w01[j].y != kSPassWord) ? 1u : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) sector_ld1_alive(bb[j], blk[j] + h[j], w2[j]);
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                uint32_t xs = 0u;                                            // a pass-through word never carries, whatever xs
-                sector_rank_alive(bb[j], rsb, (w2[j] & 0xFFu) * q.tile_stride, xs);
-                h[j] = sector_step(h[j], w2[j], xs);
-                if (COUNT) nvisit += ((int32_t)bb[j] >= 0 && w2[j] != kSPassWord) ? 1u : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) sector_ld1_alive(bb[j], blk[j] + h[j], w3[j]);
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                uint32_t xs = 0u;                                            // a pass-through word never carries, whatever xs
-                sector_rank_alive(bb[j], rsb, (w3[j] & 0xFFu) * q.tile_stride, xs);
-                h[j] = sector_step(h[j], w3[j], xs);
-                if (COUNT) nvisit += ((int32_t)bb[j] >= 0 && w3[j] != kSPassWord) ? 1u : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w01[j].x + (h[j] - 8u));   // finished: flag | index + 0
-        }
-#else
         for (;;) {
 #if RFSI_SECT_WIDE
             // one 128-bit request brings w0 and the nodes of levels 1 and 2; level 3 is one more 32-bit load
@@ -302,7 +214,6 @@ RFSI_SECT_DEV double traverse_s(const SectorView& q, int t_begin, int t_end, dou
             for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w01[j].x + (h[j] - 8u));   // implicit child: no exit load
 #endif
         }
-#endif   // RFSI_SECT_PRED
 #pragma unroll
         for (int j = 0; j < J; ++j) bb[j] &= ~kSLeafFlag;
 #pragma unroll

@@ -17,13 +17,12 @@ from rfsi_b200.forest import FlatForest
 ROOT = Path(__file__).resolve().parents[1]
 
 
-@pytest.fixture(scope="module", params=["-DRFSI_SECT_WIDE=0", "-DRFSI_SECT_WIDE=1", "-DRFSI_SECT_PRED=2"], ids=["ldg64", "ldg128", "pred"])
+@pytest.fixture(scope="module", params=[0, 1], ids=["ldg64", "ldg128"])
 def lib(request, tmp_path_factory):
-    # the forms of the block visit (sector.cuh): 64-bit first load + two 32-bit loads (product), 128-bit + one (RFSI_SECT_WIDE),
-    # and the product form with the loads of finished chains switched off instead of idling on block 0 (RFSI_SECT_PRED)
-    so = tmp_path_factory.mktemp("sector") / f"libsector_host{request.param_index}.so"
+    # both forms of the block visit (sector.cuh: RFSI_SECT_WIDE): 64-bit first load + two 32-bit loads, or 128-bit + one
+    so = tmp_path_factory.mktemp("sector") / f"libsector_host{request.param}.so"
     subprocess.run(["g++", "-O2", "-fPIC", "-std=c++17", "-shared", "-Wall", "-Wno-unknown-pragmas",
-                    request.param, "-o", str(so), str(ROOT / "tests" / "tools" / "sector_host.cpp")], check=True)
+                    f"-DRFSI_SECT_WIDE={request.param}", "-o", str(so), str(ROOT / "tests" / "tools" / "sector_host.cpp")], check=True)
     L = C.CDLL(str(so))
     L.sh_stats.restype = C.c_int64
     L.sh_stats.argtypes = [C.c_void_p, C.c_int]
