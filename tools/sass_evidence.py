@@ -100,13 +100,32 @@ def main():
         for l in L:
             if re.search(r"STG\.E\..*256|STG.*EF", l):
                 f.write(l + "\n")
-    qk = [k for k in fn if "qrf_quantile_kernelILi16EjLb1" in k]
+    qk = [k for k in fn if "qrf_direct_kernelILi16E" in k]
     with open(OUT / "r02_sass_qrf_direct.txt", "w") as f:
-        f.write(f"# {qk[0] if qk else '?'}\n# DIRECT form of the quantile kernel: the only global loads left are the id rows (LDGSTS = cp.async),\n"
-                "# the skip bytes and the two dictionary look-ups per quantile; REDUX for warp min/max\n")
+        f.write(f"# {qk[0] if qk else '?'}\n# DIRECT form of the quantile kernel with the one-pass selection (qrf.cuh: qrf_row_fast): key rows arrive by\n"
+                "# cp.async (LDGSTS), the histogram is 16 shared-memory atomics per lane (ATOMS.POPC.INC: lanes on the same bucket are\n"
+                "# combined), warp minimum / maximum / counts and the peel ranking are REDUX / CREDUX, the only global loads left are the\n"
+                "# skip bytes and the two dictionary look-ups per quantile.\n")
         if qk:
-            c = collections.Counter(opcode(l) for l in fn[qk[0]])
-            f.write("# " + ", ".join(f"{k} {v}" for k, v in c.most_common() if re.match(r"LDG|LDGSTS|REDUX|ATOMS|LDS|STS|STG", k)) + "\n")
+            Lq = fn[qk[0]]
+            c = collections.Counter(opcode(l) for l in Lq)
+            f.write("# whole kernel: " + ", ".join(f"{k} {v}" for k, v in c.most_common()
+                                                     if re.match(r"LDG|LDGSTS|REDUX|CREDUX|ATOMS|LDS|STS|STG|VOTE|IMAD.HI|VIMNMX3", k)) + "\n#\n")
+            # the marking pass: the run of instructions between the first table look-up after the last ATOMS and the next REDUX
+            last_atoms = [i for i, l in enumerate(Lq) if "ATOMS" in l][15]   # the 16th: end of the fast path's histogram (converged-warp copy)
+            # straight-line code of the fast path after the histogram: scan, targets, marking pass, up to the first window's REDUX.SUM
+            stop = next(i for i in range(last_atoms, len(Lq)) if "REDUX.SUM" in Lq[i])
+            body = Lq[last_atoms + 1:stop + 1]
+            cm = collections.Counter(opcode(l) for l in body)
+            f.write(f"# after the histogram: warp scan of the 256 buckets, rank-interval table, the three target ranks and the marking pass\n"
+                    f"# (16 elements x 3 quantiles x [ISETP.GE, ISETP.LE.AND, predicated add]): {len(body)} instructions, straight line\n")
+            f.write("# mix: " + ", ".join(f"{k} {v}" for k, v in cm.most_common(12)) + "\n")
+            f.write("\n".join(body) + "\n#\n# the peel loop of a window (one distinct value per iteration):\n")
+            for a2, b2 in loops(Lq):
+                ops = [opcode(l) for l in Lq[a2:b2 + 1]]
+                if any(o.startswith("CREDUX.MIN") for o in ops) and b2 - a2 < 24 and "VOTE.ANY" in ops:
+                    f.write("\n".join(Lq[a2:b2 + 1]) + "\n")
+                    break
     for p in sorted(OUT.glob("r02_sass_*.txt")):
         print(p.name, sum(1 for _ in open(p)), "lines")
 
