@@ -434,17 +434,21 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
 //   * per quantile the WINDOW = the elements whose bucket's rank interval meets [k, k+1] (k = floor(index) - 1): the bucket
 //     holding rank k and, when k is that bucket's last rank, the next non-empty bucket.  The three windows of a group of
 //     three quantiles are marked in ONE pass over the 16 elements of a lane (no per-quantile bucket search, no bucket
-//     matching); a window's members (a handful) are compacted into shared memory with the first rank of their bucket
-//     and ranked against each other: global rank = smallest first rank in the window + local rank;
+//     matching); a window's members (a handful) are compacted into shared memory, one per lane, with the first rank of
+//     their bucket, and the member of rank k is found by PEELING the window's distinct values from below with warp
+//     reductions (REDUX.MIN, a tie group per step): rank inside the window = k - smallest first rank in the window;
+//   * a window with more than 32 members (ties: many trees returning the same training sample, zero-inflated data) is
+//     peeled the same way on the uncompacted row, up to 8 distinct values;
 //   * lanes 0..2 finish the three quantiles side by side (R's (1-h)*x[lo] + h*x[hi], two dictionary look-ups each).
-// Returns false -- nothing written -- when a window has more than 32 members that are not all equal (heavy ties next to
-// other values): the caller then runs qrf_row_finish, which re-buckets.
+// Returns false -- nothing written -- only when a heavy window does not resolve within 8 distinct values: the caller then
+// runs qrf_row_finish, which re-buckets.  1167 warp instructions per row of 500 keys against 1742 for qrf_row_finish
+// (profiles/r02_i_qrf_fast_ncu_full.txt, r02_sass_qrf_direct.txt).
 constexpr int kQrfGroup = 3;   // quantiles marked per pass over the row
 
 // window bit of element r for rank k: bucket interval [first, end) meets {k, k+1}  <=>  first <= k+1 && end > k.
 // iv = first | end << 16, iv_lo = iv << 16 = first << 16, kk = (k+1) << 16: end > k <=> iv >= kk; first <= k+1 <=> iv_lo <= kk.
 // Three instructions: written in PTX because the compiler otherwise collects all 48 predicates of a row first and
-// spills them (profiles/r02_h_sass_qrf_fast.txt).
+// spills them into a general register (seen in the SASS of the first version).
 __device__ __forceinline__ void qrf_mark(unsigned& w, uint32_t iv, uint32_t iv_lo, uint32_t kk, uint32_t bit) {
     asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %1, %3;\n\tsetp.le.and.u32 p, %2, %3, p;\n\t@p or.b32 %0, %0, %4;\n\t}"
         : "+r"(w) : "r"(iv), "r"(iv_lo), "r"(kk), "r"(bit));
