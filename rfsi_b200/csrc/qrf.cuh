@@ -423,39 +423,30 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
 }
 
 
-// ---- one row of integer keys, all quantiles in one pass over the row (direct form) ---------------------------------
+// ---- one row of integer keys: a counting sort by bucket, then a handful of keys per quantile (direct form) -----------
 // Same selection idea as qrf_row_finish (monotone buckets between the row's min and max, exact ranking inside the few
-// buckets that matter), restated for 4-byte keys so that a row costs about half the instructions (profiles/r02_h):
+// buckets that matter), restated for 4-byte keys so that a row costs well under half the instructions:
 //   * NA keys (0xFFFFFFFF) are simply the largest keys: ranks below the number of valid samples never reach them, so
 //     there is no validity mask; the row's tail beyond T is filled with NA by the caller;
 //   * bucket(x) = min(255, umulhi(x - min, mult)), mult <= (2^40 - 1) / (max - min + 1): two integer instructions, monotone;
-//   * one histogram, one warp scan; the table is rewritten in place as tab[b] = first rank of bucket b | (one past its last
-//     rank) << 16, so every element learns the rank interval of its own bucket with one shared-memory load;
-//   * per quantile the WINDOW = the elements whose bucket's rank interval meets [k, k+1] (k = floor(index) - 1): the bucket
-//     holding rank k and, when k is that bucket's last rank, the next non-empty bucket.  The three windows of a group of
-//     three quantiles are marked in ONE pass over the 16 elements of a lane (no per-quantile bucket search, no bucket
-//     matching); a window's members (a handful) are compacted into shared memory, one per lane, with the first rank of
-//     their bucket, and the member of rank k is found by PEELING the window's distinct values from below with warp
-//     reductions (REDUX.MIN, a tie group per step): rank inside the window = k - smallest first rank in the window;
+//   * one histogram whose shared-memory atomics RETURN each key's arrival number inside its bucket, one warp scan that
+//     turns the table into tab[b] = first rank | (one past the last rank) << 16, and every key is PLACED at
+//     srt[first rank of its bucket + arrival number] -- the row is rewritten in place, grouped by bucket, buckets in rank
+//     order (a counting sort; order inside a bucket is arbitrary; one round of atomics, the placement is a table load);
+//   * rank k then sits somewhere in the bucket of srt[k]: one broadcast load of that key, its bucket, its table entry give
+//     the bucket's rank interval [first, end); when k is its last rank, the bucket of srt[end] is appended (rank k+1 lives
+//     there).  That contiguous WINDOW srt[first .. end2) -- a handful of keys -- goes one key per lane, and the member of
+//     rank k is found by PEELING the window's distinct values from below with warp reductions (REDUX.MIN, a tie group per
+//     step): no per-element marking, no compaction;
 //   * a window with more than 32 members (ties: many trees returning the same training sample, zero-inflated data) is
-//     peeled the same way on the uncompacted row, up to 8 distinct values;
-//   * lanes 0..2 finish the three quantiles side by side (R's (1-h)*x[lo] + h*x[hi], two dictionary look-ups each).
+//     peeled the same way with up to R keys per lane, at most 8 distinct values;
+//   * lanes 0..2 finish three quantiles side by side (R's (1-h)*x[lo] + h*x[hi], two dictionary look-ups each).
 // Returns false -- nothing written -- only when a heavy window does not resolve within 8 distinct values: the caller then
-// runs qrf_row_finish, which re-buckets.  1167 warp instructions per row of 500 keys against 1742 for qrf_row_finish
-// (profiles/r02_i_qrf_fast_ncu_full.txt, r02_sass_qrf_direct.txt).
-constexpr int kQrfGroup = 3;   // quantiles marked per pass over the row
-
-// window bit of element r for rank k: bucket interval [first, end) meets {k, k+1}  <=>  first <= k+1 && end > k.
-// iv = first | end << 16, iv_lo = iv << 16 = first << 16, kk = (k+1) << 16: end > k <=> iv >= kk; first <= k+1 <=> iv_lo <= kk.
-// Three instructions: written in PTX because the compiler otherwise collects all 48 predicates of a row first and
-// spills them into a general register (seen in the SASS of the first version).
-__device__ __forceinline__ void qrf_mark(unsigned& w, uint32_t iv, uint32_t iv_lo, uint32_t kk, uint32_t bit) {
-    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %1, %3;\n\tsetp.le.and.u32 p, %2, %3, p;\n\t@p or.b32 %0, %0, %4;\n\t}"
-        : "+r"(w) : "r"(iv), "r"(iv_lo), "r"(kk), "r"(bit));
-}
+// runs qrf_row_finish on the (permuted) row, which re-buckets.  profiles/r02_q_*.
+constexpr int kQrfGroup = 3;   // quantiles finished side by side
 
 template <int R>
-__device__ __forceinline__ bool qrf_row_fast(const uint32_t* sv, int* tab, uint2* mem, int lane, long long row,
+__device__ __forceinline__ bool qrf_row_fast(uint32_t* sv, int* tab, int lane, long long row,
                                              const double* __restrict__ probs, int nprobs, const double* __restrict__ dict,
                                              double* __restrict__ out_q, long long ld_q, int16_t* __restrict__ out_iqr_i16)
 {
@@ -489,18 +480,18 @@ __device__ __forceinline__ bool qrf_row_fast(const uint32_t* sv, int* tab, uint2
         if (out_q) for (int j = lane; j < nprobs; j += 32) out_q[(long long)j * ld_q + row] = q;
         qfirst = qlast = q;
     } else {
-        // ---- histogram of 256 monotone buckets, scanned into rank intervals ------------------------
+        // ---- histogram of 256 monotone buckets, scanned into first ranks ---------------------------
         const float fr = __uint2float_ru(mx - mn + 1u);                              // >= 2
         const uint32_t mult = __float2uint_rz(__fdividef(1099507433472.0f, fr));     // 2^40 (1 - 2^-18) / (range + 1), saturating
+        auto bucket_of = [&](uint32_t key) { return min(__umulhi(key - mn, mult), 255u); };   // the clamp only ever acts on NA keys
         reinterpret_cast<int4*>(tab)[lane * 2] = make_int4(0, 0, 0, 0);
         reinterpret_cast<int4*>(tab)[lane * 2 + 1] = make_int4(0, 0, 0, 0);
         __syncwarp();
-        const int* slot[R];                                                           // &tab[bucket of element r]
+        uint32_t bo[R];                                                               // bucket of element r | its arrival number in that bucket << 8
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            slot[r] = tab + min(__umulhi(x[r] - mn, mult), 255u);                    // the clamp only ever acts on NA keys
-            atomicAdd(const_cast<int*>(slot[r]), 1);
-        }
+        for (int r = 0; r < R; ++r) bo[r] = bucket_of(x[r]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) bo[r] |= (uint32_t)atomicAdd(tab + bo[r], 1) << 8;
         __syncwarp();
         {
             const int4 h0 = reinterpret_cast<const int4*>(tab)[lane * 2];
@@ -514,6 +505,7 @@ __device__ __forceinline__ bool qrf_row_fast(const uint32_t* sv, int* tab, uint2
                 if (lane >= o) incl += t;
             }
             const int e = incl - s8;                                                  // elements in the buckets of lower lanes
+            // first rank | (one past the last rank) << 16
             const int4 p0 = make_int4(e | ((e + s1) << 16), (e + s1) | ((e + s2) << 16), (e + s2) | ((e + s3) << 16),
                                       (e + s3) | ((e + s4) << 16));
             const int4 p1 = make_int4((e + s4) | ((e + s5) << 16), (e + s5) | ((e + s6) << 16), (e + s6) | ((e + s7) << 16),
@@ -523,93 +515,37 @@ __device__ __forceinline__ bool qrf_row_fast(const uint32_t* sv, int* tab, uint2
             reinterpret_cast<int4*>(tab)[lane * 2 + 1] = p1;
         }
         __syncwarp();
+        // ---- place every key at first rank of its bucket + arrival number: the row in place, grouped by bucket, buckets in
+        //      rank order (every lane holds its keys in registers; the arrival numbers came back from the histogram atomics) ----
+#pragma unroll
+        for (int r = 0; r < R; ++r) bo[r] = ((uint32_t)tab[bo[r] & 0xFFu] & 0xFFFFu) + (bo[r] >> 8);   // all loads before the first store
+#pragma unroll
+        for (int r = 0; r < R; ++r) sv[bo[r]] = x[r];
+        __syncwarp();
 
-        const unsigned lt = (1u << lane) - 1u;
         for (int j0 = 0; j0 < nprobs; j0 += kQrfGroup) {
             // ---- lane j < 3: quantile j0 + j.  R: index = 1 + (n-1)*p in two roundings, lo = floor, hi = ceil --
             const int jq = min(j0 + min(lane, kQrfGroup - 1), nprobs - 1);
             const double index = __dadd_rn(1.0, __dmul_rn((double)(m - 1), probs[jq]));
             const double lo = floor(index);
             const int k_mine = (int)lo - 1;                                           // 0-based rank of x[lo]
-            const int k0 = __shfl_sync(0xffffffffu, k_mine, 0);
-            const int k1 = __shfl_sync(0xffffffffu, k_mine, 1);
-            const int k2 = __shfl_sync(0xffffffffu, k_mine, 2);
-            // ---- mark the three windows in one pass over this lane's elements --------------------
-            const uint32_t kk0 = (uint32_t)(k0 + 1) << 16, kk1 = (uint32_t)(k1 + 1) << 16, kk2 = (uint32_t)(k2 + 1) << 16;
-            unsigned w0 = 0, w1 = 0, w2 = 0;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t iv = (uint32_t)*slot[r];
-                const uint32_t iv_lo = iv << 16;
-                qrf_mark(w0, iv, iv_lo, kk0, 1u << r);
-                qrf_mark(w1, iv, iv_lo, kk1, 1u << r);
-                qrf_mark(w2, iv, iv_lo, kk2, 1u << r);
-            }
             uint32_t klo_mine = 0, khi_mine = 0;
 #pragma unroll
             for (int g = 0; g < kQrfGroup; ++g) {
-                unsigned wm = g == 0 ? w0 : (g == 1 ? w1 : w2);
-                const int k = g == 0 ? k0 : (g == 1 ? k1 : k2);
                 if (g > 0 && j0 + g >= nprobs) break;                                 // uniform
-                const int cnt = (int)__reduce_add_sync(0xffffffffu, (unsigned)__popc(wm));
+                const int k = __shfl_sync(0xffffffffu, k_mine, g);
+                // the bucket of rank k and, when k is its last rank, the next non-empty one (rank k+1): all uniform
+                const uint32_t iv = (uint32_t)tab[bucket_of(sv[k])];
+                const int first = (int)(iv & 0xFFFFu);
+                int end = (int)(iv >> 16);
+                if (k + 1 == end && end < R * 32) end = (int)((uint32_t)tab[bucket_of(sv[end])] >> 16);
+                const int cnt = end - first;
+                int a = k - first;                                                    // rank k inside the window
                 uint32_t klo, khi;
-                if (cnt > 32) {
-                    // heavy window: more members than lanes means ties (many trees returning the same training sample,
-                    // zero-inflated data).  The same peeling on the uncompacted members: the smallest remaining value,
-                    // its multiplicity, drop it; a handful of distinct values at most before the rank is covered.
-                    uint32_t base = 0xFFFFu;
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (wm & (1u << r)) base = min(base, (uint32_t)*slot[r] & 0xFFFFu);
-                    int a = k - (int)__reduce_min_sync(0xffffffffu, base);           // rank k inside the window
-                    bool found = false;
-#pragma unroll 1
-                    for (int it = 0; it < 8 && !found; ++it) {
-                        uint32_t v = NA;
-#pragma unroll
-                        for (int r = 0; r < R; ++r) v = (wm & (1u << r)) ? min(v, sv[r * 32 + lane]) : v;
-                        v = __reduce_min_sync(0xffffffffu, v);
-                        unsigned eqm = 0;
-#pragma unroll
-                        for (int r = 0; r < R; ++r) eqm |= (sv[r * 32 + lane] == v) ? (1u << r) : 0u;
-                        eqm &= wm;
-                        const int n_eq = (int)__reduce_add_sync(0xffffffffu, (unsigned)__popc(eqm));
-                        wm &= ~eqm;
-                        if (a < n_eq || n_eq == 0) {                                  // n_eq == 0 cannot happen (a < cnt): no endless loop
-                            klo = khi = v;
-                            if (a + 1 >= n_eq) {                                      // rank k+1 is the next distinct value
-                                uint32_t nx = NA;
-#pragma unroll
-                                for (int r = 0; r < R; ++r) nx = (wm & (1u << r)) ? min(nx, sv[r * 32 + lane]) : nx;
-                                khi = __reduce_min_sync(0xffffffffu, nx);
-                            }
-                            found = true;
-                        }
-                        a -= n_eq;
-                    }
-                    if (!found) return false;        // uniform: the caller re-buckets with qrf_row_finish
-                } else {
-                    // compact the members, one per lane and round, each with the first rank of its bucket
-                    int pos = 0;
-#pragma unroll 1
-                    while (__any_sync(0xffffffffu, wm != 0u)) {
-                        const bool is = wm != 0u;
-                        const unsigned bal = __ballot_sync(0xffffffffu, is);
-                        if (is) {
-                            const int r = __ffs(wm) - 1;
-                            wm &= wm - 1u;
-                            const uint32_t xv = sv[r * 32 + lane];
-                            const uint32_t iv = (uint32_t)tab[min(__umulhi(xv - mn, mult), 255u)];
-                            mem[pos + __popc(bal & lt)] = make_uint2(xv, iv & 0xFFFFu);
-                        }
-                        pos += __popc(bal);
-                    }
-                    __syncwarp();
-                    const uint2 mine = (lane < cnt) ? mem[lane] : make_uint2(NA, 0xFFFFu);
-                    int a = k - (int)__reduce_min_sync(0xffffffffu, mine.y);          // rank k inside the window
+                if (cnt <= 32) {
                     // peel the window's distinct values from below (a tie group at a time) until the group that covers
                     // rank a is reached: about |bucket| / 2 warp reductions, all results warp-uniform
-                    uint32_t cur = mine.x;
+                    uint32_t cur = (lane < cnt) ? sv[first + lane] : NA;
 #pragma unroll 1
                     for (;;) {
                         const uint32_t v = __reduce_min_sync(0xffffffffu, cur);
@@ -623,7 +559,37 @@ __device__ __forceinline__ bool qrf_row_fast(const uint32_t* sv, int* tab, uint2
                         }
                         a -= n_eq;
                     }
-                    __syncwarp();                                                     // mem is free again
+                } else {
+                    // heavy window: more members than lanes means ties.  The same peeling with up to R keys per lane: the
+                    // smallest remaining value, its multiplicity, drop it; a handful of distinct values at most
+                    uint32_t y[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) y[r] = (lane + 32 * r < cnt) ? sv[first + lane + 32 * r] : NA;
+                    bool found = false;
+                    klo = khi = NA;
+#pragma unroll 1
+                    for (int it = 0; it < 8 && !found; ++it) {
+                        uint32_t v = NA;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) v = min(v, y[r]);
+                        v = __reduce_min_sync(0xffffffffu, v);
+                        unsigned n_eq = 0;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) { n_eq += y[r] == v ? 1u : 0u; y[r] = y[r] == v ? NA : y[r]; }
+                        n_eq = __reduce_add_sync(0xffffffffu, n_eq);
+                        if (a < (int)n_eq) {                                          // v == NA: every slot of every lane, ends the loop
+                            klo = khi = v;
+                            if (a + 1 >= (int)n_eq) {                                 // rank k+1 is the next distinct value
+                                uint32_t nx = NA;
+#pragma unroll
+                                for (int r = 0; r < R; ++r) nx = min(nx, y[r]);
+                                khi = __reduce_min_sync(0xffffffffu, nx);
+                            }
+                            found = true;
+                        }
+                        a -= (int)n_eq;
+                    }
+                    if (!found) return false;        // uniform: the caller re-buckets with qrf_row_finish
                 }
                 if (lane == g) { klo_mine = klo; khi_mine = khi; }
             }
@@ -694,8 +660,11 @@ qrf_direct_kernel(const uint32_t* __restrict__ keys, long long ld_ids, const dou
     const int nchunk = (int)(ld_ids >> 2);   // 16-byte pieces of one key row
     constexpr uint32_t NA = 0xFFFFFFFFu;
 
-    auto fetch = [&](long long rw, int slot) {      // keys of row rw -> ring slot (asynchronous); always commits a group
-        if (rw < row_end && !(skip && skip[rw])) {
+    // keys of row rw -> ring slot (asynchronous); always commits a group.  Rows whose outputs are NA are fetched too (their scratch
+    // rows exist, whatever they hold): the copy then does not wait for the skip byte, which is read two rows ahead into a register
+    auto skip_of = [&](long long rw) -> unsigned { return (skip && rw < row_end) ? (unsigned)skip[rw] : 0u; };
+    auto fetch = [&](long long rw, int slot) {
+        if (rw < row_end) {
             const uint32_t* src = keys + rw * ld_ids + 4 * lane;
             uint32_t* dst = ring + slot * (R * 32) + 4 * lane;
 #pragma unroll
@@ -704,16 +673,19 @@ qrf_direct_kernel(const uint32_t* __restrict__ keys, long long ld_ids, const dou
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    unsigned sk0 = skip_of(row), sk1 = skip_of(row + stride);
     fetch(row, 0);
     fetch(row + stride, 1);
     int slot = 0;
     for (; row < row_end; row += stride) {
         int nslot = slot + 2; nslot -= nslot >= 3 ? 3 : 0;
+        const unsigned sk2 = skip_of(row + 2 * stride);
         fetch(row + 2 * stride, nslot);                            // its previous tenant (row - stride) is finished
         asm volatile("cp.async.wait_group 2;" ::: "memory");       // this row's group has landed
         __syncwarp();
         s.sv = ring + slot * (R * 32);
-        const bool skipped = skip && skip[row];
+        const bool skipped = sk0 != 0u;
+        sk0 = sk1; sk1 = sk2;
         bool done = false;
         if (skipped) {                                             // NA row (masked pixel, NA covariate, too few stations)
             if (out_q) for (int j = lane; j < nprobs; j += 32) out_q[(long long)j * ld_q + row] = na_real();
@@ -722,8 +694,7 @@ qrf_direct_kernel(const uint32_t* __restrict__ keys, long long ld_ids, const dou
         } else if (fast) {
             for (int t = T + lane; t < R * 32; t += 32) s.sv[t] = NA;   // the tail beyond the last tree: NA keys sort last
             __syncwarp();
-            done = qrf_row_fast<R>(s.sv, s.hist0, reinterpret_cast<uint2*>(s.mem), lane, row, probs, nprobs, dict, out_q, ld_q,
-                                   out_iqr_i16);
+            done = qrf_row_fast<R>(s.sv, s.hist0, lane, row, probs, nprobs, dict, out_q, ld_q, out_iqr_i16);
             __syncwarp();
         }
         if (!done) {                                               // heavy ties next to other values: re-bucketing selection
@@ -732,7 +703,8 @@ qrf_direct_kernel(const uint32_t* __restrict__ keys, long long ld_ids, const dou
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int t = r * 32 + lane;
-                const uint32_t x = (t < T) ? s.sv[t] : NA;
+                // after qrf_row_fast the row is permuted (valid keys may sit beyond T) and its tail is NA-filled: take every slot
+                const uint32_t x = (fast || t < T) ? s.sv[t] : NA;
                 if (x != NA) { valid |= 1u << r; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }   // na.rm = TRUE
             }
             qrf_row_finish<R, uint32_t>(s, valid, mn, mx, lane, row, probs, nprobs, dict, out_q, ld_q, out_iqr_i16);
