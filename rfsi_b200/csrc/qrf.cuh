@@ -429,10 +429,9 @@ qrf_quantile_kernel(const uint32_t* __restrict__ leaf_ids, long long ld_ids, con
 //   * NA keys (0xFFFFFFFF) are simply the largest keys: ranks below the number of valid samples never reach them, so
 //     there is no validity mask; the row's tail beyond T is filled with NA by the caller;
 //   * bucket(x) = min(255, umulhi(x - min, mult)), mult <= (2^40 - 1) / (max - min + 1): two integer instructions, monotone;
-//   * one histogram whose shared-memory atomics RETURN each key's arrival number inside its bucket, one warp scan that
-//     turns the table into tab[b] = first rank | (one past the last rank) << 16, and every key is PLACED at
-//     srt[first rank of its bucket + arrival number] -- the row is rewritten in place, grouped by bucket, buckets in rank
-//     order (a counting sort; order inside a bucket is arbitrary; one round of atomics, the placement is a table load);
+//   * one histogram (shared-memory atomics), one warp scan; the table becomes tab[b] = cursor | first rank << 16 and a second
+//     round of atomics PLACES every key at srt[cursor++] -- the row is rewritten in place, grouped by bucket, buckets in
+//     rank order (a counting sort; order inside a bucket is arbitrary).  Afterwards tab[b] = end rank | first rank << 16;
 //   * rank k then sits somewhere in the bucket of srt[k]: one broadcast load of that key, its bucket, its table entry give
 //     the bucket's rank interval [first, end); when k is its last rank, the bucket of srt[end] is appended (rank k+1 lives
 //     there).  That contiguous WINDOW srt[first .. end2) -- a handful of keys -- goes one key per lane, and the member of
@@ -487,11 +486,12 @@ __device__ __forceinline__ bool qrf_row_fast(uint32_t* sv, int* tab, int lane, l
         reinterpret_cast<int4*>(tab)[lane * 2] = make_int4(0, 0, 0, 0);
         reinterpret_cast<int4*>(tab)[lane * 2 + 1] = make_int4(0, 0, 0, 0);
         __syncwarp();
-        uint32_t bo[R];                                                               // bucket of element r | its arrival number in that bucket << 8
+        int* slot[R];                                                                 // &tab[bucket of element r]
 #pragma unroll
-        for (int r = 0; r < R; ++r) bo[r] = bucket_of(x[r]);
-#pragma unroll
-        for (int r = 0; r < R; ++r) bo[r] |= (uint32_t)atomicAdd(tab + bo[r], 1) << 8;
+        for (int r = 0; r < R; ++r) {
+            slot[r] = tab + bucket_of(x[r]);
+            atomicAdd(slot[r], 1);
+        }
         __syncwarp();
         {
             const int4 h0 = reinterpret_cast<const int4*>(tab)[lane * 2];
@@ -505,23 +505,24 @@ __device__ __forceinline__ bool qrf_row_fast(uint32_t* sv, int* tab, int lane, l
                 if (lane >= o) incl += t;
             }
             const int e = incl - s8;                                                  // elements in the buckets of lower lanes
-            // first rank | (one past the last rank) << 16
-            const int4 p0 = make_int4(e | ((e + s1) << 16), (e + s1) | ((e + s2) << 16), (e + s2) | ((e + s3) << 16),
-                                      (e + s3) | ((e + s4) << 16));
-            const int4 p1 = make_int4((e + s4) | ((e + s5) << 16), (e + s5) | ((e + s6) << 16), (e + s6) | ((e + s7) << 16),
-                                      (e + s7) | ((e + s8) << 16));
+            // cursor (low half, starts at the bucket's first rank) | first rank << 16
+            const int4 p0 = make_int4(e * 0x10001, (e + s1) * 0x10001, (e + s2) * 0x10001, (e + s3) * 0x10001);
+            const int4 p1 = make_int4((e + s4) * 0x10001, (e + s5) * 0x10001, (e + s6) * 0x10001, (e + s7) * 0x10001);
             __syncwarp();
             reinterpret_cast<int4*>(tab)[lane * 2] = p0;
             reinterpret_cast<int4*>(tab)[lane * 2 + 1] = p1;
         }
         __syncwarp();
-        // ---- place every key at first rank of its bucket + arrival number: the row in place, grouped by bucket, buckets in
-        //      rank order (every lane holds its keys in registers; the arrival numbers came back from the histogram atomics) ----
+        // ---- place every key: the row in place, grouped by bucket (every lane holds its keys in registers).  A second round
+        //      of atomics on the cursors; taking the arrival numbers from the histogram's atomics instead (returning form, the
+        //      placement then a table load) measured slower: 6.04 vs 5.30 ms (profiles/r02_r_qrf_ab.txt) -- the counting round
+        //      is ATOMS.POPC.INC, which merges lanes on the same bucket, the returning form serialises them ----------------
+        int at[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) bo[r] = ((uint32_t)tab[bo[r] & 0xFFu] & 0xFFFFu) + (bo[r] >> 8);   // all loads before the first store
+        for (int r = 0; r < R; ++r) at[r] = atomicAdd(slot[r], 1);                    // all in flight before the first store
 #pragma unroll
-        for (int r = 0; r < R; ++r) sv[bo[r]] = x[r];
-        __syncwarp();
+        for (int r = 0; r < R; ++r) sv[at[r] & 0xFFFF] = x[r];
+        __syncwarp();                                                                 // tab[b] = end rank | first rank << 16
 
         for (int j0 = 0; j0 < nprobs; j0 += kQrfGroup) {
             // ---- lane j < 3: quantile j0 + j.  R: index = 1 + (n-1)*p in two roundings, lo = floor, hi = ceil --
@@ -536,9 +537,9 @@ __device__ __forceinline__ bool qrf_row_fast(uint32_t* sv, int* tab, int lane, l
                 const int k = __shfl_sync(0xffffffffu, k_mine, g);
                 // the bucket of rank k and, when k is its last rank, the next non-empty one (rank k+1): all uniform
                 const uint32_t iv = (uint32_t)tab[bucket_of(sv[k])];
-                const int first = (int)(iv & 0xFFFFu);
-                int end = (int)(iv >> 16);
-                if (k + 1 == end && end < R * 32) end = (int)((uint32_t)tab[bucket_of(sv[end])] >> 16);
+                const int first = (int)(iv >> 16);
+                int end = (int)(iv & 0xFFFFu);
+                if (k + 1 == end && end < R * 32) end = (int)((uint32_t)tab[bucket_of(sv[end])] & 0xFFFFu);
                 const int cnt = end - first;
                 int a = k - first;                                                    // rank k inside the window
                 uint32_t klo, khi;
