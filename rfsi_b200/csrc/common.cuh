@@ -60,7 +60,10 @@ constexpr uint32_t kBMaxRank = 0xFFFFFEu;
 
 // rank_of() narrows its binary search with a per-feature table of kRankBuckets monotone
 // buckets between the feature's smallest and largest threshold (forest.cuh)
-constexpr int kRankBuckets = 4096;
+#ifndef RFSI_RANK_BUCKETS
+#define RFSI_RANK_BUCKETS 4096   // experiment builds: tools/build_variant.sh rb32k -DRFSI_RANK_BUCKETS=32768
+#endif
+constexpr int kRankBuckets = RFSI_RANK_BUCKETS;
 __host__ __device__ __forceinline__ int rank_bucket(double x, double lo_half, double scale) {
 #ifdef __CUDA_ARCH__
     const double t = __dmul_rn(__dsub_rn(__dmul_rn(x, 0.5), lo_half), scale);

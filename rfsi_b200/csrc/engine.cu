@@ -508,7 +508,7 @@ bool ensure_sector(const rfsi_forest* f) {
         std::vector<uint32_t>& v = part[(size_t)t];
         sector_relocate(v.data(), v.size() / 8, (uint32_t)at);
         memcpy(W.data() + at * 8, v.data(), v.size() * sizeof(uint32_t));
-        f->sroot[(size_t)t] = (uint32_t)at;
+        f->sroot[(size_t)t] = sector_root_entry(v.data(), (uint32_t)at);
         at += v.size() / 8;
         std::vector<uint32_t>().swap(v);
     }
@@ -581,7 +581,7 @@ int forest_image(const rfsi_forest* f, int device, rfsi_forest::Image* out) {
         if (im.sector) {
             RF_TRY(up(f->sect.data(), f->sect.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.sect)));
             RF_TRY(up(f->sroot.data(), f->sroot.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.sroot)));
-            im.q.rank_shift = 8;
+            im.q.rank_shift = kSRankShift;
         } else if (im.blocked) {
             RF_TRY(up(f->blocks.data(), f->blocks.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.blocks)));
             RF_TRY(up(f->broot.data(), f->broot.size() * sizeof(uint32_t), reinterpret_cast<const void**>(&im.q.broot)));

@@ -7,45 +7,45 @@
 //
 // Layout.  One block = 8 words = ONE 32-byte sector = three tree levels:
 //     word 0      index of the first of the block's 8 child blocks (children are contiguous and
-//                 come after their parent: child = w0 + exit, exit = heap slot - 8)
+//                 come after their parent: child = w0 + exit, exit = 0..7 = the three decisions as bits)
 //     words 1..7  implicit heap of 7 nodes, children of slot h at 2h, 2h+1;
-//                 node word = (~rank << 8) | feature (rank: 24 bits): the walk goes right iff
-//                 (rank(x) << 8) + word carries out of 32 bits, i.e. iff rank(x) > rank -- the
-//                 feature byte cannot make up the difference because rank(x) << 8 ends in 00; it is
-//                 stored as it is, so the shared-memory address is one AND and one multiply-add
-//     a LEAF is a block of its own:
-//                 word 0 = 0x80000000 | its own block index
-//                 words 1, 2, 4 = pass-through nodes (the only heap slots a walk can touch: 1 -> 2 -> 4 -> exit 0)
+//                 node word = (~rank << 10) | leaf flags << 8 | feature (rank: 22 bits): the walk goes right iff
+//                 (rank(x) << 10) + word carries out of 32 bits, i.e. iff rank(x) > rank -- the low ten bits
+//                 cannot make up the difference because rank(x) << 10 ends in zeros; the feature byte is
+//                 stored as it is, so the shared-memory address is one AND and one multiply-add.
+//                 The two flag bits only mean something in the third level (slots 4..7): bit 9 = the block's
+//                 exit to the LEFT of this node is a leaf block, bit 8 = the exit to the right is.  A chain
+//                 therefore knows that it is finished when it takes its exit, WITHOUT visiting the leaf's block:
+//                 one block visit less per tree (round 2, profiles/r02_s_*: the leaf visit was 1 of 8.2 visits
+//                 of a chain and walked three pass-through levels for nothing).
+//     a LEAF is a block of its own, touched once per tree by the loads of its payload:
+//                 word 0 = 0x80000000 | its own block index (builder bookkeeping; the walk never reads it)
 //                 word 3 = leaf number (left to right within the tree, trees one after the other)
 //                 word 5 = quantile-forest key of the leaf (rank of ranger's random.node.values
 //                          entry in the forest-wide sorted dictionary, 0xFFFFFFFF = NA)
 //                 words 6..7 = the leaf's prediction (fp64)
-//     block 0 is the idle block: word 0 = 0, all nodes pass-through (= 8 zero words).
-// A leaf met before a block's third level is padded with pass-through nodes (rank 0xFFFFFF:
-// never exceeded) down to ONE exit; the child slots to the right of padding are never visited
-// and stay zero.
+//     block 0 is the idle block: 8 zero words (first child = itself, all nodes pass-through, no leaf flags).
+// A leaf met before a block's third level is padded with pass-through nodes (rank field 0 = rank 0x3FFFFF:
+// never exceeded) down to ONE exit, whose flag says "leaf"; the child slots to the right of padding are never
+// visited and stay zero.  The root entry of a single-node tree carries the finished flag itself.
 //
 // Why (profiles/r01_g): the 128-byte blocked image needs three dependent sector fetches per four
 // levels (levels 1-3 | level 4 | exit word) plus a leaf-value gather; here a block visit is one
 // sector -- one L1 miss, then two L1 hits -- per three levels, no exit load, and the leaf's value,
-// number and quantile key arrive with the leaf's own sector.
+// number and quantile key sit in the leaf's own sector.
 //
 // Walk state per chain: ONE register bb = block index, or 0x80000000 | leaf block once the
 // chain is finished.  Per block visit:
 //     idx = max((int)bb, 0)                 finished chains idle on block 0 (one shared sector)
 //     {w0, n1} = 64-bit load                three levels: node load, shared-memory rank load, add.cc/addc
-//     bb = umax(bb, w0 + h - 8)             children have larger indices than their parent, a leaf
+//     leaf = (n3 << (22 + last carry)) & 0x80000000
+//     bb = umax(bb, (w0 | leaf) + exit)     children have larger indices than their parent, a leaf exit
 //                                           carries the flag bit, the idle block yields 0: no selects
-// and the lane leaves the loop as soon as every chain is finished or standing on a leaf block
-// (sign bit of AND_j (bb_j | w0_j)), so the last visit of the deepest chain costs one load.
+// and the lane leaves the loop as soon as every chain carries the flag (sign bit of AND_j bb_j).
 #pragma once
 #include <cstddef>
 #include <cstdint>
 #include <vector>
-
-#ifndef RFSI_SECT_WIDE
-#define RFSI_SECT_WIDE 0
-#endif
 
 #if defined(RFSI_SECTOR_HOST_CHECK)
 // tests/tools/sector_host.cpp compiles the very same loop for the host (no CUDA headers)
@@ -61,14 +61,16 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 namespace rfsi {
 
 constexpr uint32_t kSLeafFlag = 0x80000000u;
-constexpr uint32_t kSPassWord = 0x00000000u;       // rank 0xFFFFFF, feature 0: never carries
-constexpr uint32_t kSMaxRank = 0xFFFFFEu;
+constexpr int kSRankShift = 10;                    // node word = (~rank << 10) | leaf flags << 8 | feature
+constexpr uint32_t kSPassWord = 0x00000000u;       // rank 0x3FFFFF, feature 0: never carries
+constexpr uint32_t kSMaxRank = 0x3FFFFEu;
+constexpr uint32_t kSLeafLeft = 1u << 9, kSLeafRight = 1u << 8;   // third-level nodes: the exit on that side is a leaf block
 constexpr int kSMaxFeat = 256;
 constexpr int kSWordLeafNo = 3, kSWordKey = 5, kSWordValue = 6;
 
 struct SectorView {
     const uint32_t* words;   // 8 per block
-    const uint32_t* root;    // [T] block of each tree's root (a leaf block for a single-node tree)
+    const uint32_t* root;    // [T] block of each tree's root (sector_root_entry: flagged leaf block for a single-node tree)
     // 32 (bytes per block) and P*4 (bytes between two features of the rank tile) as RUN-TIME values: given
     // immediates, ptxas strength-reduces idx*32 + base into LEA + LEA.HI.X and feat*1024 + base into
     // IMAD.SHL + LOP3 + IMAD.IADD; from the constant bank they stay one IMAD.WIDE / one IMAD (the walk is
@@ -77,7 +79,7 @@ struct SectorView {
     uint32_t tile_stride;
 };
 
-// h + h + carry(xs + w): one level.  xs = rank(x) << 8, w = (~rank << 8) | feature.
+// h + h + carry(xs + w): one level.  xs = rank(x) << 10, w = (~rank << 10) | flags << 8 | feature.
 RFSI_SECT_DEV uint32_t sector_step(uint32_t h, uint32_t w, uint32_t xs) {
 #if defined(RFSI_SECTOR_HOST_CHECK)
     return 2u * h + (uint32_t)(((uint64_t)xs + (uint64_t)w) >> 32);
@@ -88,9 +90,25 @@ RFSI_SECT_DEV uint32_t sector_step(uint32_t h, uint32_t w, uint32_t xs) {
 #endif
 }
 
+// The third level of a block visit: the exit e = 2h + carry (0..7) and, from the same carry, the flag of that exit moved
+// to bit 31 -- the third-level node holds it at bit 9 (left exit, carry 0: shift by 22) or bit 8 (right exit: shift by 23).
+RFSI_SECT_DEV uint32_t sector_last_step(uint32_t h, uint32_t w, uint32_t xs, uint32_t& leaf) {
+#if defined(RFSI_SECTOR_HOST_CHECK)
+    const uint32_t c = (uint32_t)(((uint64_t)xs + (uint64_t)w) >> 32);
+    leaf = (w << (22u + c)) & 0x80000000u;
+    return 2u * h + c;
+#else
+    uint32_t out, sh;
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %2, %3;\n\taddc.u32 %0, %4, %4;\n\taddc.u32 %1, 22, 0;\n\t}"
+        : "=r"(out), "=r"(sh) : "r"(xs), "r"(w), "r"(h));
+    leaf = (w << sh) & 0x80000000u;
+    return out;
+#endif
+}
+
 RFSI_SECT_DEV uint32_t sector_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
-inline uint32_t sector_node_word(uint32_t rank, uint32_t feat) { return ((~rank) << 8) | feat; }
+inline uint32_t sector_node_word(uint32_t rank, uint32_t feat) { return ((~rank) << kSRankShift) | feat; }
 
 // address of block max(bb, 0): one signed max, one 32 x 32 -> 64-bit multiply-add
 // `words` is the image base held in an ordinary register pair (sector_base): with the base in uniform registers
@@ -131,51 +149,10 @@ RFSI_SECT_DEV double traverse_s(const SectorView& q, int t_begin, int t_end, dou
 #pragma unroll
         for (int j = 0; j < J; ++j) bb[j] = (t0 + j < t_end) ? __ldg(q.root + t0 + j) : kSLeafFlag;   // no tree: finished, idles on block 0
         for (;;) {
-#if RFSI_SECT_WIDE
-            // one 128-bit request brings w0 and the nodes of levels 1 and 2; level 3 is one more 32-bit load
-            uint4 w03[J];
-            const uint32_t* blk[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                blk[j] = sector_block(q, words, bb[j]);
-                w03[j] = __ldg(reinterpret_cast<const uint4*>(blk[j]));
-            }
             uint32_t fin = kSLeafFlag;
 #pragma unroll
-            for (int j = 0; j < J; ++j) fin &= bb[j] | w03[j].x;
-            if (fin) {                                                        // every chain finished or on its leaf
-#pragma unroll
-                for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w03[j].x);
-                break;
-            }
-            uint32_t h[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w03[j].y & 0xFFu) * q.tile_stride);
-                h[j] = sector_step(1u, w03[j].y, xs);
-                if (COUNT) nvisit += (w03[j].y != kSPassWord) ? 1u : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const uint32_t w = (h[j] & 1u) ? w03[j].w : w03[j].z;         // heap slot 3 or 2
-                const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w & 0xFFu) * q.tile_stride);
-                h[j] = sector_step(h[j], w, xs);
-                if (COUNT) nvisit += (w != kSPassWord) ? 1u : 0u;
-            }
-            {
-                uint32_t w[J];
-#pragma unroll
-                for (int j = 0; j < J; ++j) w[j] = __ldg(blk[j] + h[j]);      // same sector
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w[j] & 0xFFu) * q.tile_stride);
-                    h[j] = sector_step(h[j], w[j], xs);
-                    if (COUNT) nvisit += (w[j] != kSPassWord) ? 1u : 0u;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w03[j].x + (h[j] - 8u));   // implicit child: no exit load
-#else
+            for (int j = 0; j < J; ++j) fin &= bb[j];
+            if (fin) break;                                                   // every chain has taken a leaf exit
             uint2 w01[J];
             const uint32_t* blk[J];
 #pragma unroll
@@ -183,42 +160,44 @@ RFSI_SECT_DEV double traverse_s(const SectorView& q, int t_begin, int t_end, dou
                 blk[j] = sector_block(q, words, bb[j]);
                 w01[j] = __ldg(reinterpret_cast<const uint2*>(blk[j]));     // w0 and the level-1 node: one request
             }
-            uint32_t fin = kSLeafFlag;
-#pragma unroll
-            for (int j = 0; j < J; ++j) fin &= bb[j] | w01[j].x;
-            if (fin) {                                                        // every chain finished or on its leaf
-#pragma unroll
-                for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w01[j].x);
-                break;
-            }
-            uint32_t h[J];
+            uint32_t h[J];                                                    // the decisions so far, as bits
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w01[j].y & 0xFFu) * q.tile_stride);
-                h[j] = sector_step(1u, w01[j].y, xs);
-                if (COUNT) nvisit += (w01[j].y != kSPassWord) ? 1u : 0u;
+                h[j] = sector_step(0u, w01[j].y, xs);
+                if (COUNT) nvisit += (w01[j].y >> kSRankShift) ? 1u : 0u;
             }
-#pragma unroll
-            for (int lev = 1; lev < 3; ++lev) {
+            {
                 uint32_t w[J];
 #pragma unroll
-                for (int j = 0; j < J; ++j) w[j] = __ldg(blk[j] + h[j]);      // same sector: L1 hits
+                for (int j = 0; j < J; ++j) w[j] = __ldg(blk[j] + 2 + h[j]);  // heap slot 2 or 3, same sector: L1 hit
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w[j] & 0xFFu) * q.tile_stride);
                     h[j] = sector_step(h[j], w[j], xs);
-                    if (COUNT) nvisit += (w[j] != kSPassWord) ? 1u : 0u;
+                    if (COUNT) nvisit += (w[j] >> kSRankShift) ? 1u : 0u;
                 }
             }
+            {
+                uint32_t w[J];
 #pragma unroll
-            for (int j = 0; j < J; ++j) bb[j] = sector_umax(bb[j], w01[j].x + (h[j] - 8u));   // implicit child: no exit load
-#endif
+                for (int j = 0; j < J; ++j) w[j] = __ldg(blk[j] + 4 + h[j]);  // heap slot 4..7
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const uint32_t xs = *reinterpret_cast<const uint32_t*>(rsb + (w[j] & 0xFFu) * q.tile_stride);
+                    uint32_t leaf;
+                    h[j] = sector_last_step(h[j], w[j], xs, leaf);            // the exit, 0..7, and its leaf flag
+                    if (COUNT) nvisit += (w[j] >> kSRankShift) ? 1u : 0u;
+                    // implicit child, no exit load; a leaf exit finishes the chain without a visit to the leaf's block
+                    bb[j] = sector_umax(bb[j], (w01[j].x | leaf) + h[j]);
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < J; ++j) bb[j] &= ~kSLeafFlag;
 #pragma unroll
         for (int j = 0; j < J; ++j)
-            if (t0 + j < t_end)                                                // the leaf's own sector: fetched by the walk
+            if (t0 + j < t_end)                                                // the leaf's own sector: its only visit
                 sum += __ldg(reinterpret_cast<const double*>(words + (size_t)bb[j] * 8u + kSWordValue));
         sink(t0, t_end - t0, bb);
     }
@@ -248,7 +227,6 @@ inline void sector_build_tree(uint32_t root_node, NodeAt&& node, Vec& w)
     auto make_leaf = [&](uint32_t blk, const SectorNode& n) {
         uint32_t* b = &w[(size_t)blk * 8];
         b[0] = kSLeafFlag | blk;
-        b[1] = b[2] = b[4] = kSPassWord;
         b[kSWordLeafNo] = n.leaf_no;
         b[kSWordKey] = 0xFFFFFFFFu;
         uint64_t bits;
@@ -275,7 +253,12 @@ inline void sector_build_tree(uint32_t root_node, NodeAt&& node, Vec& w)
                 if (it.dead) continue;                         // right of a pass-through node: never visited
                 const uint32_t child = kids + (uint32_t)(it.h - 8);
                 const SectorNode n = node(it.node);
-                if (n.leaf) make_leaf(child, n); else todo.push_back(Todo{it.node, child});
+                if (n.leaf) {
+                    make_leaf(child, n);
+                    w[(size_t)cur.block * 8 + (it.h >> 1)] |= (it.h & 1) ? kSLeafRight : kSLeafLeft;   // told by the third-level node
+                } else {
+                    todo.push_back(Todo{it.node, child});
+                }
                 continue;
             }
             const SectorNode n = it.dead ? SectorNode{true, 0, 0, 0, 0.0} : node(it.node);
@@ -300,5 +283,9 @@ inline void sector_relocate(uint32_t* w, size_t nblocks, uint32_t base) {
         if (!unused) w0 += base;                               // leaf flag is the top bit: the sum stays below it
     }
 }
+
+// root[] entry of a tree whose blocks start at `base` (tree_words = its first block, relocated or not): the block to
+// start at, or -- a single-node tree -- the finished flag and the leaf block at once
+inline uint32_t sector_root_entry(const uint32_t* tree_words, uint32_t base) { return base | (tree_words[0] & kSLeafFlag); }
 
 }  // namespace rfsi

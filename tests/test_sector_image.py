@@ -17,12 +17,11 @@ from rfsi_b200.forest import FlatForest
 ROOT = Path(__file__).resolve().parents[1]
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["ldg64", "ldg128"])
-def lib(request, tmp_path_factory):
-    # both forms of the block visit (sector.cuh: RFSI_SECT_WIDE): 64-bit first load + two 32-bit loads, or 128-bit + one
-    so = tmp_path_factory.mktemp("sector") / f"libsector_host{request.param}.so"
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    so = tmp_path_factory.mktemp("sector") / "libsector_host.so"
     subprocess.run(["g++", "-O2", "-fPIC", "-std=c++17", "-shared", "-Wall", "-Wno-unknown-pragmas",
-                    f"-DRFSI_SECT_WIDE={request.param}", "-o", str(so), str(ROOT / "tests" / "tools" / "sector_host.cpp")], check=True)
+                    "-o", str(so), str(ROOT / "tests" / "tools" / "sector_host.cpp")], check=True)
     L = C.CDLL(str(so))
     L.sh_stats.restype = C.c_int64
     L.sh_stats.argtypes = [C.c_void_p, C.c_int]

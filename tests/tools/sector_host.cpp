@@ -76,7 +76,7 @@ extern "C" int sh_build(int T, const int64_t* off, const int32_t* left, const in
         rfsi::sector_build_tree((uint32_t)t, node_at, w);
         const uint32_t base = (uint32_t)(im->words.size() / 8);
         rfsi::sector_relocate(w.data(), w.size() / 8, base);
-        im->root.push_back(base);
+        im->root.push_back(rfsi::sector_root_entry(w.data(), base));
         im->words.insert(im->words.end(), w.begin(), w.end());
     }
     for (size_t b = 1; b < im->words.size() / 8; ++b) {
@@ -115,7 +115,7 @@ static void walk(const Image* im, const double* X, int64_t npix, int64_t ldx, in
     for (int64_t p = 0; p < npix; ++p) {
         for (int f = 0; f < im->F; ++f) {
             const auto& u = im->u[(size_t)f];
-            rk[(size_t)f] = (uint32_t)(std::lower_bound(u.begin(), u.end(), X[(int64_t)f * ldx + p]) - u.begin()) << 8;
+            rk[(size_t)f] = (uint32_t)(std::lower_bound(u.begin(), u.end(), X[(int64_t)f * ldx + p]) - u.begin()) << rfsi::kSRankShift;
         }
         unsigned nv = 0;
         auto sink = [&](int t0, int remaining, const uint32_t (&lb)[J]) {
