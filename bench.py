@@ -269,8 +269,8 @@ def warp_sector_model(flat, X, trees):
             nxt = np.where(X[rows, v[node]] <= s[node], l[node], r[node])
             node = np.where(internal, nxt, node)
             d += 1
-        sectors += int(distinct(node.reshape(W, 32)).sum())     # the leaves' own blocks
-        visits += int(deepest.sum()) + W
+        sectors += int(distinct(node.reshape(W, 32)).sum())     # the leaves' own blocks: touched by the payload loads only
+        visits += int(deepest.sum())                            # (a leaf exit is flagged in its parent block: no leaf visit)
     n = W * trees
     return sectors / n, visits / n, depth_sum / (npix * trees)
 
@@ -526,7 +526,7 @@ def main_ours(args):
         "issue_frac": ncu.get("issue_active_frac"), "l1_hit": ncu.get("l1_sector_hit_frac"),
         "l1_data_pipe_frac": ncu.get("l1tex_data_pipe_frac"),
         "loads_per_warp_tree": {"measured": ncu.get("global_load_requests_per_warp_tree"),
-                                "path_minimum": (3.0 * (model_rec["block_visits_per_warp_tree_lockstep_floor"] - 1) + 2.0) if model_rec else None},
+                                "path_minimum": (3.0 * model_rec["block_visits_per_warp_tree_lockstep_floor"] + 1.0) if model_rec else None},
         "ncu_source": ncu.get("captured"), "ncu_source_sha": ncu.get("source_sha"), "kernel_source_sha": sha, "ncu_stale": stale,
         "peak_source": peak_src,
         "survey_model": {"bytes_per_pixel_day": b_survey, "frac": (b_survey * units_per_launch / launch_s / 1e9 / peak) if launch_s > 0 else None,

@@ -58,19 +58,23 @@ constexpr uint32_t kBPassWord = ~((0xFFFFFFu << 8) | 0u);   // complemented pass
 constexpr int kBMaxFeat = 256;
 constexpr uint32_t kBMaxRank = 0xFFFFFEu;
 
-// rank_of() narrows its binary search with a per-feature table of kRankBuckets monotone
-// buckets between the feature's smallest and largest threshold (forest.cuh)
-#ifndef RFSI_RANK_BUCKETS
-#define RFSI_RANK_BUCKETS 4096   // experiment builds: tools/build_variant.sh rb32k -DRFSI_RANK_BUCKETS=32768
-#endif
-constexpr int kRankBuckets = RFSI_RANK_BUCKETS;
-__host__ __device__ __forceinline__ int rank_bucket(double x, double lo_half, double scale) {
+// rank_of() narrows its binary search with a per-feature table of monotone buckets between the feature's smallest
+// and largest threshold (forest.cuh).  The number of buckets is chosen per feature when the forest is created: about
+// one bucket per distinct threshold (a power of two, at most kRankBucketsMax; RFSI_B200_RANK_BUCKETS lowers the
+// cap).  Measured on the bench forest (7.7e5 thresholds per feature; profiles/r02_s_*, r02_t_*): the walk's prologue
+// is 43 such searches per pixel-day whose loads diverge across a warp (neighbouring pixels sit hundreds of thresholds
+// apart in the distance columns); 4096 buckets per feature (round 1, 8 search steps) -> 2^16 -> 2^18 -> 2^20 (about
+// one step) is 130.2 -> 137.7 -> 140.2 -> 141.9 M pixel-days/s (with the leaf-flag image, itself +1 %).
+constexpr int kRankBucketsMin = 64;
+constexpr int kRankBucketsMax = 1 << 20;
+// bucket of x: nbm1 = number of buckets - 1 (as a double, so the clamp is one compare)
+__host__ __device__ __forceinline__ int rank_bucket(double x, double lo_half, double scale, double nbm1) {
 #ifdef __CUDA_ARCH__
     const double t = __dmul_rn(__dsub_rn(__dmul_rn(x, 0.5), lo_half), scale);
 #else
     const double t = (x * 0.5 - lo_half) * scale;   // host build: no FMA contraction on x86-64 SSE2
 #endif
-    return t >= (double)(kRankBuckets - 1) ? kRankBuckets - 1 : (t > 0.0 ? (int)t : 0);
+    return t >= nbm1 ? (int)nbm1 : (t > 0.0 ? (int)t : 0);
 }
 
 constexpr int32_t kIdxNone = 0x7fffffff;        // empty slot of a neighbour list

@@ -294,8 +294,8 @@ struct rfsi_forest {
     std::vector<double> leaf_val;
     std::vector<double> uvals;
     std::vector<int32_t> uoff;
-    std::vector<double> rpar;         // [F][2] bucket function of rank_of()
-    std::vector<int32_t> rtab;        // [F][kRankBuckets+1]
+    std::vector<double> rpar;         // [F][4] bucket function of rank_of(): lo/2, scale, buckets - 1, table offset
+    std::vector<int32_t> rtab;        // per feature [buckets+1]
     // The two block images are derived from the compact one on first use (forest_image / rfsi_forest_info), under `mu`:
     // only the image a process actually walks is built (the sector image of the bench forest is 2.8 GB).
     // blocked format (common.cuh)
@@ -659,17 +659,27 @@ void build_compact(rfsi_forest* f) {
     f->uvals.resize((size_t)f->uoff[F]);
     for (int j = 0; j < F; ++j) std::copy(u[j].begin(), u[j].end(), f->uvals.begin() + f->uoff[j]);
     // bucket tables for rank_of(): counts of thresholds per monotone bucket, prefix-summed
-    f->rpar.assign((size_t)F * 2, 0.0);
-    f->rtab.assign((size_t)F * (kRankBuckets + 1), 0);
+    // about one bucket per distinct threshold (a power of two): the search inside a bucket is then a step or two
+    const int cap = std::max(kRankBucketsMin, std::min(kRankBucketsMax, env_int("RFSI_B200_RANK_BUCKETS", kRankBucketsMax)));
+    f->rpar.assign((size_t)F * 4, 0.0);
+    std::vector<size_t> toff((size_t)F + 1, 0);
+    std::vector<int> nbk((size_t)F, kRankBucketsMin);
     for (int j = 0; j < F; ++j) {
-        int32_t* tab = f->rtab.data() + (size_t)j * (kRankBuckets + 1);
+        while (nbk[j] < cap && (size_t)nbk[j] < u[j].size()) nbk[j] *= 2;
+        toff[j + 1] = toff[j] + (size_t)nbk[j] + 1;
+    }
+    f->rtab.assign(toff[F], 0);
+    for (int j = 0; j < F; ++j) {
+        int32_t* tab = f->rtab.data() + toff[j];
+        const int nb = nbk[j];
+        f->rpar[4 * j + 2] = (double)(nb - 1); f->rpar[4 * j + 3] = (double)toff[j];
         if (u[j].empty()) continue;
         const double lo_half = u[j].front() * 0.5;
-        double scale = (double)kRankBuckets / (u[j].back() * 0.5 - lo_half);
+        double scale = (double)nb / (u[j].back() * 0.5 - lo_half);
         if (!(scale < 1.0e300)) scale = 1.0e300;   // one threshold, or a tiny range: still monotone
-        f->rpar[2 * j] = lo_half; f->rpar[2 * j + 1] = scale;
-        for (double v : u[j]) ++tab[rank_bucket(v, lo_half, scale) + 1];
-        for (int b = 0; b < kRankBuckets; ++b) tab[b + 1] += tab[b];
+        f->rpar[4 * j] = lo_half; f->rpar[4 * j + 1] = scale;
+        for (double v : u[j]) ++tab[rank_bucket(v, lo_half, scale, (double)(nb - 1)) + 1];
+        for (int b = 0; b < nb; ++b) tab[b + 1] += tab[b];
     }
 
     f->qnodes.assign(n, (uint64_t)0);                // leaf: {w0 = ~0xFFFFFFFF = 0, w1 = 0}

@@ -28,8 +28,8 @@ struct QForest {
     const double* leaf_val;   // [n] prediction at leaf indices
     const double* uvals;      // sorted unique thresholds, features concatenated
     const int32_t* uoff;      // [F+1]
-    const double* rpar;       // [F][2] {lo/2, scale} of the bucket function of feature f
-    const int32_t* rtab;      // [F][kRankBuckets+1] number of thresholds in buckets < b
+    const double* rpar;       // [F][4] bucket function of feature f: {lo/2, scale, buckets - 1, offset of its table in rtab}
+    const int32_t* rtab;      // per feature [buckets+1] number of thresholds in buckets < b
     const uint32_t* blocks;   // blocked format (common.cuh): 32 words per block; nullptr = use `nodes`
     const uint32_t* broot;    // [T] root block of each tree (or a leaf marker)
     int rank_shift;           // ranks are stored in shared memory shifted left by this (8 when blocked / sector)
@@ -41,11 +41,13 @@ struct QForest {
 
 // number of thresholds of feature f strictly below x (x is never NaN here).  The bucket
 // function is monotone, so every threshold in an earlier bucket is < x and every one in a later
-// bucket is > x: only x's own bucket (a few dozen thresholds) needs the binary search.
+// bucket is > x: only x's own bucket (a threshold or two: about one bucket per threshold) needs the binary search.
 __device__ __forceinline__ uint32_t rank_of(const QForest& q, int f, double x) {
     const double* __restrict__ u = q.uvals + q.uoff[f];
-    const int b = rank_bucket(x, __ldg(q.rpar + 2 * f), __ldg(q.rpar + 2 * f + 1));
-    const int32_t* __restrict__ tab = q.rtab + (size_t)f * (kRankBuckets + 1);
+    const double2 p0 = __ldg(reinterpret_cast<const double2*>(q.rpar) + 2 * f);
+    const double2 p1 = __ldg(reinterpret_cast<const double2*>(q.rpar) + 2 * f + 1);
+    const int b = rank_bucket(x, p0.x, p0.y, p1.x);
+    const int32_t* __restrict__ tab = q.rtab + (long long)p1.y;
     int lo = __ldg(tab + b);
     int n = __ldg(tab + b + 1) - lo;
     while (n > 0) {
