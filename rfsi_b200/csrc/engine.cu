@@ -1854,7 +1854,9 @@ struct FusedPlan {
     int64_t rows = 0;         // npix * db
     int64_t npix_plan = 0;    // pixels the workspace was sized for
     bool want_q = false;
+    bool cand_rank = false, obs_rank = false;   // rank caches of the rank images (fused.cuh)
     // workspace offsets
+    size_t off_cand_rank = 0, off_obs_rank = 0;
     size_t off_cand_d2 = 0, off_cand_id = 0, off_xy = 0, off_cells = 0, off_perm = 0, off_fb = 0, off_acc = 0, off_misc = 0, off_samples = 0, off_skip = 0,
            off_probs = 0, total = 0;
 };
@@ -1956,6 +1958,14 @@ FusedPlan plan_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, int kc_
     pl.off_acc = o; o += align_up(sizeof(double) * (size_t)pl.rows, 256);
     pl.off_misc = o; o += 256;  // fb_count, na_flag
     pl.off_probs = o; o += align_up(sizeof(double) * kMaxProbs, 256);
+    // rank caches (fused.cuh): worth their fill only when more than one day reads them / more pixels than stations
+    if (f->compact_ok && env_int("RFSI_B200_RANK_CACHE", 1)) {
+        const size_t ob = sizeof(uint32_t) * (size_t)db * (size_t)std::max(a->nobs, 1) * (size_t)a->n_obs;
+        pl.cand_rank = a->ndays >= 2;
+        pl.obs_rank = ob <= ((size_t)1 << 30) && (int64_t)a->nobs * 4 <= npix * (int64_t)db;
+        if (pl.cand_rank) { pl.off_cand_rank = o; o += align_up(sizeof(uint32_t) * (size_t)pl.KC * kCandShifts * npix, 256); }
+        if (pl.obs_rank) { pl.off_obs_rank = o; o += align_up(ob, 256); }
+    }
     if (pl.want_q) {
         pl.off_samples = o; o += align_up(leaf_ids_bytes(pl.rows, f->ntrees), 256);
         pl.off_skip = o; o += align_up((size_t)pl.rows, 256);
@@ -2080,6 +2090,18 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
     fp.nodes = im.nodes; fp.q = im.q; fp.leaf_rid = nullptr;
     fp.T = f->ntrees; fp.F = f->nfeat;
     fp.acc = acc;
+    // rank caches: the distance ranks of the candidates once per pixel (they live as long as the candidate lists) ...
+    uint32_t* cand_rank = (im.compact && pl.cand_rank) ? reinterpret_cast<uint32_t*>(ws + pl.off_cand_rank) : nullptr;
+    uint32_t* obs_rank = (im.compact && pl.obs_rank && a->nobs > 0) ? reinterpret_cast<uint32_t*>(ws + pl.off_obs_rank) : nullptr;
+    if (cand_rank && !reuse_candidates) {
+        ProfScope ps(PROF_KNN_RAW, st);
+        const int ncand = std::min(pl.KC, a->n_obs + kCandShifts - 1);   // later candidates have no column within the shifts
+        const long long n = (long long)a->npix * ncand;
+        cand_rank_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fp, cand_rank, ncand);
+        count_launch();
+        CU_TRY(cudaGetLastError());
+    }
+    fp.cand_rank = cand_rank;
     fp.fb_list = fb; fp.fb_count = fb_count; fp.fb_capacity = (unsigned int)std::min<int64_t>(pl.rows, 0xffffffffLL);
     fp.counters = counters; fp.na_flag = na_flag;
     fp.tile2d = (env_int("RFSI_B200_TILE2D", 1) && loc_rows(L, a->npix)) ? 1 : 0;
@@ -2114,6 +2136,14 @@ int dev_fused(const rfsi_forest_t* f, const rfsi_fused_args_t* a, const FusedPla
         fp.leaf_ids = leaf_ids; fp.ld_ids = leaf_ids_ld(f->ntrees); fp.row_skip = skip;
         fp.ids_word = leaf_ids_word(im);
         CU_TRY(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int), st));
+        if (obs_rank) {   // ... and the observation ranks once per launch: [day][station][column]
+            fp.obs_rank = nullptr;
+            const long long n = (long long)nd * a->nobs * a->n_obs;
+            obs_rank_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fp, obs_rank);
+            count_launch();
+            CU_TRY(cudaGetLastError());
+            fp.obs_rank = obs_rank;
+        }
         const unsigned grid = (unsigned)(ntiles * nd);
         for (size_t c = 0; c + 1 < cb.size(); ++c) {  // one sweep of all tiles per L2-sized forest chunk
             fp.t_begin = cb[c]; fp.t_end = cb[c + 1];

@@ -22,6 +22,17 @@ namespace rfsi {
 
 constexpr int kMaxNObs = 64;
 constexpr int kMaxCov = 32;
+// Rank caches of the rank images (the tile in shared memory holds ranks, not values): a rank search per feature and
+// pixel-day is the prologue's whole cost (43 searches whose loads diverge across the warp in the distance columns,
+// profiles/r02_t_*), and most of them repeat.
+//   * cand_rank: candidate c of a pixel lands in distance column c - s, s = the candidates skipped before it (no
+//     observation that day, or the pixel's own station).  The rank of its distance in the columns c, c-1, c-2 is computed
+//     ONCE per pixel next to the geometry pass (cand_rank_kernel) and read back by every day of the batch; s > 2 searches.
+//   * obs_rank: the rank of station s's observation of day d in observation column j depends on no pixel at all:
+//     obs_rank_kernel fills [day][station][column] once per launch.
+//     A station without an observation that day has kObsRankNone in all its columns (a shifted rank ends in zeros).
+constexpr int kCandShifts = 3;
+constexpr uint32_t kObsRankNone = 0xFFFFFFFFu;
 
 struct FusedParams {
     LocSpec loc;                 // only the FALLBACK scan needs coordinates
@@ -32,6 +43,8 @@ struct FusedParams {
     const int32_t* cand_id;
     long long ld_cand;
     int KC;
+    const uint32_t* cand_rank;   // [KC][kCandShifts][ld_cand] shifted ranks of sqrt(cand_d2) in column c - s (nullable)
+    const uint32_t* obs_rank;    // [ndays][S][n_obs] shifted ranks of obs_z in column j (nullable)
     int exhaustive;              // 1 when the candidate list holds every station
     // stations
     const double2* st_xy;
@@ -124,6 +137,40 @@ __host__ __device__ constexpr int fused_min_blocks_q() {
 #endif
 }
 
+// ranks of every candidate's distance in the distance columns it can land in: one thread per (candidate, pixel) of
+// the chunk, pixels fastest (the lists are candidate-major), candidates beyond column n.obs - 1 + kCandShifts not launched
+__global__ void __launch_bounds__(256)
+cand_rank_kernel(const __grid_constant__ FusedParams a, uint32_t* __restrict__ out, int ncand)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.npix * ncand) return;
+    const int c = (int)(i / a.npix);
+    const long long p = i - (long long)c * a.npix;
+    if (a.cand_id[(long long)c * a.ld_cand + p] == kIdxNone) return;
+    const double dist = __dsqrt_rn(a.cand_d2[(long long)c * a.ld_cand + p]);
+#pragma unroll
+    for (int s = 0; s < kCandShifts; ++s) {
+        const int j = c - s;
+        if (j < 0 || j >= a.n_obs) continue;
+        const int rd = a.dist_row[j];
+        if (rd >= 0) out[(long long)(c * kCandShifts + s) * a.ld_cand + p] = rank_of(a.q, rd, dist) << a.q.rank_shift;
+    }
+}
+
+// ranks of every station's observation of every day of the launch in every observation column
+__global__ void __launch_bounds__(256)
+obs_rank_kernel(const __grid_constant__ FusedParams a, uint32_t* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)a.ndays * a.S * a.n_obs;
+    if (i >= n) return;
+    const int j = (int)(i % a.n_obs);
+    const long long ds = i / a.n_obs;                        // (day of the launch) * S + station
+    const double z = a.obs_z[(long long)a.day0 * a.S + ds];
+    const int ro = a.obs_row[j];
+    out[i] = (z != z) ? kObsRankNone : (ro >= 0 ? rank_of(a.q, ro, z) << a.q.rank_shift : 0u);
+}
+
 template <int P, int J, bool COUNT, bool FALLBACK, bool Q>
 __global__ void __launch_bounds__(P, Q ? fused_min_blocks_q<P, J>() : ((P * (20 + 6 * J) <= 32768) ? 2 : 1))
 fused_kernel(const __grid_constant__ FusedParams a)
@@ -162,19 +209,35 @@ fused_kernel(const __grid_constant__ FusedParams a)
     if (!FALLBACK) {
         if (active) {
             bool first_valid = true;
+            const bool ranked = Q && a.cand_rank != nullptr;   // the distances are only read where their ranks are not at hand
             for (int c = 0; c < a.KC; ++c) {
                 const int32_t id = a.cand_id[(long long)c * a.ld_cand + p];
                 if (id == kIdxNone) break;
-                const double z = __ldg(zday + id);
-                if (z != z) continue;  // no observation at this station today
-                const double d2 = a.cand_d2[(long long)c * a.ld_cand + p];
+                double z = 0.0;
+                uint32_t zr = 0u;
+                if (Q && a.obs_rank != nullptr) {   // the rank table says "no observation" itself: the value is not read at all
+                    zr = __ldg(a.obs_rank + ((long long)(d - a.day0) * a.S + id) * a.n_obs + taken);
+                    if (zr == kObsRankNone) continue;
+                } else {
+                    z = __ldg(zday + id);
+                    if (z != z) continue;  // no observation at this station today
+                }
                 if (first_valid) {
                     first_valid = false;
-                    if (a.rm_dupl && d2 == 0.0) continue;  // the pixel IS this station
+                    if (a.rm_dupl && a.cand_d2[(long long)c * a.ld_cand + p] == 0.0) continue;  // the pixel IS this station
                 }
                 const int rd = a.dist_row[taken], ro = a.obs_row[taken];
-                if (rd >= 0) put_feature<P, Q>(a, smem_raw, rd, __dsqrt_rn(d2));
-                if (ro >= 0) put_feature<P, Q>(a, smem_raw, ro, z);
+                if (rd >= 0) {
+                    if (ranked && c - taken < kCandShifts)
+                        (reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x)[rd * P] =
+                            a.cand_rank[(long long)(c * kCandShifts + (c - taken)) * a.ld_cand + p];
+                    else
+                        put_feature<P, Q>(a, smem_raw, rd, __dsqrt_rn(a.cand_d2[(long long)c * a.ld_cand + p]));
+                }
+                if (ro >= 0) {
+                    if (Q && a.obs_rank != nullptr) (reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x)[ro * P] = zr;
+                    else put_feature<P, Q>(a, smem_raw, ro, z);
+                }
                 if (++taken == a.n_obs) break;
             }
             if (taken < a.n_obs) {
