@@ -90,6 +90,39 @@ def test_fallback_path_when_candidate_lists_run_dry(monkeypatch):
     _check(got, ref)
 
 
+def test_rank_caches_do_not_change_a_bit(monkeypatch):
+    """The rank caches of the fused prologue (distance ranks of the candidates once per pixel, observation ranks
+    once per launch; csrc/fused.cuh) against the search per pixel-day: days with 0, 1, 2 and many skipped
+    candidates in front of a column (missing stations next to the pixel, the pixel's own station), a one-day
+    call (no candidate cache by design), more stations than pixels (no observation table by design)."""
+    case = synth.make_case("c1", ndays=4)
+    loc = case.locations()
+    d2 = ((loc[:, None, :] - case.obs_xy[None, :, :]) ** 2).sum(-1)
+    order = np.argsort(d2[case.npix // 2 + 17])
+    case.obs_z[1, order[0]] = np.nan                      # the nearest station of one pixel: shift 1 around it
+    case.obs_z[2, order[:2]] = np.nan                     # shift 2
+    case.obs_z[3, order[:5]] = np.nan                     # shift 5: beyond the cached shifts, searched
+    case.obs_z[3, ::4] = np.nan
+    flat = _forest_for(case)
+    model = rb.RangerForest(flat)
+
+    def run(**kw):
+        return rb.predict_fused(model, obs_xy=case.obs_xy, n_obs=case.n_obs, grid=case.grid, quantiles=PROBS, **kw)
+
+    ref = oracle.predict_fused(flat.as_dict(), case.feature_names, loc_xy=loc, obs_xy=case.obs_xy, obs_z=case.obs_z,
+                               n_obs=case.n_obs, quantiles=PROBS)
+    with_cache = run(obs_z=case.obs_z, npix=case.npix)
+    _check(with_cache, ref)
+    one_day = run(obs_z=case.obs_z[3:4], npix=case.npix)
+    np.testing.assert_array_equal(one_day["mean"][0], with_cache["mean"][3])
+    few = run(obs_z=case.obs_z, npix=40)                  # 200 stations, 40 pixels
+    np.testing.assert_array_equal(few["mean"], with_cache["mean"][:, :40])
+    monkeypatch.setenv("RFSI_B200_RANK_CACHE", "0")
+    without = run(obs_z=case.obs_z, npix=case.npix)
+    np.testing.assert_array_equal(without["mean"], with_cache["mean"])
+    np.testing.assert_array_equal(without["quantiles"], with_cache["quantiles"])
+
+
 def test_too_few_valid_stations_gives_na_and_warning():
     case = synth.make_case("c1", ndays=2)
     case.obs_z[1, 5:] = np.nan                                       # 5 valid stations, n.obs = 6

@@ -21,17 +21,17 @@ big = rng.uniform(0, 100, size=(1500, 2))
 rb.near_obs(rng.uniform(0, 100, size=(999, 2)), np.column_stack([big, rng.normal(size=1500)]), zcol=2, n_obs=5)
 zt = rng.normal(size=(3, 90)); zt[1, ::2] = np.nan; zt[2, 5:] = np.nan
 rb.near_obs_days(obs, zt, 6)
-# forest (both images), quantiles, terminal nodes
+# forest (every image), quantiles, terminal nodes
 X = rng.normal(size=(700, 9)); y = X[:, 0] + rng.normal(size=700)
 flat = grow.grow_forest(X, y, [f"f{i}" for i in range(9)], num_trees=21, quantreg=True)
 import os
-for compact in ("2", "1", "0"):
+for compact in ("3", "2", "1", "0"):
     os.environ["RFSI_B200_COMPACT"] = compact
     m = rb.RangerForest(flat)
     Xp = rng.normal(size=(1001, 9))
     rb.predict(m, Xp); rb.predict(m, Xp, type="quantiles"); rb.predict(m, Xp, type="terminalNodes")
     m.close()
-os.environ["RFSI_B200_COMPACT"] = "2"
+del os.environ["RFSI_B200_COMPACT"]       # default image (sector) with its rank caches
 # fused: raster grid + explicit, fallback (many missing), QRF + Int16, raster covariate, mask
 case = synth.make_case("c4", ndays=3)
 case.obs_z[1, rng.choice(87, 60, replace=False)] = np.nan

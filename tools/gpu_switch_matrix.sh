@@ -30,3 +30,6 @@ run RFSI_B200_J=12
 run RFSI_B200_P=128
 run RFSI_B200_KC_EXTRA=0
 run RFSI_B200_CHUNK_MB=1
+run RFSI_B200_RANK_CACHE=0
+run RFSI_B200_RANK_BUCKETS=64
+run RFSI_B200_RANK_BUCKETS=4096 RFSI_B200_RANK_CACHE=0
