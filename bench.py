@@ -720,8 +720,8 @@ def reference_configs(device):
     from rfsi_b200 import grow as grower, synth
     threads = oracle.hardware_threads()
 
-    def best(fn, reps=3):
-        for _ in range(4):                       # the GPU idles (and clocks down) while the CPU port runs: bring it back up
+    def best(fn, reps=7):
+        for _ in range(6):                       # the GPU idles (and clocks down) while the CPU port runs: bring it back up
             fn()
         ts = []
         for _ in range(reps):
@@ -731,7 +731,7 @@ def reference_configs(device):
     def once(fn):
         t0 = time.perf_counter(); fn(); return time.perf_counter() - t0
 
-    out = {"cpu_threads": threads, "timing": "GPU: best of 3 after four warm-up calls (the GPU clocks down while the CPU port runs); CPU port: one call",
+    out = {"cpu_threads": threads, "timing": "GPU: best of 7 after six warm-up calls (the GPU clocks down while the CPU port runs); CPU port: one call",
            "c1_simulation_R": [], "note": "DT = near.obs(250 000 grid cells, stations, n.obs = 25), PT = predict(250-tree forest, 250 000 x 50 "
                                           "data frame): simulation/simulation.R:190-215; published reference timings in BASELINE.md"}
     rng = np.random.default_rng(42)
