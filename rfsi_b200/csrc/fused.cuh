@@ -31,10 +31,7 @@ constexpr int kMaxCov = 32;
 //   * obs_rank: the rank of station s's observation of day d in observation column j depends on no pixel at all:
 //     obs_rank_kernel fills [day][station][column] once per launch.
 //     A station without an observation that day has kObsRankNone in all its columns (a shifted rank ends in zeros).
-#ifndef RFSI_CAND_SHIFTS
-#define RFSI_CAND_SHIFTS 3   // experiment builds: tools/build_variant.sh shifts2 -DRFSI_CAND_SHIFTS=2
-#endif
-constexpr int kCandShifts = RFSI_CAND_SHIFTS;
+constexpr int kCandShifts = 3;
 constexpr uint32_t kObsRankNone = 0xFFFFFFFFu;
 
 struct FusedParams {
