@@ -71,10 +71,10 @@ constexpr int kSWordLeafNo = 3, kSWordKey = 5, kSWordValue = 6;
 struct SectorView {
     const uint32_t* words;   // 8 per block
     const uint32_t* root;    // [T] block of each tree's root (sector_root_entry: flagged leaf block for a single-node tree)
-    // 32 (bytes per block) and P*4 (bytes between two features of the rank tile) as RUN-TIME values: given
-    // immediates, ptxas strength-reduces idx*32 + base into LEA + LEA.HI.X and feat*1024 + base into
-    // IMAD.SHL + LOP3 + IMAD.IADD; from the constant bank they stay one IMAD.WIDE / one IMAD (the walk is
-    // bound by integer issue slots: profiles/r02_sass_*.txt)
+    // P*4 (bytes between two features of the rank tile) as a RUN-TIME value: given the immediate, ptxas strength-reduces
+    // feat*1024 + base into IMAD.SHL + LOP3 + IMAD.IADD; from the constant bank it stays one IMAD (the walk is bound by
+    // integer issue slots: profiles/r02_sass_*.txt).  block_bytes (32) is only read by the host check: the device uses the
+    // immediate (sector_block), which measured faster than the run-time value.
     uint32_t block_bytes;
     uint32_t tile_stride;
 };
@@ -110,16 +110,17 @@ RFSI_SECT_DEV uint32_t sector_umax(uint32_t a, uint32_t b) { return a > b ? a : 
 
 inline uint32_t sector_node_word(uint32_t rank, uint32_t feat) { return ((~rank) << kSRankShift) | feat; }
 
-// address of block max(bb, 0): one signed max, one 32 x 32 -> 64-bit multiply-add
-// `words` is the image base held in an ordinary register pair (sector_base): with the base in uniform registers
-// ptxas splits the address into IMAD.WIDE + IADD3 + IADD3.X
+// address of block max(bb, 0): one signed max, then index * 32 + base as LEA + LEA.HI.X on a base held in ordinary registers.
+// Measured forms of this address (profiles/r02_ab_block_address.txt; SASS instructions per iteration of 8 chains):
+//   run-time block size, base in uniform registers (what ptxas makes of a kernel parameter): IMAD.WIDE + IADD3 + IADD3.X, 231;
+//   run-time block size, base in registers: IMAD.WIDE + IADD3 + IMAD.X, 230 (+1.9 %);  immediate 32, base in registers: 222 (+3.9 %).
+// The base gets into ordinary registers by adding word 0 of the idle block to it -- a zero that only the memory knows, so
+// the sum is a per-thread value as far as ptxas can tell (a `mov` through inline PTX is seen through).
 RFSI_SECT_DEV const uint32_t* sector_base(const SectorView& q) {
 #if defined(RFSI_SECTOR_HOST_CHECK)
     return q.words;
 #else
-    const uint32_t* out;
-    asm volatile("mov.b64 %0, %1;" : "=l"(out) : "l"(q.words));
-    return out;
+    return q.words + __ldg(q.words);
 #endif
 }
 RFSI_SECT_DEV const uint32_t* sector_block(const SectorView& q, const uint32_t* words, uint32_t bb) {
@@ -128,8 +129,7 @@ RFSI_SECT_DEV const uint32_t* sector_block(const SectorView& q, const uint32_t* 
                                              (size_t)((int32_t)bb > 0 ? bb : 0u) * q.block_bytes);
 #else
     const uint32_t* out;
-    asm("{\n\t.reg .s32 t;\n\tmax.s32 t, %1, 0;\n\tmad.wide.u32 %0, t, %3, %2;\n\t}"
-        : "=l"(out) : "r"(bb), "l"(words), "r"(q.block_bytes));
+    asm("{\n\t.reg .s32 t;\n\tmax.s32 t, %1, 0;\n\tmad.wide.u32 %0, t, 32, %2;\n\t}" : "=l"(out) : "r"(bb), "l"(words));
     return out;
 #endif
 }
