@@ -102,23 +102,27 @@ def main():
                 f.write(l + "\n")
     qk = [k for k in fn if "qrf_direct_kernelILi16E" in k]
     with open(OUT / "r02_sass_qrf_direct.txt", "w") as f:
-        f.write(f"# {qk[0] if qk else '?'}\n# DIRECT form of the quantile kernel with the one-pass selection (qrf.cuh: qrf_row_fast): key rows arrive by\n"
+        f.write(f"# {qk[0] if qk else '?'}\n# DIRECT form of the quantile kernel with the counting-sort selection (qrf.cuh: qrf_row_fast): key rows arrive by\n"
                 "# cp.async (LDGSTS), the histogram is 16 shared-memory atomics per lane (ATOMS.POPC.INC: lanes on the same bucket are\n"
-                "# combined), warp minimum / maximum / counts and the peel ranking are REDUX / CREDUX, the only global loads left are the\n"
-                "# skip bytes and the two dictionary look-ups per quantile.\n")
+                "# combined), the placement 16 returning atomics on the cursors (ATOMS.ADD) + 16 scattered stores, warp minimum / maximum /\n"
+                "# counts and the peel ranking are REDUX / CREDUX, the only global loads left are the skip bytes and the two dictionary\n"
+                "# look-ups per quantile.\n")
         if qk:
             Lq = fn[qk[0]]
             c = collections.Counter(opcode(l) for l in Lq)
             f.write("# whole kernel: " + ", ".join(f"{k} {v}" for k, v in c.most_common()
                                                      if re.match(r"LDG|LDGSTS|REDUX|CREDUX|ATOMS|LDS|STS|STG|VOTE|IMAD.HI|VIMNMX3", k)) + "\n#\n")
-            # the marking pass: the run of instructions between the first table look-up after the last ATOMS and the next REDUX
-            last_atoms = [i for i, l in enumerate(Lq) if "ATOMS" in l][15]   # the 16th: end of the fast path's histogram (converged-warp copy)
-            # straight-line code of the fast path after the histogram: scan, targets, marking pass, up to the first window's REDUX.SUM
-            stop = next(i for i in range(last_atoms, len(Lq)) if "REDUX.SUM" in Lq[i])
+            # straight-line code of the fast path after the histogram: warp scan, cursor table, placement (ATOMS.ADD + STS)
+            popc = [i for i, l in enumerate(Lq) if "ATOMS.POPC.INC" in l]
+            last_atoms = popc[15] if len(popc) > 15 else popc[-1]              # the 16th: end of the fast path's histogram
+            adds = [i for i in range(last_atoms, len(Lq)) if "ATOMS.ADD" in Lq[i]]
+            stop = adds[15] if len(adds) > 15 else adds[-1]
+            while stop + 1 < len(Lq) and not re.search(r"BRA|BSSY|BSYNC|WARPSYNC", Lq[stop + 1]) and stop - last_atoms < 200:
+                stop += 1
             body = Lq[last_atoms + 1:stop + 1]
             cm = collections.Counter(opcode(l) for l in body)
-            f.write(f"# after the histogram: warp scan of the 256 buckets, rank-interval table, the three target ranks and the marking pass\n"
-                    f"# (16 elements x 3 quantiles x [ISETP.GE, ISETP.LE.AND, predicated add]): {len(body)} instructions, straight line\n")
+            f.write(f"# after the histogram: warp scan of the 256 buckets, cursor table, and the placement of the row's 16 keys per lane\n"
+                    f"# (a returning ATOMS.ADD on the bucket's cursor and a scattered STS each): {len(body)} instructions, straight line\n")
             f.write("# mix: " + ", ".join(f"{k} {v}" for k, v in cm.most_common(12)) + "\n")
             f.write("\n".join(body) + "\n#\n# the peel loop of a window (one distinct value per iteration):\n")
             for a2, b2 in loops(Lq):
